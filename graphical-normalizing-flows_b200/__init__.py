@@ -1,0 +1,21 @@
+"""gnf_b200 — B200-native (sm_100a) hot path of Graphical Normalizing Flows.
+
+Drop-in for the reference's ``models`` package on the density-evaluation / training path:
+same class names, constructor signatures, attributes and state_dict keys; every forward /
+backward runs in hand-written CUDA kernels behind the C-ABI of ``include/gnf.h``
+(``libgnf_sm100.so``).  There is no CPU or eager-PyTorch fallback.
+"""
+from . import _lib, ops
+from .conditioners import (AutoregressiveConditioner, Conditioner, ConditionnalMADE, CouplingConditioner, CouplingMLP,
+                           DAGConditioner, DAGMLP, MADE, MaskedLinear)
+from .flow import (FCNormalizingFlow, MNIST_A_prior, NormalLogDensity, NormalizingFlow, NormalizingFlowStep,
+                   buildFCNormalizingFlow)
+from .normalizers import AffineNormalizer, ELUPlus, IntegrandNet, MonotonicNormalizer, Normalizer
+from . import dist
+
+__all__ = [
+    "AutoregressiveConditioner", "Conditioner", "ConditionnalMADE", "CouplingConditioner", "CouplingMLP", "DAGConditioner",
+    "DAGMLP", "MADE", "MaskedLinear", "FCNormalizingFlow", "MNIST_A_prior", "NormalLogDensity", "NormalizingFlow",
+    "NormalizingFlowStep", "buildFCNormalizingFlow", "AffineNormalizer", "ELUPlus", "IntegrandNet", "MonotonicNormalizer",
+    "Normalizer", "ops", "dist",
+]

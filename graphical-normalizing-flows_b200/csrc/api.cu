@@ -1,0 +1,46 @@
+// Error reporting and version entry points of the C-ABI.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace gnf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace gnf
+
+extern "C" {
+int gnf_version(void) { return 100; }
+const char* gnf_last_error(void) { return gnf::g_err; }
+int gnf_has_device_code(void) {
+#ifdef GNF_EMU
+  return 0;
+#else
+  return 1;
+#endif
+}
+}

@@ -1,0 +1,83 @@
+// Shared declarations for libgnf_sm100: platform switch (CUDA / host SIMT simulator), error
+// reporting behind the C-ABI, cp.async wrappers, Philox4x32-10.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#ifdef GNF_EMU
+#include "cpu_emu.h"
+#else
+#include <cuda_runtime.h>
+#define GNF_SMEM(T, name)                                              \
+  extern __shared__ __align__(1024) unsigned char _gnf_smem_raw[];     \
+  T* name = reinterpret_cast<T*>(_gnf_smem_raw)
+#define GNF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+#include "../../include/gnf.h"
+
+namespace gnf {
+
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+// Check the launch status of the kernels enqueued by an entry point.
+int check_launch(const char* what);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+#ifdef GNF_EMU
+static constexpr int kNumSMs = 4;
+#else
+static constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) 16-byte copies, global -> shared
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef GNF_EMU
+  memcpy(smem_dst, gmem_src, 16);
+#else
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef GNF_EMU
+  asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef GNF_EMU
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011); one call -> 4 x 32 random bits.
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+  static constexpr unsigned kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+  __host__ __device__ static inline uint4 gen(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi) {
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+    unsigned c0 = (unsigned)ctr_lo, c1 = (unsigned)(ctr_lo >> 32), c2 = (unsigned)ctr_hi, c3 = (unsigned)(ctr_hi >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      unsigned hi0 = (unsigned)(((uint64_t)kM0 * c0) >> 32), lo0 = kM0 * c0;
+      unsigned hi1 = (unsigned)(((uint64_t)kM1 * c2) >> 32), lo1 = kM1 * c2;
+      unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += kW0; k1 += kW1;
+    }
+    uint4 out;
+    out.x = c0; out.y = c1; out.z = c2; out.w = c3;
+    return out;
+  }
+  // 24-bit uniform in the open interval (0,1): never 0, so -log(-log(u)) stays finite.
+  __host__ __device__ static inline float u01(unsigned bits) { return ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+};
+
+}  // namespace gnf

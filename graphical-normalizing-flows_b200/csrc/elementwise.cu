@@ -1,0 +1,201 @@
+// K4: AffineNormalizer + log-det + base density (HBM-bound elementwise + per-row warp reductions),
+// and the small elementwise helpers of the host side.  One warp per sample row, lanes stride the
+// feature axis so every global access is coalesced; row sums by shuffle reduction.
+#include "common.cuh"
+
+namespace gnf {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kRowsPerBlock = 8;  // 8 warps = 256 threads
+
+__global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict__ x, float* __restrict__ h, int H, float* __restrict__ z,
+                                                          float* __restrict__ zrev, float* __restrict__ jac, float* __restrict__ logdet,
+                                                          uint8_t* __restrict__ cmask, int B, int d) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x * kRowsPerBlock + warp; b < B; b += gridDim.x * kRowsPerBlock) {
+    float acc = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const size_t e = (size_t)b * d + i;
+      float* hp = h + e * H;
+      const float h0 = hp[0], h1 = hp[1];
+      const float mu = fminf(fmaxf(h0, -5.f), 5.f);
+      const float ls = fminf(fmaxf(h1, -5.f), 2.f);
+      hp[0] = mu;  // clamp_ is in place on h (AffineNormalizer.py:10)
+      hp[1] = ls;
+      const float sg = expf(ls);
+      const float zv = fmaf(x[e], sg, mu);
+      z[e] = zv;
+      if (zrev) zrev[(size_t)b * d + (d - 1 - i)] = zv;
+      if (jac) jac[e] = sg;
+      if (cmask) cmask[e] = (uint8_t)((h0 >= -5.f && h0 <= 5.f ? 1 : 0) | (h1 >= -5.f && h1 <= 2.f ? 2 : 0));
+      acc += ls;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && logdet) logdet[b] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h, int H,
+                                                          const uint8_t* __restrict__ cmask, const float* __restrict__ gz,
+                                                          const float* __restrict__ gzrev, const float* __restrict__ gjac,
+                                                          const float* __restrict__ glogdet, float* __restrict__ gx, float* __restrict__ gh,
+                                                          int B, int d) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x * kRowsPerBlock + warp; b < B; b += gridDim.x * kRowsPerBlock) {
+    const float gl = glogdet ? glogdet[b] : 0.f;
+    const int n = d * H;
+    for (int idx = lane; idx < n; idx += 32) {
+      const int i = idx / H, k = idx % H;
+      const size_t e = (size_t)b * d + i;
+      float out = 0.f;
+      if (k < 2) {
+        float g = gz ? gz[e] : 0.f;
+        if (gzrev) g += gzrev[(size_t)b * d + (d - 1 - i)];
+        const uint8_t m = cmask[e];
+        if (k == 0) {
+          out = (m & 1) ? g : 0.f;
+          const float sg = expf(h[e * H + 1]);
+          gx[e] = g * sg;
+        } else {
+          const float sg = expf(h[e * H + 1]);
+          float t = g * x[e] * sg + gl;
+          if (gjac) t += gjac[e] * sg;
+          out = (m & 2) ? t : 0.f;
+        }
+      }
+      gh[e * H + k] = out;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) normal_ll_fwd_kernel(const float* __restrict__ z, const float* __restrict__ logdet, float* __restrict__ out, int B, int d) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float log2pi = 1.8378770664093453f;
+  for (int b = blockIdx.x * kRowsPerBlock + warp; b < B; b += gridDim.x * kRowsPerBlock) {
+    float acc = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float v = z[(size_t)b * d + i];
+      acc += log2pi + v * v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[b] = (logdet ? logdet[b] : 0.f) + (-.5f) * acc;
+  }
+}
+
+__global__ void normal_ll_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gout, float* __restrict__ gz, int B, int d) {
+  const size_t n = (size_t)B * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) gz[i] = -z[i] * gout[i / d];
+}
+
+__global__ void __launch_bounds__(256) logdet_fwd_kernel(const float* __restrict__ jac, float* __restrict__ logdet, int B, int d) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x * kRowsPerBlock + warp; b < B; b += gridDim.x * kRowsPerBlock) {
+    float acc = 0.f;
+    for (int i = lane; i < d; i += 32) acc += logf(jac[(size_t)b * d + i]);
+    acc = warp_sum(acc);
+    if (lane == 0) logdet[b] = acc;
+  }
+}
+
+__global__ void reverse_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int d) {
+  const size_t n = (size_t)B * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / d;
+    const int c = (int)(i % d);
+    dst[b * d + (d - 1 - c)] = src[i];
+  }
+}
+
+__global__ void broadcast_rows_kernel(const float* __restrict__ c, float* __restrict__ h, int B, int d, int indep, int H) {
+  const size_t per = (size_t)indep * H, n = (size_t)B * per;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / per, r = i % per;
+    h[b * (size_t)d * H + r] = c[r];
+  }
+}
+
+__global__ void axpy_kernel(float a, const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaf(a, x[i], y[i]);
+}
+
+static inline int row_blocks(int B) {
+  int b = ceil_div(B, kRowsPerBlock);
+  if (b > 16 * kNumSMs) b = 16 * kNumSMs;
+  return b < 1 ? 1 : b;
+}
+static inline int flat_blocks(size_t n) {
+  size_t b = (n + 255) / 256;
+  if (b > (size_t)16 * kNumSMs) b = (size_t)16 * kNumSMs;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace gnf
+
+using namespace gnf;
+
+extern "C" {
+
+int gnf_affine_fwd(const float* x, float* h, int H, float* z, float* zrev, float* jac, float* logdet, uint8_t* clampmask,
+                   int B, int d, gnf_stream_t stream) {
+  if (!x || !h || !z || B < 0 || d <= 0 || H < 2) return fail(GNF_ERR_INVALID, "gnf_affine_fwd: bad arguments (need H >= 2)");
+  if (B == 0) return 0;
+  GNF_LAUNCH(affine_fwd_kernel, row_blocks(B), 256, 0, (cudaStream_t)stream, x, h, H, z, zrev, jac, logdet, clampmask, B, d);
+  return check_launch("gnf_affine_fwd");
+}
+
+int gnf_affine_bwd(const float* x, const float* h, int H, const uint8_t* clampmask, const float* gz, const float* gzrev,
+                   const float* gjac, const float* glogdet, float* gx, float* gh, int B, int d, gnf_stream_t stream) {
+  if (!x || !h || !clampmask || !gx || !gh || B < 0 || d <= 0 || H < 2) return fail(GNF_ERR_INVALID, "gnf_affine_bwd: bad arguments");
+  if (B == 0) return 0;
+  GNF_LAUNCH(affine_bwd_kernel, row_blocks(B), 256, 0, (cudaStream_t)stream, x, h, H, clampmask, gz, gzrev, gjac, glogdet, gx, gh, B, d);
+  return check_launch("gnf_affine_bwd");
+}
+
+int gnf_normal_ll_fwd(const float* z, const float* logdet, float* out, int B, int d, gnf_stream_t stream) {
+  if (!z || !out || B < 0 || d <= 0) return fail(GNF_ERR_INVALID, "gnf_normal_ll_fwd: bad arguments");
+  if (B == 0) return 0;
+  GNF_LAUNCH(normal_ll_fwd_kernel, row_blocks(B), 256, 0, (cudaStream_t)stream, z, logdet, out, B, d);
+  return check_launch("gnf_normal_ll_fwd");
+}
+
+int gnf_normal_ll_bwd(const float* z, const float* gout, float* gz, int B, int d, gnf_stream_t stream) {
+  if (!z || !gout || !gz || B < 0 || d <= 0) return fail(GNF_ERR_INVALID, "gnf_normal_ll_bwd: bad arguments");
+  if (B == 0) return 0;
+  GNF_LAUNCH(normal_ll_bwd_kernel, flat_blocks((size_t)B * d), 256, 0, (cudaStream_t)stream, z, gout, gz, B, d);
+  return check_launch("gnf_normal_ll_bwd");
+}
+
+int gnf_logdet_fwd(const float* jac, float* logdet, int B, int d, gnf_stream_t stream) {
+  if (!jac || !logdet || B < 0 || d <= 0) return fail(GNF_ERR_INVALID, "gnf_logdet_fwd: bad arguments");
+  if (B == 0) return 0;
+  GNF_LAUNCH(logdet_fwd_kernel, row_blocks(B), 256, 0, (cudaStream_t)stream, jac, logdet, B, d);
+  return check_launch("gnf_logdet_fwd");
+}
+
+int gnf_reverse_cols(const float* src, float* dst, int B, int d, gnf_stream_t stream) {
+  if (!src || !dst || B < 0 || d <= 0) return fail(GNF_ERR_INVALID, "gnf_reverse_cols: bad arguments");
+  if (B == 0) return 0;
+  GNF_LAUNCH(reverse_cols_kernel, flat_blocks((size_t)B * d), 256, 0, (cudaStream_t)stream, src, dst, B, d);
+  return check_launch("gnf_reverse_cols");
+}
+
+int gnf_broadcast_rows(const float* constants, float* h, int B, int d, int indep, int H, gnf_stream_t stream) {
+  if (!constants || !h || B < 0 || d <= 0 || indep < 0 || indep > d || H <= 0) return fail(GNF_ERR_INVALID, "gnf_broadcast_rows: bad arguments");
+  if (B == 0 || indep == 0) return 0;
+  GNF_LAUNCH(broadcast_rows_kernel, flat_blocks((size_t)B * indep * H), 256, 0, (cudaStream_t)stream, constants, h, B, d, indep, H);
+  return check_launch("gnf_broadcast_rows");
+}
+
+int gnf_axpy(float a, const float* x, float* y, size_t n, gnf_stream_t stream) {
+  if (!x || !y) return fail(GNF_ERR_INVALID, "gnf_axpy: bad arguments");
+  if (n == 0) return 0;
+  GNF_LAUNCH(axpy_kernel, flat_blocks(n), 256, 0, (cudaStream_t)stream, a, x, y, n);
+  return check_launch("gnf_axpy");
+}
+
+}  // extern "C"

@@ -1,0 +1,548 @@
+"""torch.autograd.Function wrappers over the C-ABI (include/gnf.h).
+
+Operator layer of the drop-in boundary: the same role the reference gives to
+``UMNN.NeuralIntegral.apply`` — custom forward/backward pairs whose arithmetic lives in the
+hand-written sm_100a kernels.  Tensors, workspaces and saved-for-backward buffers are torch
+allocations handed to the library as raw device pointers on torch's current stream.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import check, lib, ptr, require, stream_ptr
+
+_LAUNCHES = 0  # number of C-ABI compute calls issued (bench.py reports it as gpu_launches evidence)
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def launch_count():
+    return _LAUNCHES
+
+
+def _contig(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# K4: affine normalizer, base density
+# ----------------------------------------------------------------------------------------------
+class AffineFn(torch.autograd.Function):
+    """AffineNormalizer.forward + log(jac).sum(1) (AffineNormalizer.py:9-12, NormalizingFlow.py:70).
+
+    Returns (z, jac, logdet, zrev).  Like the reference's clamp_, the clamped mu / log-sigma are written
+    back into h's storage; h's autograd version counter is bumped so that an upstream op that saved h for
+    its own backward fails loudly instead of silently using modified values."""
+
+    @staticmethod
+    def forward(ctx, x, h, want_rev):
+        require(x, "x"), require(h, "h")
+        B, d = x.shape
+        H = h.shape[2]
+        if h.shape[0] != B or h.shape[1] != d or H < 2:
+            raise ValueError(f"AffineNormalizer: h must be [B, d, >=2], got {tuple(h.shape)} for x {tuple(x.shape)}")
+        z = torch.empty_like(x)
+        jac = torch.empty_like(x)
+        zrev = torch.empty_like(x) if want_rev else None
+        logdet = torch.empty(B, device=x.device, dtype=x.dtype)
+        mask = torch.empty(B, d, device=x.device, dtype=torch.uint8)
+        check(lib().gnf_affine_fwd(ptr(x), ptr(h), H, ptr(z), ptr(zrev), ptr(jac), ptr(logdet), ptr(mask), B, d, stream_ptr()))
+        _count()
+        torch.autograd.graph.increment_version(h)
+        ctx.save_for_backward(x, h, mask)
+        ctx.want_rev = want_rev
+        ctx.set_materialize_grads(False)
+        if zrev is None:
+            zrev = x.new_empty(0)
+            ctx.mark_non_differentiable(zrev)
+        return z, jac, logdet, zrev
+
+    @staticmethod
+    def backward(ctx, gz, gjac, glogdet, gzrev):
+        x, h, mask = ctx.saved_tensors
+        B, d = x.shape
+        H = h.shape[2]
+        gz = _contig(gz) if gz is not None else None
+        gjac = _contig(gjac) if gjac is not None else None
+        glogdet = _contig(glogdet) if glogdet is not None else None
+        gzrev = _contig(gzrev) if (gzrev is not None and ctx.want_rev) else None
+        gx = torch.empty_like(x)
+        gh = torch.empty_like(h)
+        check(lib().gnf_affine_bwd(ptr(x), ptr(h), H, ptr(mask), ptr(gz), ptr(gzrev), ptr(gjac), ptr(glogdet), ptr(gx), ptr(gh),
+                                   B, d, stream_ptr()))
+        _count()
+        return gx, gh, None
+
+
+class NormalLLFn(torch.autograd.Function):
+    """out[b] = (logdet[b]) - 0.5 * sum_i (log 2pi + z^2)  (NormalizingFlowFactories.py:15-16)."""
+
+    @staticmethod
+    def forward(ctx, z, logdet):
+        require(z, "z")
+        B, d = z.shape
+        if logdet is not None:
+            require(logdet, "logdet")
+        out = torch.empty(B, device=z.device, dtype=z.dtype)
+        check(lib().gnf_normal_ll_fwd(ptr(z), ptr(logdet), ptr(out), B, d, stream_ptr()))
+        _count()
+        ctx.save_for_backward(z)
+        ctx.has_logdet = logdet is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (z,) = ctx.saved_tensors
+        gout = _contig(gout)
+        gz = torch.empty_like(z)
+        check(lib().gnf_normal_ll_bwd(ptr(z), ptr(gout), ptr(gz), z.shape[0], z.shape[1], stream_ptr()))
+        _count()
+        return gz, (gout if ctx.has_logdet else None)
+
+
+def reverse_cols(z):
+    require(z, "z")
+    out = torch.empty_like(z)
+    check(lib().gnf_reverse_cols(ptr(z), ptr(out), z.shape[0], z.shape[1], stream_ptr()))
+    _count()
+    return out
+
+
+class ReverseColsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        return reverse_cols(z)
+
+    @staticmethod
+    def backward(ctx, g):
+        return reverse_cols(_contig(g))
+
+
+# ----------------------------------------------------------------------------------------------
+# K2: acyclicity term
+# ----------------------------------------------------------------------------------------------
+def _pt_workspace(d, device):
+    n = lib().gnf_power_trace_workspace_bytes(d)
+    return torch.empty((n + 3) // 4, device=device, dtype=torch.float32), n
+
+
+class PowerTraceFn(torch.autograd.Function):
+    """tr((I + alpha A∘A)^p) - d  (DAGConditioner.get_power_trace, DAGConditioner.py:176-194)."""
+
+    @staticmethod
+    def forward(ctx, A, alpha, p):
+        require(A, "A")
+        d = A.shape[0]
+        t = torch.empty((), device=A.device, dtype=A.dtype)
+        ws, n = _pt_workspace(d, A.device)
+        check(lib().gnf_power_trace_fwd(ptr(A), d, float(alpha), int(p), ptr(t), ptr(ws), n, stream_ptr()))
+        _count()
+        ctx.save_for_backward(A)
+        ctx.alpha, ctx.p = float(alpha), int(p)
+        return t
+
+    @staticmethod
+    def backward(ctx, gt):
+        (A,) = ctx.saved_tensors
+        d = A.shape[0]
+        gt = _contig(gt)
+        dA = torch.empty_like(A)
+        ws, n = _pt_workspace(d, A.device)
+        check(lib().gnf_power_trace_bwd(ptr(A), d, ctx.alpha, ctx.p, ptr(gt), ptr(dA), ptr(ws), n, stream_ptr()))
+        _count()
+        return dA, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# Conditioner MLP engine
+# ----------------------------------------------------------------------------------------------
+def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=None):
+    """Y = act(X[:, :K] @ W^T + bias).  X may be a row-strided view described by (ldx, K)."""
+    M = X.shape[0]
+    N = W.shape[0]
+    K = W.shape[1] if K is None else K
+    ldx = X.stride(0) if ldx is None else ldx
+    if out is None:
+        out = torch.empty(M, N, device=X.device, dtype=X.dtype)
+        ldy = N
+    check(lib().gnf_linear_fwd(ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
+                               stream_ptr()))
+    _count()
+    return out
+
+
+def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
+    N, K = W.shape
+    if out is None:
+        out = torch.empty(M, K, device=dY.device, dtype=dY.dtype)
+        lddx = K
+    check(lib().gnf_linear_dgrad(ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
+                                 ptr(out), lddx, M, N, K, stream_ptr()))
+    _count()
+    return out
+
+
+def linear_wgrad(dY, lddy, X, ldx, M, N, K):
+    dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
+    check(lib().gnf_linear_wgrad(ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr()))
+    _count()
+    return dW
+
+
+def colsum(Y, ldy, M, N, period=1):
+    out = torch.empty(period, N, device=Y.device, dtype=Y.dtype)
+    check(lib().gnf_colsum(ptr(Y), ldy, ptr(out), M, N, period, stream_ptr()))
+    _count()
+    return out
+
+
+def _mlp_backward(gout, ldg, acts, x_in, ldx, K0, weights, need_dx, first_layer_done=False):
+    """Shared backward of a Linear/ReLU stack.
+
+    gout: cotangent of the last layer's (un-activated) output [M, N_last] with row stride ldg.
+    acts: ReLU outputs of layers 0..n-2.  Returns (dW list, db list, d_input or None, delta_first)
+    where delta_first is the cotangent of layer 0's pre-activation (already ReLU-masked)."""
+    n = len(weights)
+    M = gout.shape[0]
+    dWs, dbs = [None] * n, [None] * n
+    delta, ldd = gout, ldg
+    for l in range(n - 1, -1, -1):
+        W = weights[l]
+        N, K = W.shape
+        if l == 0 and first_layer_done:
+            break
+        dbs[l] = colsum(delta, ldd, M, N).view(N)
+        if l > 0:
+            a_prev = acts[l - 1]
+            dWs[l] = linear_wgrad(delta, ldd, a_prev, a_prev.stride(0), M, N, K)
+            delta = linear_dgrad(delta, ldd, W, a_prev, M)
+            ldd = K
+        else:
+            dWs[0] = linear_wgrad(delta, ldd, x_in, ldx, M, N, K0)
+            dx = linear_dgrad(delta, ldd, W, None, M) if need_dx else None
+            return dWs, dbs, dx, delta
+    return dWs, dbs, None, delta
+
+
+class MlpFn(torch.autograd.Function):
+    """Plain nn.Linear/ReLU stack on the MLP engine (CouplingMLP, CouplingConditioner.py:6-18; MADE with
+    pre-masked weights).  forward(x2d, out_or_None, ldy, *params) with params = W0, b0, W1, b1, ..."""
+
+    @staticmethod
+    def forward(ctx, x, K0, *params):
+        require(x, "x")
+        weights = [require(_contig(p), "weight") for p in params[0::2]]
+        biases = [require(_contig(p), "bias") for p in params[1::2]]
+        n = len(weights)
+        if weights[0].shape[1] != K0 or x.shape[1] < K0:
+            raise ValueError(f"MLP: first layer expects {weights[0].shape[1]} inputs, got {K0} (x has {x.shape[1]} columns)")
+        acts = []
+        cur, ldx, K = x, x.stride(0), K0
+        for l in range(n):
+            cur = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), K=K, ldx=ldx)
+            ldx, K = cur.stride(0), cur.shape[1]
+            if l < n - 1:
+                acts.append(cur)
+        ctx.save_for_backward(x, *weights, *acts)
+        ctx.n, ctx.K0 = n, K0
+        ctx.need_dx = x.requires_grad
+        return cur
+
+    @staticmethod
+    def backward(ctx, gout):
+        saved = ctx.saved_tensors
+        n = ctx.n
+        x, weights, acts = saved[0], list(saved[1:1 + n]), list(saved[1 + n:])
+        gout = _contig(gout)
+        dWs, dbs, dx, _ = _mlp_backward(gout, gout.stride(0), acts, x, x.stride(0), ctx.K0, weights, ctx.need_dx)
+        gx = None
+        if dx is not None:
+            if x.shape[1] == ctx.K0:
+                gx = dx
+            else:
+                gx = torch.zeros_like(x)
+                gx[:, :ctx.K0] = dx
+        out = [gx, None]
+        for l in range(n):
+            out += [dWs[l], dbs[l]]
+        return tuple(out)
+
+
+def pack_rows(W, mask=None, perm=None, R=None):
+    R = W.shape[0] if R is None else R
+    K = W.shape[1]
+    out = torch.empty(R, K, device=W.device, dtype=W.dtype)
+    check(lib().gnf_pack_rows(ptr(W), ptr(mask), ptr(perm), ptr(out), R, K, stream_ptr()))
+    _count()
+    return out
+
+
+class PackRowsFn(torch.autograd.Function):
+    """out[r,:] = (mask*W)[perm[r],:] — MaskedLinear's mask*weight (AutoregressiveConditioner.py:24-25) fused
+    with the row permutation that makes MADE's output land directly in [B, d, H] order (:108-109)."""
+
+    @staticmethod
+    def forward(ctx, W, mask, perm):
+        W = require(_contig(W), "W")
+        ctx.mask, ctx.perm, ctx.shape = mask, perm, W.shape
+        return pack_rows(W, mask, perm, R=(perm.numel() if perm is not None else None))
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _contig(g)
+        N, K = ctx.shape
+        dW = torch.empty(N, K, device=g.device, dtype=g.dtype)
+        check(lib().gnf_unpack_rows(ptr(g), ptr(ctx.mask), ptr(ctx.perm), ptr(dW), g.shape[0], N, K, stream_ptr()))
+        _count()
+        return dW, None, None
+
+
+class PackVecFn(torch.autograd.Function):
+    """out[r] = b[perm[r]]."""
+
+    @staticmethod
+    def forward(ctx, b, perm):
+        b = require(_contig(b), "bias")
+        ctx.perm, ctx.n = perm, b.numel()
+        return pack_rows(b.view(-1, 1), None, perm, R=perm.numel()).view(-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _contig(g)
+        db = torch.empty(ctx.n, device=g.device, dtype=g.dtype)
+        check(lib().gnf_unpack_vec(ptr(g), ptr(ctx.perm), ptr(db), g.numel(), ctx.n, stream_ptr()))
+        _count()
+        return db, None
+
+
+def broadcast_rows(constants, h, indep):
+    B, d, H = h.shape
+    check(lib().gnf_broadcast_rows(ptr(constants), ptr(h), B, d, indep, H, stream_ptr()))
+    _count()
+
+
+# ----------------------------------------------------------------------------------------------
+# K1: DAG conditioner
+# ----------------------------------------------------------------------------------------------
+class GateSpec:
+    """Host description of DAGConditioner's gating branch (DAGConditioner.py:126-153)."""
+
+    def __init__(self, mode, imp, h_thresh=0., T=1., seed=0, offset=0, noise=None):
+        self.mode, self.imp, self.h_thresh, self.T = mode, imp, float(h_thresh), float(T)
+        self.seed, self.offset, self.noise = int(seed), int(offset), noise
+
+    def c_struct(self):
+        g = L.GateT()
+        g.mode, g.temperature, g.seed, g.offset = self.mode, self.T, self.seed, self.offset
+        n = self.noise or ()
+        g.noise1 = n[0].data_ptr() if len(n) > 0 else None
+        g.noise2 = n[1].data_ptr() if len(n) > 1 else None
+        return g
+
+
+def dag_dump_noise(gate, B, d, device):
+    """Materialise the in-kernel Philox draws of a GateSpec (parity / debugging hook)."""
+    n1 = torch.empty(B, d, d, device=device, dtype=torch.float32)
+    n2 = torch.empty(B, d, d, device=device, dtype=torch.float32) if gate.mode == L.GATE_GUMBEL else None
+    g = GateSpec(gate.mode, gate.imp, gate.h_thresh, gate.T, gate.seed, gate.offset, None).c_struct()
+    check(lib().gnf_dag_dump_noise(C.byref(g), ptr(n1), ptr(n2), B, d, stream_ptr()))
+    _count()
+    return (n1, n2) if n2 is not None else (n1,)
+
+
+class DagMlpFn(torch.autograd.Function):
+    """DAGConditioner.forward (DAGConditioner.py:126-169): gate/threshold of A, masked expansion of x,
+    optional one-hot encoding, embedding MLP — with the [B,d,d] masked tensor generated inside the first
+    GEMM's operand loader.  forward(x, A, gate, hot, *params) -> h [B, d, H]."""
+
+    @staticmethod
+    def forward(ctx, x, A, gate, hot, *params):
+        require(x, "x")
+        A = require(_contig(A), "A")
+        weights = [require(_contig(p), "weight") for p in params[0::2]]
+        biases = [require(_contig(p), "bias") for p in params[1::2]]
+        B, d = x.shape
+        n = len(weights)
+        if weights[0].shape[1] != (2 * d if hot else d):
+            raise ValueError(f"DAGConditioner: first layer expects {weights[0].shape[1]} inputs, d={d}, hot_encoding={hot}")
+        for t in (gate.noise or ()):
+            require(t, "noise")
+            if tuple(t.shape) != (B, d, d):
+                raise ValueError("replayed gate noise must be [B, d, d]")
+        st = stream_ptr()
+        P = torch.empty_like(A)
+        dPdA = torch.empty_like(A)
+        check(lib().gnf_dag_importance(ptr(A), d, gate.imp, gate.h_thresh, ptr(P), ptr(dPdA), st))
+        N1 = weights[0].shape[0]
+        T = torch.empty(d if hot else 1, N1, device=x.device, dtype=x.dtype)
+        check(lib().gnf_dag_bias_table(ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st))
+        g = gate.c_struct()
+        y = torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
+        check(lib().gnf_dag_l1_fwd(ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
+                                   ptr(y), N1, B, d, N1, int(n > 1), st))
+        _count(3)
+        acts = []
+        cur = y
+        for l in range(1, n):
+            acts.append(cur)
+            out = None
+            if l == n - 1:   # final layer writes straight into the [B, d, H] result (no view of an internal tensor)
+                out = torch.empty(B, d, weights[l].shape[0], device=x.device, dtype=x.dtype)
+            cur = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), out=out, ldy=weights[l].shape[0])
+        ctx.save_for_backward(x, A, P, dPdA, *weights, *acts)
+        ctx.gate, ctx.hot, ctx.n = gate, hot, n
+        if n == 1:
+            cur = cur.view(B, d, -1).clone()
+        return cur
+
+    @staticmethod
+    def backward(ctx, gh):
+        saved = ctx.saved_tensors
+        n, hot, gate = ctx.n, ctx.hot, ctx.gate
+        needs = ctx.needs_input_grad
+        x, A, P, dPdA = saved[:4]
+        weights, acts = list(saved[4:4 + n]), list(saved[4 + n:])
+        B, d = x.shape
+        M = B * d
+        gh = _contig(gh).view(M, -1)
+        st = stream_ptr()
+        dWs, dbs, _, delta = _mlp_backward(gh, gh.stride(0), acts, None, 0, 0, weights, False, first_layer_done=True)
+        W1 = weights[0]
+        N1 = W1.shape[0]
+        g = gate.c_struct()
+        dW1 = torch.empty_like(W1)
+        check(lib().gnf_dag_l1_wgrad(ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st))
+        dT = colsum(delta, delta.stride(0), M, N1, period=(d if hot else 1))
+        db1 = torch.empty(N1, device=x.device, dtype=x.dtype)
+        check(lib().gnf_dag_bias_table_bwd(ptr(dT), ptr(dW1), W1.stride(0), ptr(db1), d, N1, int(hot), st))
+        _count(2)
+        dWs[0], dbs[0] = dW1, db1
+        dx = dA = None
+        if needs[0] or needs[1]:
+            dx = torch.empty_like(x)
+            dP = torch.empty_like(A)
+            check(lib().gnf_dag_l1_dgrad(ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx),
+                                         ptr(dP), B, d, N1, st))
+            dA = torch.empty_like(A)
+            check(lib().gnf_dag_finish_dA(ptr(dP), ptr(dPdA), ptr(dA), d, 0, st))
+            _count(2)
+        out = [dx if needs[0] else None, dA if needs[1] else None, None, None]
+        for l in range(n):
+            out += [dWs[l], dbs[l]]
+        return tuple(out)
+
+
+# ----------------------------------------------------------------------------------------------
+# K3: UMNN integral
+# ----------------------------------------------------------------------------------------------
+_CC_CACHE = {}
+
+
+def cc_weights(nb_steps, device):
+    """Clenshaw-Curtis weights / nodes, float64 numpy -> fp32, exactly as UMNN's compute_cc_weights
+    (SURVEY.md App. B); cached per (S, device)."""
+    key = (int(nb_steps), str(device))
+    if key not in _CC_CACHE:
+        S = int(nb_steps)
+        k = np.arange(S + 1, dtype=np.float64)
+        lam = np.cos(np.outer(k, k) * math.pi / S)
+        lam[:, 0] = .5
+        lam[:, -1] = .5 * lam[:, -1]
+        lam = lam * 2 / S
+        W = np.zeros(S + 1, dtype=np.float64)
+        even = np.arange(0, S + 1, 2)
+        W[even] = 2. / (1. - even.astype(np.float64) ** 2)
+        W[0] = 1.
+        w = torch.tensor(lam.T @ W).float().to(device)
+        t = torch.tensor(np.cos(k * math.pi / S)).float().to(device)
+        _CC_CACHE[key] = (w, t)
+    return _CC_CACHE[key]
+
+
+def _mlp_struct(weights, biases):
+    n = len(weights)
+    if n > L.GNF_MAX_LAYERS:
+        raise ValueError(f"integrand network deeper than {L.GNF_MAX_LAYERS} linear layers is not supported")
+    m = L.MlpT()
+    m.n_layers = n
+    m.dims[0] = weights[0].shape[1]
+    for l in range(n):
+        m.dims[l + 1] = weights[l].shape[0]
+        m.W[l] = weights[l].data_ptr()
+        m.b[l] = biases[l].data_ptr()
+    return m
+
+
+class UmnnFn(torch.autograd.Function):
+    """MonotonicNormalizer.forward (MonotonicNormalizer.py:51-66) = UMNN (Parallel)NeuralIntegral + h[...,0]
+    and the Jacobian evaluation, fused.  forward(x [B,d], h [B,d,E], S, want_rev, *params)
+    -> (z, jac, logdet, zrev)."""
+
+    @staticmethod
+    def forward(ctx, x, h, S, want_rev, *params):
+        require(x, "x"), require(h, "h")
+        weights = [require(_contig(p), "weight") for p in params[0::2]]
+        biases = [require(_contig(p), "bias") for p in params[1::2]]
+        B, d = x.shape
+        E = h.shape[2]
+        if weights[0].shape[1] != 1 + E:
+            raise ValueError(f"integrand expects {weights[0].shape[1] - 1} conditioning features, h has {E}")
+        R = B * d
+        net = _mlp_struct(weights, biases)
+        nbytes = lib().gnf_umnn_workspace_bytes(C.byref(net))
+        if nbytes == 0:
+            raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
+        ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+        ccw, ccn = cc_weights(S, x.device)
+        z = torch.empty_like(x)
+        jac = torch.empty_like(x)
+        zrev = torch.empty_like(x) if want_rev else None
+        logdet = torch.empty(B, device=x.device, dtype=x.dtype)
+        check(lib().gnf_umnn_fwd(ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac), ptr(logdet),
+                                 R, d, ptr(ws), nbytes, stream_ptr()))
+        _count(2)
+        ctx.save_for_backward(x, h, jac, *weights, *biases)
+        ctx.S, ctx.want_rev, ctx.n = int(S), want_rev, len(weights)
+        ctx.set_materialize_grads(False)
+        if zrev is None:
+            zrev = x.new_empty(0)
+            ctx.mark_non_differentiable(zrev)
+        return z, jac, logdet, zrev
+
+    @staticmethod
+    def backward(ctx, gz, gjac, glogdet, gzrev):
+        saved = ctx.saved_tensors
+        n = ctx.n
+        x, h, jac = saved[:3]
+        weights, biases = list(saved[3:3 + n]), list(saved[3 + n:])
+        B, d = x.shape
+        R = B * d
+        net = _mlp_struct(weights, biases)
+        nbytes = lib().gnf_umnn_workspace_bytes(C.byref(net))
+        ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+        ccw, ccn = cc_weights(ctx.S, x.device)
+        gz = _contig(gz) if gz is not None else None
+        gjac = _contig(gjac) if gjac is not None else None
+        glogdet = _contig(glogdet) if glogdet is not None else None
+        gzrev = _contig(gzrev) if (gzrev is not None and ctx.want_rev) else None
+        dx = torch.empty_like(x)
+        dh = torch.empty_like(h)
+        grads = L.MlpGradT()
+        dWs = [torch.empty_like(w) for w in weights]
+        dbs = [torch.empty_like(b) for b in biases]
+        for l in range(n):
+            grads.dW[l] = dWs[l].data_ptr()
+            grads.db[l] = dbs[l].data_ptr()
+        check(lib().gnf_umnn_bwd(ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev), ptr(gjac),
+                                 ptr(glogdet), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr()))
+        _count(2)
+        out = [dx, dh, None, None]
+        for l in range(n):
+            out += [dWs[l], dbs[l]]
+        return tuple(out)

@@ -1,0 +1,207 @@
+/* libgnf_sm100 — C-ABI of the B200-native Graphical-Normalizing-Flows hot path.
+ *
+ * One shared library (nvcc -gencode arch=compute_100a,code=sm_100a), loaded with ctypes by the
+ * Python package.  The entry points replace, one for one, the device work that the
+ * reference's plugin hierarchy launches through ATen / UMNN on its hot path; the reference
+ * file:line each one stands in for is cited on the declaration (paths relative to the
+ * reference checkout).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 unless stated, row-major, caller-owned;
+ *    the library never allocates or frees device memory and keeps no pointer after return;
+ *  - scratch space is passed in by the caller (gnf_*_workspace_bytes tells how much);
+ *  - all entry points are asynchronous on `stream` (a cudaStream_t) and re-entrant;
+ *  - return 0 on success, non-zero on error (a cudaError_t value, or GNF_ERR_*);
+ *    gnf_last_error() gives a thread-local message; an unsupported shape / mode is an
+ *    error, never a silent fallback.
+ */
+#ifndef GNF_H_
+#define GNF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gnf_stream_t; /* cudaStream_t */
+
+#define GNF_ERR_INVALID 1001     /* bad argument */
+#define GNF_ERR_UNSUPPORTED 1002 /* shape or mode outside what the kernels cover */
+#define GNF_ERR_WORKSPACE 1003   /* workspace too small */
+
+#define GNF_MAX_LAYERS 8
+
+int gnf_version(void);
+const char* gnf_last_error(void);
+/* 1 when this build contains device code (always, for the product library). */
+int gnf_has_device_code(void);
+
+/* --------------------------------------------------------------------------------------------
+ * K4 — AffineNormalizer + log-det + base density
+ * ------------------------------------------------------------------------------------------ */
+
+/* AffineNormalizer.forward (models/Normalizers/AffineNormalizer.py:9-12) fused with
+ * NormalizingFlowStep.forward's log(jac).sum(1) (models/NormalizingFlow.py:70).
+ *   mu = clamp(h[b,i,0],-5,5); ls = clamp(h[b,i,1],-5,2)  (written back into h: in-place
+ *   semantics of clamp_);  z = x*exp(ls)+mu;  jac = exp(ls);  logdet[b] = sum_i ls.
+ * h: [B,d,H] (H >= 2).  clampmask: [B,d] uint8, bit0 = h0 was inside [-5,5], bit1 = h1 inside
+ * [-5,2] (saved for backward).  zrev (nullable): z with reversed columns
+ * (FCNormalizingFlow.forward's z[:, inv_idx], NormalizingFlow.py:120,123).  jac nullable. */
+int gnf_affine_fwd(const float* x, float* h, int H, float* z, float* zrev, float* jac, float* logdet,
+                   uint8_t* clampmask, int B, int d, gnf_stream_t stream);
+
+/* Backward of the above.  gz, gzrev, gjac, glogdet are cotangents (each nullable);
+ * gx: [B,d]; gh: [B,d,H] fully written (zeros beyond channel 1). */
+int gnf_affine_bwd(const float* x, const float* h, int H, const uint8_t* clampmask, const float* gz,
+                   const float* gzrev, const float* gjac, const float* glogdet, float* gx, float* gh, int B,
+                   int d, gnf_stream_t stream);
+
+/* NormalLogDensity.forward (models/NormalizingFlowFactories.py:15-16), optionally fused with the
+ * `+ jac` of the log-likelihood (UCIExperiments.py:160): out[b] = (logdet? logdet[b]:0) - 0.5*sum_i(log(2pi)+z^2). */
+int gnf_normal_ll_fwd(const float* z, const float* logdet, float* out, int B, int d, gnf_stream_t stream);
+/* gz[b,i] = -z[b,i]*gout[b]. */
+int gnf_normal_ll_bwd(const float* z, const float* gout, float* gz, int B, int d, gnf_stream_t stream);
+
+/* log(jac).sum(1) for a jac [B,d] produced elsewhere (NormalizingFlow.py:70). */
+int gnf_logdet_fwd(const float* jac, float* logdet, int B, int d, gnf_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * K2 — acyclicity term  tr((I + alpha A∘A)^p) - d
+ * (DAGConditioner.get_power_trace, models/Conditionners/DAGConditioner.py:176-194)
+ * ------------------------------------------------------------------------------------------ */
+size_t gnf_power_trace_workspace_bytes(int d);
+/* t_out: device scalar.  Multiplication order follows torch.matrix_power. */
+int gnf_power_trace_fwd(const float* A, int d, float alpha, int p, float* t_out, void* work, size_t work_bytes,
+                        gnf_stream_t stream);
+/* dA = gt * 2*alpha*p * A ∘ ((I+alpha A∘A)^(p-1))^T ;  gt: device scalar. */
+int gnf_power_trace_bwd(const float* A, int d, float alpha, int p, const float* gt, float* dA, void* work,
+                        size_t work_bytes, gnf_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Conditioner MLP engine (K1 layers 2..L, K5, K6): nn.Linear / ReLU stacks
+ * (DAGConditioner.py:7-20, AutoregressiveConditioner.py:24-25, CouplingConditioner.py:6-18)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Y[m,n] = act( sum_k X[m,k] W[n,k] + bias[(m % bias_period), n] ),  act = relu or identity.
+ * bias: [bias_period, N] (bias_period = 1 -> ordinary bias). */
+int gnf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, int bias_period, float* Y,
+                   int ldy, int M, int N, int K, int relu, gnf_stream_t stream);
+/* dX[m,k] = (sum_n dY[m,n] W[n,k]) * (act? act[m,k] > 0 : 1)   (act = the ReLU output feeding this layer). */
+int gnf_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const float* act, int ldact, float* dX,
+                     int lddx, int M, int N, int K, gnf_stream_t stream);
+/* dW[n,k] = sum_m dY[m,n] X[m,k]  (overwrites dW). */
+int gnf_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
+                     gnf_stream_t stream);
+/* out[p,n] = sum_{m % period == p} Y[m,n]  (bias gradients; one-hot column gradients). */
+int gnf_colsum(const float* Y, int ldy, float* out, int M, int N, int period, gnf_stream_t stream);
+/* dY[m,n] *= (act[m,n] > 0)  — ReLU backward for a cotangent produced outside the engine. */
+int gnf_relu_mask(float* dY, int lddy, const float* act, int ldact, int M, int N, gnf_stream_t stream);
+
+/* MaskedLinear's `mask * weight` (AutoregressiveConditioner.py:24-25) fused with the output-row
+ * permutation that turns MADE's view(B,out,d).permute(0,2,1) (:108-109) into a plain row-major
+ * h[b,i,k]:  out[r,k] = W[perm[r],k] * mask[perm[r],k]   (mask, perm nullable; perm int32 [R]). */
+int gnf_pack_rows(const float* W, const float* mask, const int32_t* perm, float* out, int R, int K,
+                  gnf_stream_t stream);
+/* Scatter for the gradient: dW[perm[r],k] = dWp[r,k]*mask[perm[r],k]; dW [N,K] is zero-filled first. */
+int gnf_unpack_rows(const float* dWp, const float* mask, const int32_t* perm, float* dW, int R, int N, int K,
+                    gnf_stream_t stream);
+/* dst[perm[r]] = src[r] (bias gradient un-permutation; dst [N] zero-filled first; perm nullable = copy). */
+int gnf_unpack_vec(const float* src, const int32_t* perm, float* dst, int R, int N, gnf_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * K1 — DAGConditioner masked embedding fused into the first Linear
+ * (DAGConditioner.forward, models/Conditionners/DAGConditioner.py:94-169)
+ * The [B,d,d] masked tensor e[b,i,j] = x[b,j]*G[b,i,j] is generated inside the GEMM's operand
+ * loader and never written to memory.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  GNF_GATE_TABLE = 0,  /* G[b,i,j] = P[i,j]  (deterministic soft/hard threshold, or raw A after post_process) */
+  GNF_GATE_GUMBEL = 1, /* G = z1/(z1+z2), Gumbel relaxed Bernoulli (DAGConditioner.py:94-103) */
+  GNF_GATE_NOISER = 2  /* e = P*(x + n*|1-P|)  (noiser_gate, DAGConditioner.py:114-116) */
+};
+enum { GNF_IMP_RAW = 0, GNF_IMP_SOFT = 1, GNF_IMP_HARD_SOFT = 2, GNF_IMP_HARD_SQ = 3 };
+
+typedef struct {
+  int32_t mode;        /* GNF_GATE_* */
+  float temperature;   /* gumble_T */
+  uint64_t seed;       /* Philox key when noise pointers are NULL */
+  uint64_t offset;     /* Philox counter offset (advanced by the caller per forward) */
+  const float* noise1; /* optional replay of the reference's draws: u1 (Gumbel) or n (noiser), [B,d,d] */
+  const float* noise2; /* u2 (Gumbel), [B,d,d] */
+} gnf_gate_t;
+
+/* Importance table P[d,d] and dP/dA[d,d] from A (DAGConditioner.py:118-124).
+ * imp: RAW P=A; SOFT P=2(sigmoid(2A^2)-.5); HARD_SOFT P=soft*[soft>h]; HARD_SQ P=A^2*[A^2>h]. */
+int gnf_dag_importance(const float* A, int d, int imp, float h_thresh, float* P, float* dPdA, gnf_stream_t stream);
+/* T[i,n] = W1[n, d+i] + b1[n]  (one-hot half of layer 1 as a per-variable bias, hot_encoding=True),
+ * or T[0,n] = b1[n] when hot == 0.  W1: [N, ldw]. */
+int gnf_dag_bias_table(const float* W1, int ldw, const float* b1, float* T, int d, int N, int hot,
+                       gnf_stream_t stream);
+/* Gradient of the bias table: dW1[n, d+i] = dT[i,n] (hot), db1[n] = sum_i dT[i,n]. */
+int gnf_dag_bias_table_bwd(const float* dT, float* dW1, int ldw, float* db1, int d, int N, int hot,
+                           gnf_stream_t stream);
+/* Y[b*d+i, n] = act( sum_j x[b,j] G[b,i,j] W1[n,j] + T[i or 0, n] ). */
+int gnf_dag_l1_fwd(const float* x, const float* P, const gnf_gate_t* gate, const float* W1, int ldw, const float* T,
+                   int bias_period, float* Y, int ldy, int B, int d, int N, int relu, gnf_stream_t stream);
+/* dW1[n,j] = sum_{b,i} dY[b*d+i,n] e[b,i,j]  (first d columns of dW1; overwrites them). */
+int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, const gnf_gate_t* gate, float* dW1,
+                     int ldw, int B, int d, int N, gnf_stream_t stream);
+/* Fused input-cotangent GEMM + reductions; the [B,d,d] cotangent never leaves the SM:
+ *   ebar[b,i,j] = sum_n dY[b*d+i,n] W1[n,j];  dx[b,j] = sum_i ebar*de/dx;  dP[i,j] = sum_b ebar*de/dP.
+ * dx [B,d] and dP [d,d] are zero-filled by the call. */
+int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const float* x, const float* P,
+                     const gnf_gate_t* gate, float* dx, float* dP, int B, int d, int N, gnf_stream_t stream);
+/* dA[i,j] (+)= dP[i,j]*dPdA[i,j]. */
+int gnf_dag_finish_dA(const float* dP, const float* dPdA, float* dA, int d, int accumulate, gnf_stream_t stream);
+/* Debug / parity hook: materialise the in-kernel Philox draws for (seed, offset) as [B,d,d] tensors. */
+int gnf_dag_dump_noise(const gnf_gate_t* gate, float* n1, float* n2, int B, int d, gnf_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * K3 — MonotonicNormalizer: fused Clenshaw-Curtis UMNN integral
+ * (MonotonicNormalizer.forward, models/Normalizers/MonotonicNormalizer.py:12-66; UMNN==1.0
+ * NeuralIntegral / ParallelNeuralIntegral forward + recompute backward)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_layers;                 /* number of nn.Linear layers (hidden layers + 1) */
+  int32_t dims[GNF_MAX_LAYERS + 1]; /* dims[0] = 1 + E, dims[n_layers] = 1 */
+  const float* W[GNF_MAX_LAYERS];   /* W[l]: [dims[l+1], dims[l]] row-major (nn.Linear.weight) */
+  const float* b[GNF_MAX_LAYERS];   /* b[l]: [dims[l+1]] */
+} gnf_mlp_t;
+
+typedef struct {
+  float* dW[GNF_MAX_LAYERS]; /* same shapes as gnf_mlp_t; zero-filled by the call, then accumulated */
+  float* db[GNF_MAX_LAYERS];
+} gnf_mlp_grad_t;
+
+size_t gnf_umnn_workspace_bytes(const gnf_mlp_t* net);
+/* x: [R] (R = B*d rows, row r = b*d+i), h: [R,E] -> z[r] = int_0^x f(t;h_r)dt + h[r,0], jac[r] = f(x;h_r).
+ * ccw / ccn: [S+1] Clenshaw-Curtis weights and nodes cos(k pi/S) (fp32, computed in float64 by the
+ * caller exactly like UMNN's compute_cc_weights).  zrev (nullable): z with the d columns reversed.
+ * logdet (nullable): [R/d], logdet[b] = sum_i log jac[b,i]. */
+int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
+                 float* z, float* zrev, float* jac, float* logdet, int R, int d, void* work, size_t work_bytes,
+                 gnf_stream_t stream);
+/* Cotangents: gz [R], gzrev [R] (nullable), gjac [R] (nullable), glogdet [R/d] (nullable).
+ * Gradient convention = UMNN's: dtheta, dh by quadrature of the integrand's gradients with weights
+ * w_k*gz*x/2; dx by the Leibniz rule f(x)*gz; the jac output is differentiated by the plain chain rule. */
+int gnf_umnn_bwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
+                 const float* jac, const float* gz, const float* gzrev, const float* gjac, const float* glogdet,
+                 float* dx, float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work, size_t work_bytes,
+                 gnf_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Small elementwise helpers used by the host side
+ * ------------------------------------------------------------------------------------------ */
+/* dst[b, d-1-i] = src[b,i]. */
+int gnf_reverse_cols(const float* src, float* dst, int B, int d, gnf_stream_t stream);
+/* CouplingConditioner: h[b,i,:] = constants[i,:] for i < indep (CouplingConditioner.py:33). h: [B,d,H]. */
+int gnf_broadcast_rows(const float* constants, float* h, int B, int d, int indep, int H, gnf_stream_t stream);
+/* y[i] += a * x[i]  (flat gradient bucket packing / scaling for the data-parallel all-reduce). */
+int gnf_axpy(float a, const float* x, float* y, size_t n, gnf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNF_H_ */
