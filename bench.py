@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the Graphical-Normalizing-Flows hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config cfg1..cfg5] [--batch B_per_gpu] [--mode train|eval]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  train: zero_grad -> forward -> loss -> backward -> (gradient all-reduce if N>1) -> Adam step
+  eval : compute_ll under no_grad.
+Default workload: BASELINE.json configs[3] (BSDS300 shape, d=63, DAG conditioner + Monotonic/UMNN normalizer),
+the configuration north_star's target is quoted on; 100 samples per GPU (its YAML batch), weak-scaled.
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM, timed per step with CUDA
+events (L2 flushed between timed steps), max over ranks.  `e2e` = the same metric through the public API with
+pinned HOST input batches copied H2D and the loss read back D2H inside the timed region.
+`--impl reference` times the reference algorithm's CPU port (oracle/, torch CPU, all host threads) on the same
+workload: /root/reference does not exist on the GPU box and its UMNN dependency is not installable, so the
+CPU arm is the oracle port ("kind": "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import gnf_b200 as G  # noqa: E402
+
+CONFIGS = G.CONFIGS
+
+DEFAULT_BATCH = {"cfg1": 100, "cfg2": 2500, "cfg3": 10000, "cfg4": 100, "cfg5": 100}
+WORKLOAD_NAME = {
+    "cfg1": "toy-8gaussians d=2, 3x(DAG+Affine)",
+    "cfg2": "UCI-POWER shape d=6, DAG+Monotonic(UMNN) S=20",
+    "cfg3": "UCI-HEPMASS shape d=21, Autoregressive+Monotonic(UMNN) S=20",
+    "cfg4": "BSDS300 shape d=63, DAG(630x3,hot)+Monotonic(UMNN 150x3) S=20",
+    "cfg5": "MNIST shape d=784, DAG(1024x3,hot,prior k=2)+Affine",
+}
+ADAM = {"cfg1": (1e-4, 1e-5), "cfg2": (1e-3, 1e-5), "cfg3": (1e-3, 1e-4), "cfg4": (1e-3, 1e-4), "cfg5": (1e-3, 1e-5)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work
+# ------------------------------------------------------------------------------------------------
+def flops_per_sample(spec, S):
+    d = spec["d"]
+    hid = list(spec["hidden"])
+    H = spec["out"]
+    if spec["cond"] == "DAG":
+        sizes = [d] + hid + [H]                      # one-hot half of layer 1 is a bias gather: not counted
+        f_cond = 2 * d * sum(a * b for a, b in zip(sizes[:-1], sizes[1:]))
+    elif spec["cond"] == "Autoregressive":
+        sizes = [d] + hid + [H * d]
+        f_cond = 2 * sum(a * b for a, b in zip(sizes[:-1], sizes[1:]))
+    else:
+        c = d // 2
+        sizes = [d - c] + hid + [H * c]
+        f_cond = 2 * sum(a * b for a, b in zip(sizes[:-1], sizes[1:]))
+    f_int = 0
+    if spec["norm"] == "monotonic":
+        I = list(spec["int_net"])
+        per_node = I[0] + sum(a * b for a, b in zip(I[:-1], I[1:])) + I[-1]
+        f_int = 2 * d * ((S + 2) * per_node + H * I[0])
+    f_cond *= spec["nb_flow"]
+    f_int *= spec["nb_flow"]
+    return f_cond, f_int
+
+
+def umnn_kernel_flops(spec, S, rows, backward):
+    """FLOPs one gnf_umnn_{fwd,bwd} call executes algorithmically for `rows` = B*d rows."""
+    I = list(spec["int_net"])
+    E = spec["out"]
+    per_node = (1 + E) * I[0] + sum(a * b for a, b in zip(I[:-1], I[1:])) + I[-1]
+    if not backward:
+        return 2 * rows * (S + 1) * per_node
+    return 3 * 2 * rows * (S + 2) * per_node          # recompute forward + dgrad + wgrad
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (reference algorithm, torch CPU)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(cfg, B, mode, S):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gnf_oracle as O
+    spec = {k: v for k, v in CONFIGS[cfg].items() if k != "A_prior"}
+    A_prior = None
+    if CONFIGS[cfg].get("A_prior") == "mnist":
+        A_prior = G.MNIST_A_prior(28, 2)
+    sd = O.init_state_dict(spec, seed=0, A_prior=A_prior)
+    keys = O.trainable_keys(sd)
+    for k in keys:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    lr, wd = ADAM[cfg]
+    opt = torch.optim.Adam([sd[k] for k in keys], lr=lr, weight_decay=wd)
+    g = torch.Generator().manual_seed(0)
+    d = spec["d"]
+
+    def noises():
+        if spec["cond"] != "DAG":
+            return None
+        return [(torch.rand(B, d, d), torch.rand(B, d, d)) for _ in range(spec["nb_flow"])]
+
+    def train_step():
+        x = torch.randn(B, d, generator=g)
+        opt.zero_grad()
+        z, jac = O.flow_forward(x, sd, spec, None, noises(), S)
+        loss = O.flow_loss(z, jac, sd, spec)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    def eval_step():
+        x = torch.randn(B, d, generator=g)
+        with torch.no_grad():
+            ll, _ = O.compute_ll(x, sd, spec, None, noises(), S)
+        return float(ll.mean())
+
+    return train_step if mode == "train" else eval_step
+
+
+def time_cpu(cfg, B, mode, S, steps, warmup, budget_s=25.):
+    """Bounded CPU timing: batch reduced (stated in `sample`) when a full step would blow the budget."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    Bc = B
+    probe_B = min(B, 16)
+    fn = cpu_reference_step_fn(cfg, probe_B, mode, S)
+    t0 = time.perf_counter(); fn(); fn(); t1 = time.perf_counter()
+    per_sample = (t1 - t0) / 2 / probe_B
+    total_steps = steps + warmup
+    if per_sample * B * total_steps > budget_s:
+        Bc = max(1, int(budget_s / (per_sample * total_steps)))
+    fn = cpu_reference_step_fn(cfg, Bc, mode, S)
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": Bc / med, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} {mode} steps of {WORKLOAD_NAME[cfg]} at batch {Bc} (of {B}) on the host CPU, "
+                      f"median step {med * 1e3:.1f} ms, after {warmup} warm-up"}, med
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the config's own batch)")
+    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    ap.add_argument("--nb-steps", type=int, default=None, help="quadrature steps S (default 20 train / 40 eval)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = args.config
+    spec = CONFIGS[cfg]
+    B = args.batch or DEFAULT_BATCH[cfg]
+    S = args.nb_steps or (20 if args.mode == "train" else 40)
+    metric = "train_samples_per_s" if args.mode == "train" else "loglik_eval_samples_per_s"
+    config = {"workload": WORKLOAD_NAME[cfg], "config": cfg, "batch_per_gpu": B, "global_batch": B * max(world, 1),
+              "nb_steps": S, "mode": args.mode, "parallelism": f"dp{max(world, 1)}", "gate": "stochastic (reference default)",
+              "precision_mode": "strict fp32 (FFMA kernels)", "l2": "flushed between timed steps (256 MiB write)"}
+
+    # ---------------- reference arm ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, med = time_cpu(cfg, B, args.mode, S, max(3, min(args.steps, 10)), 2, budget_s=120.)
+        line = {"metric": metric, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ----------------
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = G.build_from_spec(spec, dev, seed=0)
+    G.dist.broadcast_parameters(model)
+    G.dist.decorrelate_gate_noise(model, rank)
+    for n in model.getNormalizers():
+        if hasattr(n, "nb_steps"):
+            n.nb_steps = S
+    d = spec["d"]
+    lr, wd = ADAM[cfg]
+    bucket = G.dist.GradBucket(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd, fused=True)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    n_pool = 8
+    pool = [torch.randn(B, d, device=dev, generator=gen) for _ in range(n_pool)]
+    host_pool = [torch.randn(B, d).pin_memory() for _ in range(n_pool)]
+    flush_buf = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
+
+    def train_step(x):
+        bucket.zero()
+        z, jac = model(x)
+        loss = model.loss(z, jac)
+        loss.backward()
+        bucket.allreduce_mean()
+        opt.step()
+        return loss
+
+    def eval_step(x):
+        with torch.no_grad():
+            ll, _ = model.compute_ll(x)
+        return ll.mean()
+
+    step = train_step if args.mode == "train" else eval_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(pool[i % n_pool])
+    barrier()
+
+    # -------- device-resident timing: per-step CUDA events, L2 flushed between steps --------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = G.ops.launch_count()
+    G.ops.enable_kernel_timing(True)
+    evs = []
+    barrier()
+    for i in range(args.steps):
+        flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(pool[i % n_pool])
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = G.ops.launch_count() - l0
+    ktimes = G.ops.collect_kernel_timing()
+    G.ops.enable_kernel_timing(False)
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # -------- end-to-end: pinned host batch -> H2D -> step -> loss D2H, every step --------
+    barrier()
+    t0 = time.perf_counter()
+    last = 0.
+    for i in range(args.steps):
+        x = host_pool[i % n_pool].to(dev, non_blocking=True)
+        last = float(step(x))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (dev_ms / 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    f_cond, f_int = flops_per_sample(spec, S)
+    flops_step = (3 * f_cond + 4 * f_int if args.mode == "train" else f_cond + f_int) * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    roofline = None
+    if spec["norm"] == "monotonic":
+        kname = "gnf_umnn_bwd" if args.mode == "train" else "gnf_umnn_fwd"
+        if ktimes.get(kname):
+            avg_ms = sum(ktimes[kname]) / len(ktimes[kname])
+            fl = umnn_kernel_flops(spec, S, B * d, backward=(args.mode == "train"))
+            ach = fl / (avg_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": ach / peak_tf, "traffic": None, "avg_launch_ms": avg_ms, "flops_per_launch": fl,
+                        "peak_source": peak_src,
+                        "note": "strict-fp32 FFMA kernel (no tensor-core instructions yet): fp32 CUDA-core ceiling is "
+                                "~70 TFLOP/s; fraction is quoted against the measured bf16 tensor peak as the contract asks",
+                        "share_of_step": avg_ms / (dev_ms / args.steps)}
+    else:
+        kname = "gnf_linear_fwd"
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu_baseline, _ = time_cpu(cfg, B, args.mode, S, 5, 2, budget_s=25.)
+
+    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * d * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "achieved_tflops_step": flops_step / (dev_ms / args.steps / 1e3) / 1e12,
+            "algorithmic_gflop_per_step": flops_step / 1e9, "last_loss": last,
+            "kernel_ms": {k: sum(v) / len(v) for k, v in ktimes.items() if v}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

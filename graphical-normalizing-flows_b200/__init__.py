@@ -12,10 +12,11 @@ from .flow import (FCNormalizingFlow, MNIST_A_prior, NormalLogDensity, Normalizi
                    buildFCNormalizingFlow)
 from .normalizers import AffineNormalizer, ELUPlus, IntegrandNet, MonotonicNormalizer, Normalizer
 from . import dist
+from .configs import CONFIGS, build_from_spec
 
 __all__ = [
     "AutoregressiveConditioner", "Conditioner", "ConditionnalMADE", "CouplingConditioner", "CouplingMLP", "DAGConditioner",
     "DAGMLP", "MADE", "MaskedLinear", "FCNormalizingFlow", "MNIST_A_prior", "NormalLogDensity", "NormalizingFlow",
     "NormalizingFlowStep", "buildFCNormalizingFlow", "AffineNormalizer", "ELUPlus", "IntegrandNet", "MonotonicNormalizer",
-    "Normalizer", "ops", "dist",
+    "Normalizer", "ops", "dist", "CONFIGS", "build_from_spec",
 ]

@@ -22,6 +22,37 @@ def _count(n=1):
     _LAUNCHES += n
 
 
+_TIMING = False
+_TIMES = {}
+
+
+def enable_kernel_timing(flag):
+    """bench.py: bracket every C-ABI call with CUDA events on the launching stream."""
+    global _TIMING
+    _TIMING = bool(flag)
+    if flag:
+        _TIMES.clear()
+
+
+def collect_kernel_timing():
+    """{entry point: [ms per call]} — synchronises."""
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in _TIMES.items()}
+
+
+def _call(name, *args):
+    fn = getattr(lib(), name)
+    if _TIMING and not L._SIMULATOR:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _TIMES.setdefault(name, []).append((e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc)
+
+
 def launch_count():
     return _LAUNCHES
 
@@ -52,7 +83,7 @@ class AffineFn(torch.autograd.Function):
         zrev = torch.empty_like(x) if want_rev else None
         logdet = torch.empty(B, device=x.device, dtype=x.dtype)
         mask = torch.empty(B, d, device=x.device, dtype=torch.uint8)
-        check(lib().gnf_affine_fwd(ptr(x), ptr(h), H, ptr(z), ptr(zrev), ptr(jac), ptr(logdet), ptr(mask), B, d, stream_ptr()))
+        _call("gnf_affine_fwd", ptr(x), ptr(h), H, ptr(z), ptr(zrev), ptr(jac), ptr(logdet), ptr(mask), B, d, stream_ptr())
         _count()
         torch.autograd.graph.increment_version(h)
         ctx.save_for_backward(x, h, mask)
@@ -74,8 +105,8 @@ class AffineFn(torch.autograd.Function):
         gzrev = _contig(gzrev) if (gzrev is not None and ctx.want_rev) else None
         gx = torch.empty_like(x)
         gh = torch.empty_like(h)
-        check(lib().gnf_affine_bwd(ptr(x), ptr(h), H, ptr(mask), ptr(gz), ptr(gzrev), ptr(gjac), ptr(glogdet), ptr(gx), ptr(gh),
-                                   B, d, stream_ptr()))
+        _call("gnf_affine_bwd", ptr(x), ptr(h), H, ptr(mask), ptr(gz), ptr(gzrev), ptr(gjac), ptr(glogdet), ptr(gx), ptr(gh),
+                                   B, d, stream_ptr())
         _count()
         return gx, gh, None
 
@@ -90,7 +121,7 @@ class NormalLLFn(torch.autograd.Function):
         if logdet is not None:
             require(logdet, "logdet")
         out = torch.empty(B, device=z.device, dtype=z.dtype)
-        check(lib().gnf_normal_ll_fwd(ptr(z), ptr(logdet), ptr(out), B, d, stream_ptr()))
+        _call("gnf_normal_ll_fwd", ptr(z), ptr(logdet), ptr(out), B, d, stream_ptr())
         _count()
         ctx.save_for_backward(z)
         ctx.has_logdet = logdet is not None
@@ -101,7 +132,7 @@ class NormalLLFn(torch.autograd.Function):
         (z,) = ctx.saved_tensors
         gout = _contig(gout)
         gz = torch.empty_like(z)
-        check(lib().gnf_normal_ll_bwd(ptr(z), ptr(gout), ptr(gz), z.shape[0], z.shape[1], stream_ptr()))
+        _call("gnf_normal_ll_bwd", ptr(z), ptr(gout), ptr(gz), z.shape[0], z.shape[1], stream_ptr())
         _count()
         return gz, (gout if ctx.has_logdet else None)
 
@@ -109,7 +140,7 @@ class NormalLLFn(torch.autograd.Function):
 def reverse_cols(z):
     require(z, "z")
     out = torch.empty_like(z)
-    check(lib().gnf_reverse_cols(ptr(z), ptr(out), z.shape[0], z.shape[1], stream_ptr()))
+    _call("gnf_reverse_cols", ptr(z), ptr(out), z.shape[0], z.shape[1], stream_ptr())
     _count()
     return out
 
@@ -141,7 +172,7 @@ class PowerTraceFn(torch.autograd.Function):
         d = A.shape[0]
         t = torch.empty((), device=A.device, dtype=A.dtype)
         ws, n = _pt_workspace(d, A.device)
-        check(lib().gnf_power_trace_fwd(ptr(A), d, float(alpha), int(p), ptr(t), ptr(ws), n, stream_ptr()))
+        _call("gnf_power_trace_fwd", ptr(A), d, float(alpha), int(p), ptr(t), ptr(ws), n, stream_ptr())
         _count()
         ctx.save_for_backward(A)
         ctx.alpha, ctx.p = float(alpha), int(p)
@@ -154,7 +185,7 @@ class PowerTraceFn(torch.autograd.Function):
         gt = _contig(gt)
         dA = torch.empty_like(A)
         ws, n = _pt_workspace(d, A.device)
-        check(lib().gnf_power_trace_bwd(ptr(A), d, ctx.alpha, ctx.p, ptr(gt), ptr(dA), ptr(ws), n, stream_ptr()))
+        _call("gnf_power_trace_bwd", ptr(A), d, ctx.alpha, ctx.p, ptr(gt), ptr(dA), ptr(ws), n, stream_ptr())
         _count()
         return dA, None, None
 
@@ -171,8 +202,8 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
     if out is None:
         out = torch.empty(M, N, device=X.device, dtype=X.dtype)
         ldy = N
-    check(lib().gnf_linear_fwd(ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
-                               stream_ptr()))
+    _call("gnf_linear_fwd", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
+                               stream_ptr())
     _count()
     return out
 
@@ -182,22 +213,22 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
     if out is None:
         out = torch.empty(M, K, device=dY.device, dtype=dY.dtype)
         lddx = K
-    check(lib().gnf_linear_dgrad(ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
-                                 ptr(out), lddx, M, N, K, stream_ptr()))
+    _call("gnf_linear_dgrad", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
+                                 ptr(out), lddx, M, N, K, stream_ptr())
     _count()
     return out
 
 
 def linear_wgrad(dY, lddy, X, ldx, M, N, K):
     dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
-    check(lib().gnf_linear_wgrad(ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr()))
+    _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr())
     _count()
     return dW
 
 
 def colsum(Y, ldy, M, N, period=1):
     out = torch.empty(period, N, device=Y.device, dtype=Y.dtype)
-    check(lib().gnf_colsum(ptr(Y), ldy, ptr(out), M, N, period, stream_ptr()))
+    _call("gnf_colsum", ptr(Y), ldy, ptr(out), M, N, period, stream_ptr())
     _count()
     return out
 
@@ -278,7 +309,7 @@ def pack_rows(W, mask=None, perm=None, R=None):
     R = W.shape[0] if R is None else R
     K = W.shape[1]
     out = torch.empty(R, K, device=W.device, dtype=W.dtype)
-    check(lib().gnf_pack_rows(ptr(W), ptr(mask), ptr(perm), ptr(out), R, K, stream_ptr()))
+    _call("gnf_pack_rows", ptr(W), ptr(mask), ptr(perm), ptr(out), R, K, stream_ptr())
     _count()
     return out
 
@@ -298,7 +329,7 @@ class PackRowsFn(torch.autograd.Function):
         g = _contig(g)
         N, K = ctx.shape
         dW = torch.empty(N, K, device=g.device, dtype=g.dtype)
-        check(lib().gnf_unpack_rows(ptr(g), ptr(ctx.mask), ptr(ctx.perm), ptr(dW), g.shape[0], N, K, stream_ptr()))
+        _call("gnf_unpack_rows", ptr(g), ptr(ctx.mask), ptr(ctx.perm), ptr(dW), g.shape[0], N, K, stream_ptr())
         _count()
         return dW, None, None
 
@@ -316,14 +347,14 @@ class PackVecFn(torch.autograd.Function):
     def backward(ctx, g):
         g = _contig(g)
         db = torch.empty(ctx.n, device=g.device, dtype=g.dtype)
-        check(lib().gnf_unpack_vec(ptr(g), ptr(ctx.perm), ptr(db), g.numel(), ctx.n, stream_ptr()))
+        _call("gnf_unpack_vec", ptr(g), ptr(ctx.perm), ptr(db), g.numel(), ctx.n, stream_ptr())
         _count()
         return db, None
 
 
 def broadcast_rows(constants, h, indep):
     B, d, H = h.shape
-    check(lib().gnf_broadcast_rows(ptr(constants), ptr(h), B, d, indep, H, stream_ptr()))
+    _call("gnf_broadcast_rows", ptr(constants), ptr(h), B, d, indep, H, stream_ptr())
     _count()
 
 
@@ -351,7 +382,7 @@ def dag_dump_noise(gate, B, d, device):
     n1 = torch.empty(B, d, d, device=device, dtype=torch.float32)
     n2 = torch.empty(B, d, d, device=device, dtype=torch.float32) if gate.mode == L.GATE_GUMBEL else None
     g = GateSpec(gate.mode, gate.imp, gate.h_thresh, gate.T, gate.seed, gate.offset, None).c_struct()
-    check(lib().gnf_dag_dump_noise(C.byref(g), ptr(n1), ptr(n2), B, d, stream_ptr()))
+    _call("gnf_dag_dump_noise", C.byref(g), ptr(n1), ptr(n2), B, d, stream_ptr())
     _count()
     return (n1, n2) if n2 is not None else (n1,)
 
@@ -378,14 +409,14 @@ class DagMlpFn(torch.autograd.Function):
         st = stream_ptr()
         P = torch.empty_like(A)
         dPdA = torch.empty_like(A)
-        check(lib().gnf_dag_importance(ptr(A), d, gate.imp, gate.h_thresh, ptr(P), ptr(dPdA), st))
+        _call("gnf_dag_importance", ptr(A), d, gate.imp, gate.h_thresh, ptr(P), ptr(dPdA), st)
         N1 = weights[0].shape[0]
         T = torch.empty(d if hot else 1, N1, device=x.device, dtype=x.dtype)
-        check(lib().gnf_dag_bias_table(ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st))
+        _call("gnf_dag_bias_table", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st)
         g = gate.c_struct()
         y = torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
-        check(lib().gnf_dag_l1_fwd(ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
-                                   ptr(y), N1, B, d, N1, int(n > 1), st))
+        _call("gnf_dag_l1_fwd", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
+                                   ptr(y), N1, B, d, N1, int(n > 1), st)
         _count(3)
         acts = []
         cur = y
@@ -417,20 +448,20 @@ class DagMlpFn(torch.autograd.Function):
         N1 = W1.shape[0]
         g = gate.c_struct()
         dW1 = torch.empty_like(W1)
-        check(lib().gnf_dag_l1_wgrad(ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st))
+        _call("gnf_dag_l1_wgrad", ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st)
         dT = colsum(delta, delta.stride(0), M, N1, period=(d if hot else 1))
         db1 = torch.empty(N1, device=x.device, dtype=x.dtype)
-        check(lib().gnf_dag_bias_table_bwd(ptr(dT), ptr(dW1), W1.stride(0), ptr(db1), d, N1, int(hot), st))
+        _call("gnf_dag_bias_table_bwd", ptr(dT), ptr(dW1), W1.stride(0), ptr(db1), d, N1, int(hot), st)
         _count(2)
         dWs[0], dbs[0] = dW1, db1
         dx = dA = None
         if needs[0] or needs[1]:
             dx = torch.empty_like(x)
             dP = torch.empty_like(A)
-            check(lib().gnf_dag_l1_dgrad(ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx),
-                                         ptr(dP), B, d, N1, st))
+            _call("gnf_dag_l1_dgrad", ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx),
+                                         ptr(dP), B, d, N1, st)
             dA = torch.empty_like(A)
-            check(lib().gnf_dag_finish_dA(ptr(dP), ptr(dPdA), ptr(dA), d, 0, st))
+            _call("gnf_dag_finish_dA", ptr(dP), ptr(dPdA), ptr(dA), d, 0, st)
             _count(2)
         out = [dx if needs[0] else None, dA if needs[1] else None, None, None]
         for l in range(n):
@@ -504,8 +535,8 @@ class UmnnFn(torch.autograd.Function):
         jac = torch.empty_like(x)
         zrev = torch.empty_like(x) if want_rev else None
         logdet = torch.empty(B, device=x.device, dtype=x.dtype)
-        check(lib().gnf_umnn_fwd(ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac), ptr(logdet),
-                                 R, d, ptr(ws), nbytes, stream_ptr()))
+        _call("gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac), ptr(logdet),
+                                 R, d, ptr(ws), nbytes, stream_ptr())
         _count(2)
         ctx.save_for_backward(x, h, jac, *weights, *biases)
         ctx.S, ctx.want_rev, ctx.n = int(S), want_rev, len(weights)
@@ -539,8 +570,8 @@ class UmnnFn(torch.autograd.Function):
         for l in range(n):
             grads.dW[l] = dWs[l].data_ptr()
             grads.db[l] = dbs[l].data_ptr()
-        check(lib().gnf_umnn_bwd(ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev), ptr(gjac),
-                                 ptr(glogdet), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr()))
+        _call("gnf_umnn_bwd", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev), ptr(gjac),
+                                 ptr(glogdet), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr())
         _count(2)
         out = [dx, dh, None, None]
         for l in range(n):

@@ -6,22 +6,8 @@ import torch
 import gnf_b200 as G
 from helpers import load_golden, rel_err, rel_l2
 
-COND = {"DAG": G.DAGConditioner, "Autoregressive": G.AutoregressiveConditioner, "Coupling": G.CouplingConditioner}
-
-
 def build_model(spec, device):
-    cargs = {"in_size": spec["d"], "hidden": list(spec["hidden"]), "out_size": spec["out"]}
-    if spec["cond"] == "DAG":
-        cargs.update(l1=spec.get("l1", 0.), gumble_T=spec.get("gumble_T", 1.), nb_epoch_update=10,
-                     hot_encoding=spec.get("hot_encoding", False))
-    if spec["norm"] == "monotonic":
-        ntype = G.MonotonicNormalizer
-        nargs = {"integrand_net": list(spec["int_net"]), "cond_size": spec["out"], "nb_steps": spec["nb_steps"],
-                 "solver": spec.get("solver", "CC")}
-    else:
-        ntype, nargs = G.AffineNormalizer, {}
-    model = G.buildFCNormalizingFlow(spec["nb_flow"], COND[spec["cond"]], cargs, ntype, nargs)
-    return model.to(device)
+    return G.build_from_spec(spec, device)
 
 
 def set_modes(model, mode):

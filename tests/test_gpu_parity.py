@@ -1,0 +1,210 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the product API -> autograd Functions -> C-ABI,
+against (1) the reference-generated golden vectors, (2) the CPU oracle on seeded inputs at the BASELINE
+configs' real layer shapes, (3) size-independent properties at BASELINE's full batch sizes.
+
+Tolerances (BASELINE.json north_star, strict fp32 mode): per-sample log-likelihood 1e-4 relative,
+per-parameter-tensor gradients 1e-3 relative L2."""
+import ctypes as C
+
+import pytest
+import torch
+
+import gnf_b200 as G
+from helpers import golden_names
+import parity
+
+pytestmark = pytest.mark.gpu
+
+LL_TOL, GRAD_TOL = 1e-4, 1e-3
+
+
+def _mvo():
+    import model_vs_oracle
+    return model_vs_oracle
+
+
+def test_product_library_is_the_device_build():
+    assert G._lib.lib().gnf_has_device_code() == 1
+    assert not G._lib._SIMULATOR
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_vectors(name):
+    parity.run_case(name, "cuda", LL_TOL, GRAD_TOL)
+
+
+def _check(rep):
+    bad = {k: v for k, v in rep.items() if (k.startswith("grad.") and not v < GRAD_TOL) or (k in ("ll", "loss") and not v < LL_TOL)}
+    assert not bad, f"out of tolerance: {bad}\n{rep}"
+
+
+@pytest.mark.parametrize("cfg,B", [("cfg1", 100), ("cfg2", 256), ("cfg3", 48), ("cfg4", 12), ("cfg5", 2)])
+def test_train_step_vs_oracle_at_config_shapes(cfg, B):
+    M = _mvo()
+    _check(M.compare(M.CONFIGS[cfg], B, "cuda", train=True))
+
+
+@pytest.mark.parametrize("cfg,B,S", [("cfg2", 300, 40), ("cfg3", 64, 40), ("cfg4", 20, 40), ("cfg4", 7, 150), ("cfg2", 33, 29)])
+def test_compute_ll_vs_oracle_eval_steps(cfg, B, S):
+    M = _mvo()
+    _check(M.compare(M.CONFIGS[cfg], B, "cuda", train=False, nb_steps=S))
+
+
+@pytest.mark.parametrize("mode", [dict(stoch_gate=False), dict(stoch_gate=False, s_thresh=False),
+                                  dict(h_thresh=.3, stoch_gate=False), dict(h_thresh=.3)])
+def test_dag_gate_modes_vs_oracle(mode):
+    M = _mvo()
+    _check(M.compare(M.CONFIGS["cfg2"], 64, "cuda", mode=mode, scaleA=.3, train=True))
+
+
+def test_compute_ll_api_matches_forward():
+    M = _mvo()
+    model = M.build(M.CONFIGS["cfg2"], "cuda")
+    parity.set_modes(model, dict(stoch_gate=False))
+    x = torch.randn(128, 6, device="cuda")
+    with torch.no_grad():
+        ll, z = model.compute_ll(x)
+        z2, jac = model(x)
+        ll2 = model.z_log_density(z2) + jac
+    assert torch.allclose(ll, ll2, rtol=1e-5, atol=1e-5) and torch.allclose(z, z2, rtol=1e-5, atol=1e-6)
+
+
+# ---------------- kernel-level checks through the C-ABI wrappers ----------------
+@pytest.mark.parametrize("M_,N,K", [(1, 1, 1), (127, 33, 65), (300, 630, 126), (1000, 30, 630), (64, 2, 1024), (513, 210, 21)])
+def test_linear_engine_vs_torch(M_, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M_ + N + K)
+    X = torch.randn(M_, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** .5
+    b = torch.randn(N, device="cuda", generator=g)
+    Y = G.ops.linear_fwd(X, W, b, relu=True)
+    ref = torch.relu((X.double() @ W.double().t() + b.double())).float()
+    assert torch.allclose(Y, ref, rtol=1e-4, atol=1e-5)
+    dY = torch.randn(M_, N, device="cuda", generator=g)
+    dX = G.ops.linear_dgrad(dY, N, W, X, M_)
+    refdX = ((dY.double() @ W.double()) * (X > 0)).float()
+    assert torch.allclose(dX, refdX, rtol=1e-4, atol=1e-4)
+    dW = G.ops.linear_wgrad(dY, N, X, K, M_, N, K)
+    refdW = (dY.double().t() @ X.double()).float()
+    assert torch.allclose(dW, refdW, rtol=1e-4, atol=1e-3)
+    db = G.ops.colsum(dY, N, M_, N).view(-1)
+    assert torch.allclose(db, dY.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+
+
+def test_power_trace_golden_on_gpu():
+    import os
+    import numpy as np
+    from helpers import GOLDEN, rel_l2
+    f = np.load(os.path.join(GOLDEN, "power_trace.npz"))
+    for key in sorted({k.rsplit(".", 1)[0] for k in f.files}):
+        A = torch.from_numpy(f[key + ".A"]).cuda().requires_grad_(True)
+        d, p, alpha = f[key + ".meta"]
+        t = G.ops.PowerTraceFn.apply(A, float(alpha), int(p))
+        t.backward()
+        want = float(f[key + ".t"])
+        assert abs(float(t.detach()) - want) <= 2e-5 * abs(want) + 1e-5 * float(d), key
+        assert rel_l2(A.grad.cpu(), torch.from_numpy(f[key + ".dA"])) < 1e-4, key
+
+
+def test_power_trace_large_d_vs_torch():
+    d, p = 784, 34
+    A = (G.MNIST_A_prior(28, 2) * .7).cuda().requires_grad_(True)
+    t = G.ops.PowerTraceFn.apply(A, 1. / d, p)
+    t.backward()
+    A2 = A.detach().double().requires_grad_(True)
+    Bm = torch.eye(d, device="cuda", dtype=torch.float64) + A2 ** 2 / d
+    t2 = torch.diag(torch.matrix_power(Bm, p)).sum() - d
+    t2.backward()
+    assert abs(float(t.detach()) - float(t2)) < 1e-3 * abs(float(t2)) + 1e-3
+    assert float((A.grad.double() - A2.grad).norm() / A2.grad.norm()) < 1e-4
+
+
+def test_affine_clamps_h_in_place_and_masks_gradients():
+    x = torch.randn(5, 3, device="cuda")
+    h = (torch.randn(5, 3, 4, device="cuda") * 6).requires_grad_(True)
+    hh = h * 1.
+    z, jac = G.AffineNormalizer()(x, hh)
+    (z.sum() + jac.sum()).backward()
+    hc = h.detach()
+    mu, ls = hc[..., 0].clamp(-5, 5), hc[..., 1].clamp(-5, 2)
+    assert torch.equal(hh.detach()[..., 0], mu) and torch.equal(hh.detach()[..., 1], ls)       # in-place write-back (Q7)
+    assert torch.allclose(z, x * ls.exp() + mu, rtol=1e-6, atol=1e-6)
+    m0 = ((hc[..., 0] >= -5) & (hc[..., 0] <= 5)).float()
+    m1 = ((hc[..., 1] >= -5) & (hc[..., 1] <= 2)).float()
+    assert torch.allclose(h.grad[..., 0], m0) and torch.allclose(h.grad[..., 1], (x * ls.exp() + ls.exp()) * m1, rtol=1e-5, atol=1e-6)
+    assert float(h.grad[..., 2:].abs().max()) == 0.
+
+
+def test_wrappers_reject_cpu_and_wrong_dtype():
+    with pytest.raises(TypeError):
+        G.AffineNormalizer()(torch.randn(2, 3), torch.randn(2, 3, 2))
+    with pytest.raises(TypeError):
+        G.AffineNormalizer()(torch.randn(2, 3, device="cuda").double(), torch.randn(2, 3, 2, device="cuda").double())
+
+
+def test_unsupported_shape_is_a_loud_error():
+    with pytest.raises((RuntimeError, ValueError)):
+        n = G.MonotonicNormalizer([300, 300], 4).cuda()          # hidden width > 256: outside the kernel's range
+        n(torch.randn(4, 2, device="cuda"), torch.randn(4, 2, 4, device="cuda"))
+
+
+# ---------------- properties at BASELINE's full sizes ----------------
+@pytest.mark.parametrize("cfg,B", [("cfg2", 2500), ("cfg3", 10000), ("cfg4", 100), ("cfg1", 100)])
+def test_full_size_batch_split_invariance_and_finiteness(cfg, B):
+    """ll of a sample does not depend on which batch it is evaluated in (deterministic gate); everything finite."""
+    M = _mvo()
+    model = M.build(M.CONFIGS[cfg], "cuda")
+    parity.set_modes(model, dict(stoch_gate=False))
+    x = torch.randn(B, M.CONFIGS[cfg]["d"], device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    with torch.no_grad():
+        ll, z = model.compute_ll(x)
+        idx = torch.tensor([0, B // 3, B - 1], device="cuda")
+        ll_s, z_s = model.compute_ll(x[idx].contiguous())
+    assert torch.isfinite(ll).all() and torch.isfinite(z).all()
+    assert torch.allclose(ll[idx], ll_s, rtol=2e-5, atol=1e-4)
+    assert torch.allclose(z[idx], z_s, rtol=1e-5, atol=1e-5)
+
+
+def test_full_size_quadrature_refinement_converges():
+    """z(S) converges as S grows (CC quadrature of a smooth integrand): |z40 - z80| << |z20 - z80|, and the
+    monotone map has a strictly positive Jacobian >= 0.05 (ELU+1.05)."""
+    M = _mvo()
+    model = M.build(M.CONFIGS["cfg4"], "cuda")
+    parity.set_modes(model, dict(stoch_gate=False))
+    x = torch.randn(100, 63, device="cuda")
+    zs = {}
+    with torch.no_grad():
+        for S in (20, 40, 80):
+            for n in model.getNormalizers():
+                n.nb_steps = S
+            zs[S], jac = model(x)
+        h = model.getConditioners()[0](x)
+        _, j = model.getNormalizers()[0](x, h)
+    assert float(j.min()) >= 0.05 - 1e-6
+    e20, e40 = float((zs[20] - zs[80]).abs().max()), float((zs[40] - zs[80]).abs().max())
+    assert e40 <= e20 + 1e-6 and e40 < 1e-3
+
+
+def test_one_step_affine_flow_inverts_exactly():
+    M = _mvo()
+    spec = dict(nb_flow=1, d=6, cond="DAG", hidden=[32, 32], out=2, hot_encoding=True, gumble_T=.5, l1=0., norm="affine")
+    model = M.build(spec, "cuda")
+    cond = model.getConditioners()[0]
+    with torch.no_grad():
+        cond.A.copy_(torch.tril(torch.ones(6, 6), -1).cuda())
+    cond.post_process(.5)
+    cond.is_invertible = True
+    x = torch.randn(50, 6, device="cuda")
+    with torch.no_grad():
+        z, _ = model(x)
+        xr = model.invert(z)
+    assert float((x - xr).abs().max()) < 1e-4
+
+
+def test_philox_gate_noise_is_reproducible_and_uniform():
+    gs = G.ops.GateSpec(G._lib.GATE_GUMBEL, G._lib.IMP_SOFT, 0., .5, seed=1234, offset=7)
+    a1, a2 = G.ops.dag_dump_noise(gs, 64, 20, "cuda")
+    b1, b2 = G.ops.dag_dump_noise(gs, 64, 20, "cuda")
+    assert torch.equal(a1, b1) and torch.equal(a2, b2)
+    assert 0. < float(a1.min()) and float(a1.max()) < 1.
+    assert abs(float(a1.mean()) - .5) < .02 and abs(float(a2.mean()) - .5) < .02
+    assert abs(float(((a1 - .5) * (a2 - .5)).mean())) < .01
