@@ -106,6 +106,8 @@ def test_power_trace_golden_on_gpu():
 
 
 def test_power_trace_large_d_vs_torch():
+    """d = 784 (host-driven GEMM chain).  t = tr(B^p) - d cancels ~788 - 784 in fp32, so the forward value is
+    compared on the trace's own scale (the reference computes the same fp32 difference)."""
     d, p = 784, 34
     A = (G.MNIST_A_prior(28, 2) * .7).cuda().requires_grad_(True)
     t = G.ops.PowerTraceFn.apply(A, 1. / d, p)
@@ -114,7 +116,10 @@ def test_power_trace_large_d_vs_torch():
     Bm = torch.eye(d, device="cuda", dtype=torch.float64) + A2 ** 2 / d
     t2 = torch.diag(torch.matrix_power(Bm, p)).sum() - d
     t2.backward()
-    assert abs(float(t.detach()) - float(t2)) < 1e-3 * abs(float(t2)) + 1e-3
+    A3 = A.detach()
+    t3 = torch.diag(torch.matrix_power(torch.eye(d, device="cuda") + A3 ** 2 / d, p)).sum() - d   # fp32 torch
+    assert abs(float(t.detach()) - float(t2)) < 3e-5 * (d + abs(float(t2)))
+    assert abs(float(t.detach()) - float(t3)) < 3e-5 * (d + abs(float(t2)))
     assert float((A.grad.double() - A2.grad).norm() / A2.grad.norm()) < 1e-4
 
 
