@@ -1,0 +1,403 @@
+// K3 on the 5th-generation tensor cores: fused Clenshaw-Curtis UMNN integral, forward, "fast" mode
+// (single-pass TF32 operands, fp32 accumulation in TMEM; per-sample log-likelihood tolerance 2e-3).
+//
+// Design (one CTA per SM, persistent over 128-node-row tiles):
+//   * every layer's weight matrix is packed once per call into the UMMA canonical K-major shared-memory
+//     image and pulled into shared memory by bulk async copies (TMA unit, mbarrier completion); it stays
+//     resident for the CTA's lifetime -- B operand of every tcgen05.mma;
+//   * the activation chain never touches shared or global memory: thread t owns tile row t = TMEM lane t;
+//     the layer input lives in TMEM columns [0, NP) (A operand, TS form), the accumulator in columns
+//     [NP, 2NP); the epilogue (tcgen05.ld -> bias + ReLU in registers -> tcgen05.st) rewrites the A region
+//     for the next layer;
+//   * the last Linear (N = 1), ELU + 1.05, the CC weighting and the per-row segment reduction are done in
+//     registers / a 128-float shared buffer, emitting z, jac, logdet (+ zrev) directly.
+#include "tc_common.cuh"
+
+#ifndef GNF_EMU
+namespace gnf {
+
+constexpr int kTcRows = 128;
+
+struct TcPlan {
+  int L, NP, alloc_cols;
+  int kp[GNF_MAX_LAYERS];          // K of layer l rounded up to 8 (number of A columns consumed)
+  size_t off[GNF_MAX_LAYERS];      // float offset of layer l's image
+  size_t off_bias, off_wlast, total_floats;
+};
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int make_tc_plan(const gnf_mlp_t* net, TcPlan* pl) {
+  if (!net || net->n_layers < 2 || net->n_layers > GNF_MAX_LAYERS) return fail(GNF_ERR_UNSUPPORTED, "umnn tc: integrand needs 2..%d linear layers", GNF_MAX_LAYERS);
+  if (net->dims[net->n_layers] != 1) return fail(GNF_ERR_UNSUPPORTED, "umnn tc: integrand output size must be 1");
+  const int L = net->n_layers - 1;
+  int maxh = 0;
+  for (int l = 1; l <= L; ++l) maxh = net->dims[l] > maxh ? net->dims[l] : maxh;
+  const int NP = round_up(maxh, 16);
+  if (NP > 256 || round_up(net->dims[0], 8) > NP) return fail(GNF_ERR_UNSUPPORTED, "umnn tc: widths out of range (hidden max %d, input %d)", maxh, net->dims[0]);
+  size_t off = 0;
+  for (int l = 0; l < L; ++l) {
+    pl->kp[l] = round_up(net->dims[l], 8);
+    pl->off[l] = off;
+    off += (size_t)pl->kp[l] * NP;
+  }
+  pl->off_bias = off; off += (size_t)L * NP;
+  pl->off_wlast = off; off += NP;
+  pl->total_floats = off;
+  pl->L = L; pl->NP = NP;
+  int a = 32;
+  while (a < 2 * NP) a <<= 1;
+  pl->alloc_cols = a;
+  const size_t smem = off * sizeof(float) + 1024;
+  if (smem > 227 * 1024) return fail(GNF_ERR_UNSUPPORTED, "umnn tc: resident weights need %zu B of shared memory (> 227 KB); use the strict kernel", smem);
+  return 0;
+}
+
+struct TcPackArgs {
+  const float* W[GNF_MAX_LAYERS];
+  const float* b[GNF_MAX_LAYERS];
+  size_t off[GNF_MAX_LAYERS], off_bias, off_wlast;
+  int dims[GNF_MAX_LAYERS + 1], kp[GNF_MAX_LAYERS];
+  int L, NP;
+};
+
+// Canonical K-major / no-swizzle image of layer l:  img[(k/4)][n][k%4] = W[n][k]  (zero padded)
+__global__ void umnn_tc_pack_kernel(TcPackArgs a, float* __restrict__ ws, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i >= a.off_wlast) {
+      const int k = (int)(i - a.off_wlast);
+      if (k < a.dims[a.L]) v = a.W[a.L][k];
+    } else if (i >= a.off_bias) {
+      const int e = (int)(i - a.off_bias);
+      const int l = e / a.NP, n = e % a.NP;
+      if (n < a.dims[l + 1]) v = a.b[l][n];
+    } else {
+      int l = 0;
+      while (l + 1 < a.L && i >= a.off[l + 1]) ++l;
+      const size_t e = i - a.off[l];
+      const int kc = (int)(e / ((size_t)a.NP * 4)), n = (int)((e / 4) % a.NP), kk = (int)(e % 4);
+      const int k = kc * 4 + kk;
+      if (n < a.dims[l + 1] && k < a.dims[l]) v = a.W[l][(size_t)n * a.dims[l] + k];
+    }
+    ws[i] = v;
+  }
+}
+
+struct TcFwdParams {
+  const float* x; const float* h; const float* ccw; const float* ccn; const float* image; const float* blast;
+  float* z; float* zrev; float* jac; float* logdet;
+  int R, d, E, S, L, alloc_cols;
+  long long Q;
+  int kp[GNF_MAX_LAYERS];
+  unsigned off[GNF_MAX_LAYERS];     // float offsets inside the image
+  unsigned off_bias, off_wlast, total_floats;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(kTcRows) umnn_fwd_tc_kernel(TcFwdParams p) {
+  using namespace tc;
+  GNF_SMEM(float, smem);
+  float* img = smem;                                                        // weight images + bias + wlast
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((p.total_floats + 3) / 4) * 4);   // [0]: weights landed, [1]: MMA done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* red = reinterpret_cast<float*>(bars + 4);                          // [128]
+  const int t = threadIdx.x, warp = t >> 5;
+  const int nodes = p.S + 1;
+
+  if (warp == 0) tmem_alloc(tmem_slot, p.alloc_cols);
+  if (t == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t tA = tmem_base + lane_sel;             // activations: columns [0, NP)
+  const uint32_t tD = tmem_base + lane_sel + NP;        // accumulator: columns [NP, 2NP)
+
+  if (t == 0) {
+    const uint32_t bytes = p.total_floats * 4u;
+    mbar_expect_tx(&bars[0], bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u) {
+      const uint32_t n = (bytes - o < 32768u) ? bytes - o : 32768u;
+      bulk_g2s(reinterpret_cast<char*>(img) + o, reinterpret_cast<const char*>(p.image) + o, n, &bars[0]);
+    }
+  }
+  mbar_wait(&bars[0], 0);
+
+  const float* bias = img + p.off_bias;
+  const float* wlast = img + p.off_wlast;
+  const float blast = __ldg(p.blast);
+  constexpr uint32_t idesc = make_idesc_tf32(kTcRows, NP);
+  const uint32_t img_addr = smem_u32(img);
+  uint32_t phase = 0;
+  const long long ntiles = (p.Q + kTcRows - 1) / kTcRows;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long q = tile * kTcRows + t;
+    const bool valid = q < p.Q;
+    int r = 0, kn = 0;
+    float xv = 0.f;
+    if (valid) { r = (int)(q / nodes); kn = (int)(q % nodes); xv = __ldg(p.x + r); }
+    // ---- layer-0 input row [X, h_r, 0...] -> TMEM A region
+    for (int c = 0; c < p.kp[0]; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = c + j;
+        float val = 0.f;
+        if (valid) {
+          if (k == 0) val = (xv * (__ldg(p.ccn + kn) + 1.f)) / 2.f;
+          else if (k <= p.E) val = __ldg(p.h + (size_t)r * p.E + (k - 1));
+        }
+        v[j] = val;
+      }
+      tmem_st8(tA + c, v);
+    }
+    tmem_wait_st();
+    fence_before_sync();
+    __syncthreads();
+
+    float y = 0.f;
+    for (int l = 0; l < p.L; ++l) {
+      if (t == 0) {
+        fence_after_sync();
+        const uint32_t wbase = img_addr + p.off[l] * 4u;
+        const int nk = p.kp[l] / 8;
+        for (int ks = 0; ks < nk; ++ks) {
+          // B: [k/4][n][k%4] image -> lbo (between 16-byte K chunks) = NP*16, sbo (between 8-row groups) = 128
+          const uint64_t bdesc = make_smem_desc(wbase + (uint32_t)ks * 2u * NP * 16u, NP * 16u, 128u);
+          mma_tf32_ts(tmem_base + NP, tmem_base + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+        }
+        mma_commit(&bars[1]);
+      }
+      mbar_wait(&bars[1], phase);
+      phase ^= 1u;
+      fence_after_sync();
+      const float* bl = bias + l * NP;
+      if (l + 1 < p.L) {
+#pragma unroll 1
+        for (int c = 0; c < NP; c += 16) {
+          float v[16];
+          tmem_ld16(tD + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + bl[c + j], 0.f);
+          tmem_st16(tA + c, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        __syncthreads();
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NP; c += 16) {
+          float v[16];
+          tmem_ld16(tD + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y = fmaf(fmaxf(v[j] + bl[c + j], 0.f), wlast[c + j], y);
+        }
+        y += blast;
+      }
+    }
+    // ---- integrand value, CC-weighted segment sums (same epilogue as the strict kernel)
+    const float f = (y > 0.f ? y : expm1f(y)) + 1.05f;
+    float wv = 0.f;
+    if (valid) {
+      wv = __ldg(p.ccw + kn) * f;
+      if (kn == 0) {
+        p.jac[r] = f;
+        if (p.logdet) atomicAdd(p.logdet + r / p.d, logf(f));
+      }
+    }
+    red[t] = wv;
+    fence_before_sync();
+    __syncthreads();
+    if (valid && (kn == 0 || t == 0)) {
+      float s = 0.f;
+      int rem = nodes - kn;
+      if (rem > kTcRows - t) rem = kTcRows - t;
+      for (int i = 0; i < rem; ++i) s += red[t + i];
+      float c = s * xv / 2.f;
+      if (kn == 0) c += __ldg(p.h + (size_t)r * p.E);
+      atomicAdd(p.z + r, c);
+      if (p.zrev) { const int b = r / p.d, i = r % p.d; atomicAdd(p.zrev + (size_t)b * p.d + (p.d - 1 - i), c); }
+    }
+    __syncthreads();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, p.alloc_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test kernel: C[128, N] = A[128, K] * W[N, K]^T with one CTA, TS (A via TMEM) or SS (A via smem) form.
+// Exercises exactly the descriptor / TMEM-layout conventions the fused kernel relies on.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C, int N, int K, int NPc, int KP, int alloc_cols, int ss_mode) {
+  using namespace tc;
+  GNF_SMEM(float, smem);
+  float* wimg = smem;                                   // [KP/4][NPc][4]
+  float* aimg = wimg + (size_t)KP * NPc;                // [KP/4][128][4]  (SS mode)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aimg + (size_t)KP * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) tmem_alloc(tmem_slot, alloc_cols);
+  if (t == 0) { mbar_init(&bars[0], 1); fence_mbar_init(); }
+  for (int i = t; i < KP * NPc; i += 128) {
+    const int kc = i / (NPc * 4), n = (i / 4) % NPc, kk = i % 4, k = kc * 4 + kk;
+    wimg[i] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+  }
+  for (int i = t; i < KP * 128; i += 128) {
+    const int kc = i / (128 * 4), row = (i / 4) % 128, kk = i % 4, k = kc * 4 + kk;
+    aimg[i] = (k < K) ? A[(size_t)row * K + k] : 0.f;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t colA = 0, colD = 256;                  // A columns [0, KP), D columns [256, 256+NPc)
+  if (!ss_mode) {
+    for (int c = 0; c < KP; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < K) ? A[(size_t)t * K + c + j] : 0.f;
+      tmem_st8(tmem_base + lane_sel + colA + c, v);
+    }
+    tmem_wait_st();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (t == 0) {
+    fence_after_sync();
+    const uint32_t idesc = make_idesc_tf32(128, NPc);
+    for (int ks = 0; ks < KP / 8; ++ks) {
+      const uint64_t bdesc = make_smem_desc(smem_u32(wimg) + (uint32_t)ks * 2u * NPc * 16u, NPc * 16u, 128u);
+      if (ss_mode) {
+        const uint64_t adesc = make_smem_desc(smem_u32(aimg) + (uint32_t)ks * 2u * 128u * 16u, 128u * 16u, 128u);
+        mma_tf32_ss(tmem_base + colD, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+      } else {
+        mma_tf32_ts(tmem_base + colD, tmem_base + colA + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+      }
+    }
+    mma_commit(&bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  fence_after_sync();
+  for (int c = 0; c < NPc; c += 16) {
+    float v[16];
+    tmem_ld16(tmem_base + lane_sel + colD + c, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c + j < N) C[(size_t)t * N + c + j] = v[j];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, alloc_cols);
+}
+
+template <int NP>
+static int launch_tc_fwd(const TcFwdParams& p, size_t smem, cudaStream_t s) {
+  cudaFuncSetAttribute(umnn_fwd_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long ntiles = (p.Q + kTcRows - 1) / kTcRows;
+  long long grid = kNumSMs;
+  if (grid > ntiles) grid = ntiles;
+  GNF_LAUNCH(umnn_fwd_tc_kernel<NP>, (unsigned)grid, kTcRows, smem, s, p);
+  return 0;
+}
+
+}  // namespace gnf
+using namespace gnf;
+#endif  // !GNF_EMU
+
+extern "C" {
+
+size_t gnf_umnn_tc_workspace_bytes(const gnf_mlp_t* net) {
+#ifdef GNF_EMU
+  (void)net;
+  gnf::set_error("tensor-core kernels have no host-simulator flavour");
+  return 0;
+#else
+  TcPlan pl;
+  if (make_tc_plan(net, &pl)) return 0;
+  return pl.total_floats * sizeof(float);
+#endif
+}
+
+int gnf_umnn_fwd_tc(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn, float* z,
+                    float* zrev, float* jac, float* logdet, int R, int d, void* work, size_t work_bytes, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!x || !h || !net || !ccw || !ccn || !z || !jac || R < 0 || d <= 0 || S < 1 || (R % d) != 0) return fail(GNF_ERR_INVALID, "gnf_umnn_fwd_tc: bad arguments");
+  TcPlan pl;
+  if (int e = make_tc_plan(net, &pl)) return e;
+  if (!work || work_bytes < pl.total_floats * sizeof(float)) return fail(GNF_ERR_WORKSPACE, "gnf_umnn_fwd_tc: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(work) & 15) != 0) return fail(GNF_ERR_INVALID, "gnf_umnn_fwd_tc: workspace must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (R == 0) return 0;
+  TcPackArgs a;
+  for (int l = 0; l < GNF_MAX_LAYERS; ++l) { a.W[l] = nullptr; a.b[l] = nullptr; a.off[l] = 0; a.kp[l] = 0; }
+  for (int l = 0; l <= pl.L; ++l) { a.W[l] = net->W[l]; a.b[l] = net->b[l]; }
+  for (int l = 0; l < pl.L; ++l) { a.off[l] = pl.off[l]; a.kp[l] = pl.kp[l]; }
+  a.off_bias = pl.off_bias; a.off_wlast = pl.off_wlast;
+  for (int l = 0; l <= net->n_layers; ++l) a.dims[l] = net->dims[l];
+  a.L = pl.L; a.NP = pl.NP;
+  int blocks = (int)((pl.total_floats + 255) / 256);
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  GNF_LAUNCH(umnn_tc_pack_kernel, blocks, 256, 0, s, a, (float*)work, pl.total_floats);
+  cudaMemsetAsync(z, 0, (size_t)R * sizeof(float), s);
+  if (zrev) cudaMemsetAsync(zrev, 0, (size_t)R * sizeof(float), s);
+  if (logdet) cudaMemsetAsync(logdet, 0, (size_t)(R / d) * sizeof(float), s);
+  TcFwdParams p;
+  p.x = x; p.h = h; p.ccw = ccw; p.ccn = ccn; p.image = (const float*)work; p.blast = net->b[pl.L];
+  p.z = z; p.zrev = zrev; p.jac = jac; p.logdet = logdet;
+  p.R = R; p.d = d; p.E = net->dims[0] - 1; p.S = S; p.L = pl.L; p.alloc_cols = pl.alloc_cols;
+  p.Q = (long long)R * (S + 1);
+  for (int l = 0; l < GNF_MAX_LAYERS; ++l) { p.kp[l] = l < pl.L ? pl.kp[l] : 0; p.off[l] = l < pl.L ? (unsigned)pl.off[l] : 0; }
+  p.off_bias = (unsigned)pl.off_bias; p.off_wlast = (unsigned)pl.off_wlast; p.total_floats = (unsigned)pl.total_floats;
+  const size_t smem = ((pl.total_floats + 3) / 4 * 4) * sizeof(float) + 4 * sizeof(uint64_t) + kTcRows * sizeof(float);
+  int e = 0;
+  switch (pl.NP) {
+    case 16: e = launch_tc_fwd<16>(p, smem, s); break;
+    case 32: e = launch_tc_fwd<32>(p, smem, s); break;
+    case 48: e = launch_tc_fwd<48>(p, smem, s); break;
+    case 64: e = launch_tc_fwd<64>(p, smem, s); break;
+    case 80: e = launch_tc_fwd<80>(p, smem, s); break;
+    case 96: e = launch_tc_fwd<96>(p, smem, s); break;
+    case 112: e = launch_tc_fwd<112>(p, smem, s); break;
+    case 128: e = launch_tc_fwd<128>(p, smem, s); break;
+    case 144: e = launch_tc_fwd<144>(p, smem, s); break;
+    case 160: e = launch_tc_fwd<160>(p, smem, s); break;
+    case 176: e = launch_tc_fwd<176>(p, smem, s); break;
+    case 192: e = launch_tc_fwd<192>(p, smem, s); break;
+    case 208: e = launch_tc_fwd<208>(p, smem, s); break;
+    case 224: e = launch_tc_fwd<224>(p, smem, s); break;
+    case 240: e = launch_tc_fwd<240>(p, smem, s); break;
+    default: e = launch_tc_fwd<256>(p, smem, s); break;
+  }
+  if (e) return e;
+  return check_launch("gnf_umnn_fwd_tc");
+#endif
+}
+
+/* C[128,N] = A[128,K] W[N,K]^T on one CTA through tcgen05 (mode 0: A staged in TMEM, mode 1: A in shared memory). */
+int gnf_tc_selftest(const float* A, const float* W, float* C, int N, int K, int mode, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!A || !W || !C || N < 1 || N > 256 || K < 1 || K > 256) return fail(GNF_ERR_INVALID, "gnf_tc_selftest: bad arguments");
+  const int NPc = round_up(N, 16), KP = round_up(K, 8);
+  const size_t smem = ((size_t)KP * NPc + (size_t)KP * 128) * sizeof(float) + 64;
+  if (smem > 227 * 1024) return fail(GNF_ERR_UNSUPPORTED, "gnf_tc_selftest: too large");
+  cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  GNF_LAUNCH(tc_selftest_kernel, 1, 128, smem, (cudaStream_t)stream, A, W, C, N, K, NPc, KP, 512, mode);
+  return check_launch("gnf_tc_selftest");
+#endif
+}
+
+}  // extern "C"

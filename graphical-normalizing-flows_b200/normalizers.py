@@ -78,7 +78,7 @@ class IntegrandNet(nn.Module):
         UMNN kernel's Jacobian output (node 0 of the quadrature is the upper limit x itself)."""
         N, d = x.shape
         h3 = h.view(N, -1, d).permute(0, 2, 1).contiguous()
-        _, jac, _, _ = ops.UmnnFn.apply(x.contiguous(), h3, 1, False, *self.linear_params())
+        _, jac, _, _ = ops.UmnnFn.apply(x.contiguous(), h3, 1, False, False, *self.linear_params())
         return jac
 
 
@@ -94,13 +94,18 @@ class MonotonicNormalizer(Normalizer):
                                       "covered by the fused UMNN kernel; there is no eager fallback")
         self.solver = solver
         self.nb_steps = nb_steps
+        # "strict": fp32 FFMA kernels (ll 1e-4, gradients 1e-3).  "tf32": forward on the tensor cores with
+        # single-pass TF32 operands (ll 2e-3); gradients still come from the strict backward kernel.
+        self.precision = "strict"
 
     def forward_fused(self, x, h, want_rev=False):
         if self.solver not in ("CC", "CCParallel"):
             return None
         # "CC" (sequential) and "CCParallel" (batched) are the same quadrature; one kernel serves both.
+        if self.precision not in ("strict", "tf32"):
+            raise ValueError(f"MonotonicNormalizer.precision must be 'strict' or 'tf32', got {self.precision!r}")
         z, jac, logdet, zrev = ops.UmnnFn.apply(x.contiguous(), h.contiguous(), int(self.nb_steps), want_rev,
-                                                *self.integrand_net.linear_params())
+                                                self.precision == "tf32", *self.integrand_net.linear_params())
         return z, jac, logdet, (zrev if want_rev else None)
 
     def forward(self, x, h, context=None):

@@ -512,11 +512,12 @@ def _mlp_struct(weights, biases):
 
 class UmnnFn(torch.autograd.Function):
     """MonotonicNormalizer.forward (MonotonicNormalizer.py:51-66) = UMNN (Parallel)NeuralIntegral + h[...,0]
-    and the Jacobian evaluation, fused.  forward(x [B,d], h [B,d,E], S, want_rev, *params)
-    -> (z, jac, logdet, zrev)."""
+    and the Jacobian evaluation, fused.  forward(x [B,d], h [B,d,E], S, want_rev, fast, *params)
+    -> (z, jac, logdet, zrev).  fast=True runs the forward on the tensor cores (single-pass TF32, ll tolerance
+    2e-3); the backward always uses the strict fp32 kernel."""
 
     @staticmethod
-    def forward(ctx, x, h, S, want_rev, *params):
+    def forward(ctx, x, h, S, want_rev, fast, *params):
         require(x, "x"), require(h, "h")
         weights = [require(_contig(p), "weight") for p in params[0::2]]
         biases = [require(_contig(p), "bias") for p in params[1::2]]
@@ -526,7 +527,7 @@ class UmnnFn(torch.autograd.Function):
             raise ValueError(f"integrand expects {weights[0].shape[1] - 1} conditioning features, h has {E}")
         R = B * d
         net = _mlp_struct(weights, biases)
-        nbytes = lib().gnf_umnn_workspace_bytes(C.byref(net))
+        nbytes = (lib().gnf_umnn_tc_workspace_bytes if fast else lib().gnf_umnn_workspace_bytes)(C.byref(net))
         if nbytes == 0:
             raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
         ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
@@ -535,7 +536,7 @@ class UmnnFn(torch.autograd.Function):
         jac = torch.empty_like(x)
         zrev = torch.empty_like(x) if want_rev else None
         logdet = torch.empty(B, device=x.device, dtype=x.dtype)
-        _call("gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac), ptr(logdet),
+        _call("gnf_umnn_fwd_tc" if fast else "gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac), ptr(logdet),
                                  R, d, ptr(ws), nbytes, stream_ptr())
         _count(2)
         ctx.save_for_backward(x, h, jac, *weights, *biases)
@@ -573,7 +574,16 @@ class UmnnFn(torch.autograd.Function):
         _call("gnf_umnn_bwd", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev), ptr(gjac),
                                  ptr(glogdet), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr())
         _count(2)
-        out = [dx, dh, None, None]
+        out = [dx, dh, None, None, None]
         for l in range(n):
             out += [dWs[l], dbs[l]]
         return tuple(out)
+
+
+def tc_selftest(A, W, mode):
+    """C = A @ W^T for A [128,K], W [N,K] through one tcgen05 CTA (mode 0: A in TMEM, 1: A in shared memory)."""
+    require(A, "A"), require(W, "W")
+    Cm = torch.empty(128, W.shape[0], device=A.device, dtype=A.dtype)
+    _call("gnf_tc_selftest", ptr(A), ptr(W), ptr(Cm), W.shape[0], W.shape[1], int(mode), stream_ptr())
+    _count()
+    return Cm

@@ -191,6 +191,18 @@ int gnf_umnn_bwd(const float* x, const float* h, const gnf_mlp_t* net, int S, co
                  float* dx, float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work, size_t work_bytes,
                  gnf_stream_t stream);
 
+/* Tensor-core ("fast", single-pass TF32 operands / fp32 TMEM accumulation) forward of the same integral:
+ * tcgen05.mma with the activation chain resident in TMEM and all weights resident in shared memory.
+ * Same arguments and outputs as gnf_umnn_fwd; per-sample log-likelihood tolerance 2e-3 (north_star's
+ * TF32 bar).  Returns GNF_ERR_UNSUPPORTED when the integrand's weights do not fit in shared memory. */
+size_t gnf_umnn_tc_workspace_bytes(const gnf_mlp_t* net);
+int gnf_umnn_fwd_tc(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
+                    float* z, float* zrev, float* jac, float* logdet, int R, int d, void* work, size_t work_bytes,
+                    gnf_stream_t stream);
+/* Self-test of the tcgen05 conventions: C[128,N] = A[128,K] W[N,K]^T on one CTA (mode 0: A staged in TMEM,
+ * mode 1: A staged in shared memory).  N, K <= 256. */
+int gnf_tc_selftest(const float* A, const float* W, float* C, int N, int K, int mode, gnf_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------
  * Small elementwise helpers used by the host side
  * ------------------------------------------------------------------------------------------ */

@@ -1,0 +1,79 @@
+"""GPU tests of the tcgen05 (tensor-core) path: the UMMA descriptor / TMEM-layout conventions via the one-CTA
+self-test GEMM, then the fused TF32 UMNN forward against the strict fp32 kernel and the CPU oracle.
+Tolerance: north_star's TF32 bar — per-sample log-likelihood within 2e-3 relative."""
+import pytest
+import torch
+
+import gnf_b200 as G
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("N,K", [(16, 8), (160, 32), (160, 152), (112, 104), (208, 200), (256, 256), (30, 31)])
+def test_tcgen05_selftest_gemm_exact_on_tf32_representable_inputs(mode, N, K):
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + K + mode)
+    A = torch.randint(-8, 9, (128, K), device="cuda", generator=g).float()
+    W = torch.randint(-8, 9, (N, K), device="cuda", generator=g).float()
+    Cm = G.ops.tc_selftest(A, W, mode)
+    ref = A @ W.t()
+    assert torch.equal(Cm, ref), f"max err {float((Cm - ref).abs().max())}"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tcgen05_selftest_gemm_tf32_accuracy(mode):
+    A = torch.randn(128, 152, device="cuda")
+    W = torch.randn(160, 152, device="cuda") / 152 ** .5
+    Cm = G.ops.tc_selftest(A, W, mode)
+    ref = (A.double() @ W.double().t()).float()
+    assert float((Cm - ref).abs().max()) < 5e-3          # 10-bit mantissa operands, fp32 accumulation
+
+
+@pytest.mark.parametrize("cfg,B,S", [("cfg4", 100, 20), ("cfg4", 7, 40), ("cfg2", 500, 40), ("cfg2", 3, 7)])
+def test_umnn_tensorcore_forward_matches_strict(cfg, B, S):
+    import model_vs_oracle as M
+    model = M.build(M.CONFIGS[cfg], "cuda")
+    parity.set_modes(model, dict(stoch_gate=False))
+    for n in model.getNormalizers():
+        n.nb_steps = S
+    x = torch.randn(B, M.CONFIGS[cfg]["d"], device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
+    with torch.no_grad():
+        ll_s, z_s = model.compute_ll(x)
+        for n in model.getNormalizers():
+            n.precision = "tf32"
+        ll_f, z_f = model.compute_ll(x)
+    rel = float(((ll_f - ll_s).abs() / ll_s.abs().clamp_min(1e-6)).max())
+    assert rel < 2e-3, f"per-sample ll relative error {rel}"
+    assert float((z_f - z_s).abs().max()) < 5e-3
+
+
+def test_umnn_tensorcore_forward_vs_oracle_and_strict_backward():
+    """fast forward + strict backward still trains: ll within the TF32 bar of the CPU oracle, gradients finite and
+    close to the strict ones (they are the strict kernel's gradients of the same weights)."""
+    import model_vs_oracle as M
+    spec = M.CONFIGS["cfg2"]
+    model = M.build(spec, "cuda")
+    parity.set_modes(model, dict(stoch_gate=False))
+    x = torch.randn(64, 6, device="cuda")
+    model.zero_grad()
+    z, jac = model(x)
+    model.loss(z, jac).backward()
+    g_strict = {k: p.grad.clone() for k, p in model.named_parameters()}
+    for n in model.getNormalizers():
+        n.precision = "tf32"
+    model.zero_grad()
+    z2, jac2 = model(x)
+    model.loss(z2, jac2).backward()
+    assert float((z - z2).abs().max()) < 5e-3
+    for k, p in model.named_parameters():
+        assert torch.isfinite(p.grad).all()
+        if "integrand_net" in k:
+            assert float((p.grad - g_strict[k]).norm() / g_strict[k].norm().clamp_min(1e-12)) < 5e-2, k
+
+
+def test_tensorcore_unsupported_width_is_loud():
+    n = G.MonotonicNormalizer([200, 200, 200], 30).cuda()      # 2 x 208 x 200 fp32 weights do not fit in 227 KB
+    n.precision = "tf32"
+    with pytest.raises(RuntimeError):
+        n(torch.randn(4, 3, device="cuda"), torch.randn(4, 3, 30, device="cuda"))
