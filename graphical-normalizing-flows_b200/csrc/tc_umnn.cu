@@ -233,6 +233,206 @@ __global__ void __launch_bounds__(kTcRows) umnn_fwd_tc_kernel(TcFwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// v2: two tiles in flight per CTA, three rotating TMEM regions.
+//
+// Warpgroup g (128 threads) owns the CTA's tiles of parity g.  The tensor pipe executes the MMAs of the two
+// tiles alternately (global MMA sequence m = 0,1,2,...; m % 2 = warpgroup); while tile X's layer runs on the
+// tensor cores, tile Y's epilogue (TMEM -> registers -> bias/ReLU -> TMEM, IN PLACE) runs on the CUDA cores.
+// With the in-place epilogue a tile needs two regions only while its MMA runs (A and D) and one otherwise, so
+// three NP-column regions suffice:   A(m) = m % 3,  D(m) = (m + 2) % 3   (D(m) is the region freed by MMA m-1).
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p) {
+  using namespace tc;
+  GNF_SMEM(float, smem);
+  float* img = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((p.total_floats + 3) / 4) * 4);   // [0]: weights, [1],[2]: MMA done (wg 0/1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* red_all = reinterpret_cast<float*>(bars + 4);                                   // [2][128]
+  const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5;
+  float* red = red_all + g * kTcRows;
+  const int nodes = p.S + 1;
+  const int L = p.L;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+
+  if (tid == 0) {
+    const uint32_t bytes = p.total_floats * 4u;
+    mbar_expect_tx(&bars[0], bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u) {
+      const uint32_t n = (bytes - o < 32768u) ? bytes - o : 32768u;
+      bulk_g2s(reinterpret_cast<char*>(img) + o, reinterpret_cast<const char*>(p.image) + o, n, &bars[0]);
+    }
+  }
+  mbar_wait(&bars[0], 0);
+
+  const float* bias = img + p.off_bias;
+  const float* wlast = img + p.off_wlast;
+  const float blast = __ldg(p.blast);
+  constexpr uint32_t idesc = make_idesc_tf32(kTcRows, NP);
+  const uint32_t img_addr = smem_u32(img);
+  const long long ntiles = (p.Q + kTcRows - 1) / kTcRows;
+  // CTA-local tiles c = 0,1,..: global tile blockIdx.x + c*gridDim.x; both warpgroups run the same number of
+  // iterations (a warpgroup without a tile processes an all-invalid one) so the MMA hand-shake never stalls.
+  const long long cta_tiles = (ntiles > (long long)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long n_local = (cta_tiles + 1) / 2;
+  const int K0P = p.kp[0];
+
+  // per-thread description of the current tile row, and prefetched input of the next tile
+  bool valid = false; int r = 0, kn = 0; float xv = 0.f;
+  float pre[32];
+  auto load_tile_row = [&](long long c_local) {
+    const long long c = 2 * c_local + g;
+    const long long q = (c < cta_tiles) ? ((long long)blockIdx.x + c * gridDim.x) * kTcRows + t : p.Q;
+    valid = q < p.Q;
+    r = 0; kn = 0; xv = 0.f;
+    if (valid) { r = (int)(q / nodes); kn = (int)(q % nodes); xv = __ldg(p.x + r); }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float val = 0.f;
+      if (valid && k < K0P) {
+        if (k == 0) val = (xv * (__ldg(p.ccn + kn) + 1.f)) / 2.f;
+        else if (k <= p.E) val = __ldg(p.h + (size_t)r * p.E + (k - 1));
+      }
+      pre[k] = val;
+    }
+  };
+  auto store_input = [&](uint32_t region_addr) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      if (c < K0P) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = pre[c + j];
+        tmem_st8(region_addr + c, v);
+      }
+    }
+  };
+
+  // prologue: first tile's input into region A(m = g) = g
+  load_tile_row(0);
+  store_input(tmem_base + lane_sel + (uint32_t)(g % 3) * NP);
+  tmem_wait_st();
+  fence_before_sync();
+  named_bar_sync(1 + g, kTcRows);
+
+  const long long n_iter = n_local * L;
+  for (long long i = 0; i < n_iter; ++i) {
+    const int layer = (int)(i % L);
+    const long long m = 2 * i + g;
+    const uint32_t rA = (uint32_t)(m % 3) * NP, rD = (uint32_t)((m + 2) % 3) * NP;
+    if (t == 0) {
+      if (m > 0) {   // the region we are about to overwrite as D is the A operand of MMA m-1 (other warpgroup)
+        const long long io = (g == 1) ? i : i - 1;
+        mbar_wait(&bars[1 + (1 - g)], (uint32_t)(io & 1));
+      }
+      fence_after_sync();
+      const uint32_t wbase = img_addr + p.off[layer] * 4u;
+      const int nk = p.kp[layer] / 8;
+      for (int ks = 0; ks < nk; ++ks) {
+        const uint64_t bdesc = make_smem_desc(wbase + (uint32_t)ks * 2u * NP * 16u, NP * 16u, 128u);
+        mma_tf32_ts(tmem_base + rD, tmem_base + rA + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+      }
+      mma_commit(&bars[1 + g]);
+    }
+    // what this thread needs after the last layer: its own row's result context, then the next tile's input
+    bool cur_valid = valid; int cur_r = r, cur_kn = kn; float cur_xv = xv;
+    if (layer == L - 1) load_tile_row(i / L + 1);      // prefetch while the tensor cores work
+    mbar_wait(&bars[1 + g], (uint32_t)(i & 1));
+    fence_after_sync();
+    const uint32_t R = tmem_base + lane_sel + rD;
+    const float* bl = bias + layer * NP;
+    if (layer < L - 1) {
+      uint32_t cur[16], nxt[16];
+      tmem_ld16_nowait(R, cur);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < NP; c += 16) {
+        if (c + 16 < NP) tmem_ld16_nowait(R + c + 16, nxt);
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bl + c + j4);
+          cur[j4 + 0] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 0]) + b4.x, 0.f));
+          cur[j4 + 1] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 1]) + b4.y, 0.f));
+          cur[j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 2]) + b4.z, 0.f));
+          cur[j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 3]) + b4.w, 0.f));
+        }
+        tmem_st16u(R + c, cur);
+        if (c + 16 < NP) {
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+        }
+      }
+    } else {
+      float y = 0.f;
+      uint32_t cur[16], nxt[16];
+      tmem_ld16_nowait(R, cur);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < NP; c += 16) {
+        if (c + 16 < NP) tmem_ld16_nowait(R + c + 16, nxt);
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bl + c + j4);
+          const float4 w4 = *reinterpret_cast<const float4*>(wlast + c + j4);
+          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 0]) + b4.x, 0.f), w4.x, y);
+          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 1]) + b4.y, 0.f), w4.y, y);
+          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 2]) + b4.z, 0.f), w4.z, y);
+          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 3]) + b4.w, 0.f), w4.w, y);
+        }
+        if (c + 16 < NP) {
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+        }
+      }
+      y += blast;
+      const float f = (y > 0.f ? y : expm1f(y)) + 1.05f;
+      float wv = 0.f;
+      if (cur_valid) {
+        wv = __ldg(p.ccw + cur_kn) * f;
+        if (cur_kn == 0) {
+          p.jac[cur_r] = f;
+          if (p.logdet) atomicAdd(p.logdet + cur_r / p.d, logf(f));
+        }
+      }
+      red[t] = wv;
+      named_bar_sync(1 + g, kTcRows);
+      if (cur_valid && (cur_kn == 0 || t == 0)) {
+        float s = 0.f;
+        int rem = nodes - cur_kn;
+        if (rem > kTcRows - t) rem = kTcRows - t;
+        for (int k = 0; k < rem; ++k) s += red[t + k];
+        float c = s * cur_xv / 2.f;
+        if (cur_kn == 0) c += __ldg(p.h + (size_t)cur_r * p.E);
+        atomicAdd(p.z + cur_r, c);
+        if (p.zrev) { const int b = cur_r / p.d, ii = cur_r % p.d; atomicAdd(p.zrev + (size_t)b * p.d + (p.d - 1 - ii), c); }
+      }
+      // next tile's input row, in place in this region (its A for MMA m+2)
+      store_input(R);
+    }
+    tmem_wait_st();
+    fence_before_sync();
+    named_bar_sync(1 + g, kTcRows);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Self-test kernel: C[128, N] = A[128, K] * W[N, K]^T with one CTA, TS (A via TMEM) or SS (A via smem) form.
 // Exercises exactly the descriptor / TMEM-layout conventions the fused kernel relies on.
 // ------------------------------------------------------------------------------------------------
@@ -302,8 +502,19 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
 
 template <int NP>
 static int launch_tc_fwd(const TcFwdParams& p, size_t smem, cudaStream_t s) {
-  cudaFuncSetAttribute(umnn_fwd_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long ntiles = (p.Q + kTcRows - 1) / kTcRows;
+  if constexpr (3 * NP <= 512) {
+    // two tiles in flight need 3 regions of NP columns and the next tile's input prefetched in 32 registers
+    if (p.kp[0] <= 32 && smem + kTcRows * sizeof(float) + 64 <= 227 * 1024) {
+      const size_t smem2 = smem + kTcRows * sizeof(float) + 64;
+      cudaFuncSetAttribute(umnn_fwd_tc2_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      long long grid = kNumSMs;
+      if (grid > (ntiles + 1) / 2) grid = (ntiles + 1) / 2;
+      GNF_LAUNCH(umnn_fwd_tc2_kernel<NP>, (unsigned)grid, 2 * kTcRows, smem2, s, p);
+      return 0;
+    }
+  }
+  cudaFuncSetAttribute(umnn_fwd_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long grid = kNumSMs;
   if (grid > ntiles) grid = ntiles;
   GNF_LAUNCH(umnn_fwd_tc_kernel<NP>, (unsigned)grid, kTcRows, smem, s, p);

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("N,K", [(16, 8), (160, 32), (160, 152), (112, 104), (208, 200), (256, 256), (30, 31)])
+@pytest.mark.parametrize("N,K", [(16, 8), (160, 32), (160, 152), (112, 104), (208, 96), (256, 64), (30, 31)])
 def test_tcgen05_selftest_gemm_exact_on_tf32_representable_inputs(mode, N, K):
     g = torch.Generator(device="cuda").manual_seed(N * 1000 + K + mode)
     A = torch.randint(-8, 9, (128, K), device="cuda", generator=g).float()
