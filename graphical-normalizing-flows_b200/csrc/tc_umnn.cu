@@ -353,51 +353,36 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
     fence_after_sync();
     const uint32_t R = tmem_base + lane_sel + rD;
     const float* bl = bias + layer * NP;
+    // whole accumulator row -> registers in one burst (NP/16 loads in flight, one wait)
+    uint32_t v[NP];
+#pragma unroll
+    for (int c = 0; c < NP; c += 16) tmem_ld16p(R + c, &v[c]);
+    tmem_wait_ld();
     if (layer < L - 1) {
-      uint32_t cur[16], nxt[16];
-      tmem_ld16_nowait(R, cur);
-      tmem_wait_ld();
 #pragma unroll
       for (int c = 0; c < NP; c += 16) {
-        if (c + 16 < NP) tmem_ld16_nowait(R + c + 16, nxt);
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bl + c + j4);
-          cur[j4 + 0] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 0]) + b4.x, 0.f));
-          cur[j4 + 1] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 1]) + b4.y, 0.f));
-          cur[j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 2]) + b4.z, 0.f));
-          cur[j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 3]) + b4.w, 0.f));
+          v[c + j4 + 0] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 0]) + b4.x, 0.f));
+          v[c + j4 + 1] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 1]) + b4.y, 0.f));
+          v[c + j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 2]) + b4.z, 0.f));
+          v[c + j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 3]) + b4.w, 0.f));
         }
-        tmem_st16u(R + c, cur);
-        if (c + 16 < NP) {
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
-        }
+        tmem_st16p(R + c, &v[c]);
       }
     } else {
-      float y = 0.f;
-      uint32_t cur[16], nxt[16];
-      tmem_ld16_nowait(R, cur);
-      tmem_wait_ld();
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < NP; c += 16) {
-        if (c + 16 < NP) tmem_ld16_nowait(R + c + 16, nxt);
-#pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bl + c + j4);
-          const float4 w4 = *reinterpret_cast<const float4*>(wlast + c + j4);
-          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 0]) + b4.x, 0.f), w4.x, y);
-          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 1]) + b4.y, 0.f), w4.y, y);
-          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 2]) + b4.z, 0.f), w4.z, y);
-          y = fmaf(fmaxf(__uint_as_float(cur[j4 + 3]) + b4.w, 0.f), w4.w, y);
-        }
-        if (c + 16 < NP) {
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
-        }
+      for (int c = 0; c < NP; c += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bl + c);
+        const float4 w4 = *reinterpret_cast<const float4*>(wlast + c);
+        y0 = fmaf(fmaxf(__uint_as_float(v[c + 0]) + b4.x, 0.f), w4.x, y0);
+        y1 = fmaf(fmaxf(__uint_as_float(v[c + 1]) + b4.y, 0.f), w4.y, y1);
+        y2 = fmaf(fmaxf(__uint_as_float(v[c + 2]) + b4.z, 0.f), w4.z, y2);
+        y3 = fmaf(fmaxf(__uint_as_float(v[c + 3]) + b4.w, 0.f), w4.w, y3);
       }
+      float y = (y0 + y1) + (y2 + y3);
       y += blast;
       const float f = (y > 0.f ? y : expm1f(y)) + 1.05f;
       float wv = 0.f;
