@@ -193,6 +193,23 @@ class PowerTraceFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # Conditioner MLP engine
 # ----------------------------------------------------------------------------------------------
+_GEMM_PASSES = 0     # 0: fp32 FFMA engine; 1: tcgen05 single-pass TF32; 3: tcgen05 3xTF32 (fp32-equivalent)
+_GEMM_MODES = {"ffma": 0, "tf32": 1, "tf32x3": 3}
+
+
+def set_gemm_mode(mode):
+    """Select the conditioner-MLP GEMM engine: 'ffma' (fp32 CUDA cores), 'tf32x3' (tensor cores, fp32-equivalent
+    3xTF32 split: strict), 'tf32' (tensor cores, single pass: ll tolerance 2e-3, not for gradient parity)."""
+    global _GEMM_PASSES
+    if mode not in _GEMM_MODES:
+        raise ValueError(f"gemm mode must be one of {sorted(_GEMM_MODES)}")
+    _GEMM_PASSES = _GEMM_MODES[mode]
+
+
+def get_gemm_mode():
+    return {v: k for k, v in _GEMM_MODES.items()}[_GEMM_PASSES]
+
+
 def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=None):
     """Y = act(X[:, :K] @ W^T + bias).  X may be a row-strided view described by (ldx, K)."""
     M = X.shape[0]
@@ -202,8 +219,12 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
     if out is None:
         out = torch.empty(M, N, device=X.device, dtype=X.dtype)
         ldy = N
-    _call("gnf_linear_fwd", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
-                               stream_ptr())
+    if _GEMM_PASSES:
+        _call("gnf_linear_fwd_tc", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
+              _GEMM_PASSES, stream_ptr())
+    else:
+        _call("gnf_linear_fwd", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
+              stream_ptr())
     _count()
     return out
 
@@ -213,15 +234,22 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
     if out is None:
         out = torch.empty(M, K, device=dY.device, dtype=dY.dtype)
         lddx = K
-    _call("gnf_linear_dgrad", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
-                                 ptr(out), lddx, M, N, K, stream_ptr())
+    if _GEMM_PASSES:
+        _call("gnf_linear_dgrad_tc", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
+              ptr(out), lddx, M, N, K, _GEMM_PASSES, stream_ptr())
+    else:
+        _call("gnf_linear_dgrad", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
+              ptr(out), lddx, M, N, K, stream_ptr())
     _count()
     return out
 
 
 def linear_wgrad(dY, lddy, X, ldx, M, N, K):
     dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
-    _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr())
+    if _GEMM_PASSES:
+        _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, _GEMM_PASSES, stream_ptr())
+    else:
+        _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr())
     _count()
     return dW
 

@@ -99,6 +99,17 @@ int gnf_colsum(const float* Y, int ldy, float* out, int M, int N, int period, gn
 /* dY[m,n] *= (act[m,n] > 0)  — ReLU backward for a cotangent produced outside the engine. */
 int gnf_relu_mask(float* dY, int lddy, const float* act, int ldact, int M, int N, gnf_stream_t stream);
 
+/* The same three GEMMs on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in TMEM; warp-specialised
+ * persistent kernel, operands staged into 128B-swizzled UMMA tiles by producer warps).
+ *   passes = 1: single-pass TF32 (fast mode, log-likelihood tolerance 2e-3);
+ *   passes = 3: 3xTF32 hi/lo split, fp32-equivalent (strict mode: ll 1e-4, gradients 1e-3). */
+int gnf_linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, int bias_period, float* Y,
+                      int ldy, int M, int N, int K, int relu, int passes, gnf_stream_t stream);
+int gnf_linear_dgrad_tc(const float* dY, int lddy, const float* W, int ldw, const float* act, int ldact, float* dX,
+                        int lddx, int M, int N, int K, int passes, gnf_stream_t stream);
+int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
+                        int passes, gnf_stream_t stream);
+
 /* MaskedLinear's `mask * weight` (AutoregressiveConditioner.py:24-25) fused with the output-row
  * permutation that turns MADE's view(B,out,d).permute(0,2,1) (:108-109) into a plain row-major
  * h[b,i,k]:  out[r,k] = W[perm[r],k] * mask[perm[r],k]   (mask, perm nullable; perm int32 [R]). */

@@ -77,3 +77,71 @@ def test_tensorcore_unsupported_width_is_loud():
     n.precision = "tf32"
     with pytest.raises(RuntimeError):
         n(torch.randn(4, 3, device="cuda"), torch.randn(4, 3, 30, device="cuda"))
+
+
+# ---------------- tensor-core conditioner GEMM engine (tcgen05, 128B-swizzled producer-staged tiles) ----------------
+@pytest.fixture
+def gemm_mode():
+    yield G.ops.set_gemm_mode
+    G.ops.set_gemm_mode("ffma")
+
+
+SHAPES = [(1, 1, 1), (127, 33, 65), (300, 630, 126), (1000, 30, 630), (64, 2, 1024), (513, 210, 21), (6300, 630, 630),
+          (256, 1024, 784)]
+
+
+@pytest.mark.parametrize("M_,N,K", SHAPES)
+def test_tc_gemm_exact_on_small_integers(gemm_mode, M_, N, K):
+    """Integer-valued operands are exactly representable in TF32 and all partial sums in fp32: the single-pass
+    engine must reproduce fwd / dgrad / wgrad bit-exactly (checks tile staging, swizzle, both operand majors)."""
+    gemm_mode("tf32")
+    g = torch.Generator(device="cuda").manual_seed(M_ * 7 + N * 3 + K)
+    X = torch.randint(-3, 4, (M_, K), device="cuda", generator=g).float()
+    W = torch.randint(-3, 4, (N, K), device="cuda", generator=g).float()
+    b = torch.randint(-3, 4, (N,), device="cuda", generator=g).float()
+    dY = torch.randint(-3, 4, (M_, N), device="cuda", generator=g).float()
+    Y = G.ops.linear_fwd(X, W, b, relu=True)
+    assert torch.equal(Y, torch.relu(X @ W.t() + b)), float((Y - torch.relu(X @ W.t() + b)).abs().max())
+    dX = G.ops.linear_dgrad(dY, N, W, X, M_)
+    assert torch.equal(dX, (dY @ W) * (X > 0)), float((dX - (dY @ W) * (X > 0)).abs().max())
+    dW = G.ops.linear_wgrad(dY, N, X, K, M_, N, K)
+    ref = (dY.double().t() @ X.double()).float()
+    assert torch.equal(dW, ref), float((dW - ref).abs().max())
+
+
+@pytest.mark.parametrize("M_,N,K", SHAPES)
+def test_tc_gemm_3xtf32_is_fp32_equivalent(gemm_mode, M_, N, K):
+    gemm_mode("tf32x3")
+    g = torch.Generator(device="cuda").manual_seed(M_ + N + K)
+    X = torch.randn(M_, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** .5
+    b = torch.randn(N, device="cuda", generator=g)
+    dY = torch.randn(M_, N, device="cuda", generator=g)
+    Y = G.ops.linear_fwd(X, W, b, relu=True)
+    ref = torch.relu(X.double() @ W.double().t() + b.double()).float()
+    assert torch.allclose(Y, ref, rtol=2e-5, atol=2e-5), float((Y - ref).abs().max())
+    dX = G.ops.linear_dgrad(dY, N, W, X, M_)
+    refdX = ((dY.double() @ W.double()) * (X > 0)).float()
+    assert torch.allclose(dX, refdX, rtol=2e-5, atol=5e-5), float((dX - refdX).abs().max())
+    dW = G.ops.linear_wgrad(dY, N, X, K, M_, N, K)
+    refdW = (dY.double().t() @ X.double()).float()
+    assert float((dW - refdW).norm() / refdW.norm().clamp_min(1e-12)) < 2e-6
+
+
+def test_tc_gemm_single_pass_tf32_accuracy(gemm_mode):
+    gemm_mode("tf32")
+    X = torch.randn(2000, 630, device="cuda")
+    W = torch.randn(630, 630, device="cuda") / 630 ** .5
+    Y = G.ops.linear_fwd(X, W, None, relu=False)
+    ref = (X.double() @ W.double().t()).float()
+    assert float((Y - ref).norm() / ref.norm()) < 2e-3
+
+
+@pytest.mark.parametrize("cfg,B", [("cfg2", 256), ("cfg3", 48), ("cfg4", 12), ("cfg1", 100)])
+def test_train_step_vs_oracle_with_3xtf32_conditioner(gemm_mode, cfg, B):
+    """Strict bars (ll 1e-4, per-tensor gradients 1e-3) with the conditioner GEMMs on the tensor cores."""
+    import model_vs_oracle as M
+    gemm_mode("tf32x3")
+    rep = M.compare(M.CONFIGS[cfg], B, "cuda", train=True)
+    bad = {k: v for k, v in rep.items() if (k.startswith("grad.") and not v < 1e-3) or (k in ("ll", "loss") and not v < 1e-4)}
+    assert not bad, f"out of tolerance: {bad}\n{rep}"
