@@ -206,6 +206,8 @@ def main():
     ap.add_argument("--nb-steps", type=int, default=None, help="quadrature steps S (default 20 train / 40 eval)")
     ap.add_argument("--precision", default="strict", choices=["strict", "tf32"],
                     help="strict: fp32 FFMA kernels; tf32: tensor-core (tcgen05) UMNN forward, ll tolerance 2e-3")
+    ap.add_argument("--gemm", default="ffma", choices=["ffma", "tf32x3", "tf32"],
+                    help="conditioner GEMM engine: fp32 FFMA, tensor-core 3xTF32 (fp32-equivalent) or single-pass TF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -244,6 +246,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    G.ops.set_gemm_mode(args.gemm)
+    config["gemm_engine"] = args.gemm
     model = G.build_from_spec(spec, dev, seed=0)
     G.dist.broadcast_parameters(model)
     G.dist.decorrelate_gate_noise(model, rank)

@@ -37,13 +37,16 @@ struct TcGemmParams {
   const float* act; long long ldact;                    // TCG_EPI_MASK
 };
 
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+// K-major fp32 tiles use SWIZZLE_128B (16-byte chunks XOR (row & 7), 8-row atoms: SBO = 1024).  MN-major tiles of
+// a 32-bit type must use SWIZZLE_128B_BASE32B (32-byte granules XOR (row & 3), 4-row atoms: SBO = 512); LBO is the
+// stride between 32-element MN slabs.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, bool mn_major) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;      // SBO: 8 rows x 128 bytes
+  d |= (uint64_t)(((mn_major ? 4096u : 0u) >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(((mn_major ? 512u : 1024u) >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  d |= (uint64_t)(mn_major ? 1 : 2) << 61;           // SWIZZLE_128B_BASE32B : SWIZZLE_128B
   return d;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -92,7 +95,7 @@ __device__ __forceinline__ void fill_tile(char* img_hi, char* img_lo, const floa
         for (int j = 0; j < VEC; ++j) v[j] = (k_ok && r0 + r + j < r_end) ? __ldg(src_p + j) : 0.f;
       }
       const int slab = r >> 5, e = r & 31;
-      off = slab * 4096 + kk * 128 + ((((e >> 2) ^ (kk & 7)) << 4) | ((e & 3) << 2));
+      off = slab * 4096 + kk * 128 + ((((e >> 2) ^ ((kk & 3) << 1)) << 4) | ((e & 3) << 2));
     }
     float hi[VEC], lo[VEC];
 #pragma unroll
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
       const uint32_t idesc = make_idesc_tf32(kGemmBM, BN) | (p.a_src == TCG_SRC_MN ? (1u << 15) : 0u) | (p.b_src == TCG_SRC_MN ? (1u << 16) : 0u);
       // per k-step (8 k) descriptor advance: K-major: 32 bytes inside the swizzle atom; MN-major: 8 tile rows = 1024 bytes
       const uint32_t a_step = (p.a_src == TCG_SRC_K) ? 2u : 64u, b_step = (p.b_src == TCG_SRC_K) ? 2u : 64u;
-      const uint32_t a_lbo = (p.a_src == TCG_SRC_K) ? 0u : 4096u, b_lbo = (p.b_src == TCG_SRC_K) ? 0u : 4096u;
+      const bool a_mn = p.a_src == TCG_SRC_MN, b_mn = p.b_src == TCG_SRC_MN;
       long long it = 0;
       int tcount = 0;
       for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
@@ -192,8 +195,8 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
           mbar_wait(&full[s], (uint32_t)((it / p.stages) & 1));
           fence_after_sync();
           const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t da_hi = make_sw128_desc(st, a_lbo), db_hi = make_sw128_desc(st + a_bytes, b_lbo);
-          const uint64_t da_lo = make_sw128_desc(st + a_bytes + b_bytes, a_lbo), db_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes, b_lbo);
+          const uint64_t da_hi = make_sw128_desc(st, a_mn), db_hi = make_sw128_desc(st + a_bytes, b_mn);
+          const uint64_t da_lo = make_sw128_desc(st + a_bytes + b_bytes, a_mn), db_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes, b_mn);
 #pragma unroll
           for (int ks = 0; ks < kGemmKC / 8; ++ks) {
             const uint64_t oa = (uint64_t)(a_step * ks), ob = (uint64_t)(b_step * ks);
