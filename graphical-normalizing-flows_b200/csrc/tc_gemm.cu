@@ -57,61 +57,72 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // Fill one operand tile (rows x 32 k) for one k-chunk.  Tile image: 128-byte rows, 16-byte chunks XOR-swizzled by
 // (row & 7).  K-major: tile row = operand row.  MN-major: slabs of 32 operand rows; tile row = k index inside the chunk.
 template <int VEC>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, bool ok_all, bool ok_any, int n_valid, float (&v)[VEC]) {
+  if (ok_all) {
+    if (VEC == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(p)); v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w; }
+    else if (VEC == 2) { const float2 q = __ldg(reinterpret_cast<const float2*>(p)); v[0] = q.x; v[1 % VEC] = q.y; }
+    else v[0] = __ldg(p);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = (ok_any && j < n_valid) ? __ldg(p + j) : 0.f;
+  }
+}
+
+// Loads are issued in batches of kFillUnroll per thread before any of them is consumed, so one global-memory
+// latency is paid per batch instead of per vector.
+constexpr int kFillUnroll = 8;
+
+template <int VEC>
 __device__ __forceinline__ void fill_tile(char* img_hi, char* img_lo, const float* __restrict__ g, long long ld, int src, int r0,
                                           int r_end, int k0, int k_end, int rows, int ptid, bool split) {
   constexpr int VPR = 32 / VEC;                           // vectors per 128-byte line
-  const int total = (src == TCG_SRC_K) ? rows * VPR : kGemmKC * (rows / VEC);
-  for (int i = ptid; i < total; i += kProdThreads) {
-    float v[VEC];
-    int off;
-    if (src == TCG_SRC_K) {
-      const int r = i / VPR, cv = i % VPR;
-      const int k = k0 + cv * VEC;
-      const float* src_p = g + (long long)(r0 + r) * ld + k;
-      const bool row_ok = (r0 + r) < r_end;
-      if (row_ok && k + VEC <= k_end) {
-        if (VEC == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(src_p)); v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w; }
-        else if (VEC == 2) { const float2 q = __ldg(reinterpret_cast<const float2*>(src_p)); v[0] = q.x; v[1 % VEC] = q.y; }
-        else v[0] = __ldg(src_p);
-      } else {
+  const int per = rows / VEC;
+  const int total = (src == TCG_SRC_K) ? rows * VPR : kGemmKC * per;
+  for (int base = ptid; base < total; base += kProdThreads * kFillUnroll) {
+    float v[kFillUnroll][VEC];
+    int off[kFillUnroll];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) v[j] = (row_ok && k + j < k_end) ? __ldg(src_p + j) : 0.f;
+    for (int u = 0; u < kFillUnroll; ++u) {
+      const int i = base + u * kProdThreads;
+      off[u] = -1;
+      if (i < total) {
+        if (src == TCG_SRC_K) {
+          const int r = i / VPR, cv = i % VPR;
+          const int k = k0 + cv * VEC;
+          const bool row_ok = (r0 + r) < r_end;
+          load_vec<VEC>(g + (long long)(r0 + r) * ld + k, row_ok && k + VEC <= k_end, row_ok, k_end - k, v[u]);
+          const int e = cv * VEC;                         // first element inside the line
+          off[u] = r * 128 + ((((e >> 2) ^ (r & 7)) << 4) | ((e & 3) << 2));
+        } else {
+          const int kk = i / per, rv = i - kk * per;
+          const int r = rv * VEC;
+          const int k = k0 + kk;
+          const bool k_ok = k < k_end;
+          load_vec<VEC>(g + (long long)k * ld + r0 + r, k_ok && r0 + r + VEC <= r_end, k_ok, r_end - (r0 + r), v[u]);
+          const int slab = r >> 5, e = r & 31;
+          off[u] = slab * 4096 + kk * 128 + ((((e >> 2) ^ ((kk & 3) << 1)) << 4) | ((e & 3) << 2));
+        }
       }
-      const int e = cv * VEC;                             // first element inside the line
-      off = r * 128 + ((((e >> 2) ^ (r & 7)) << 4) | ((e & 3) << 2));
-    } else {
-      const int per = rows / VEC;
-      const int kk = i / per, rv = i % per;
-      const int r = rv * VEC;
-      const int k = k0 + kk;
-      const float* src_p = g + (long long)k * ld + r0 + r;
-      const bool k_ok = k < k_end;
-      if (k_ok && r0 + r + VEC <= r_end) {
-        if (VEC == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(src_p)); v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w; }
-        else if (VEC == 2) { const float2 q = __ldg(reinterpret_cast<const float2*>(src_p)); v[0] = q.x; v[1 % VEC] = q.y; }
-        else v[0] = __ldg(src_p);
-      } else {
+    }
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) v[j] = (k_ok && r0 + r + j < r_end) ? __ldg(src_p + j) : 0.f;
+    for (int u = 0; u < kFillUnroll; ++u) {
+      if (off[u] < 0) continue;
+      float hi[VEC], lo[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        hi[j] = split ? __uint_as_float(__float_as_uint(v[u][j]) & 0xFFFFE000u) : v[u][j];
+        lo[j] = v[u][j] - hi[j];
       }
-      const int slab = r >> 5, e = r & 31;
-      off = slab * 4096 + kk * 128 + ((((e >> 2) ^ ((kk & 3) << 1)) << 4) | ((e & 3) << 2));
-    }
-    float hi[VEC], lo[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      hi[j] = split ? __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u) : v[j];
-      lo[j] = v[j] - hi[j];
-    }
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1 % VEC], hi[2 % VEC], hi[3 % VEC]);
-      if (split) *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
-    } else if (VEC == 2) {
-      *reinterpret_cast<float2*>(img_hi + off) = make_float2(hi[0], hi[1 % VEC]);
-      if (split) *reinterpret_cast<float2*>(img_lo + off) = make_float2(lo[0], lo[1 % VEC]);
-    } else {
-      *reinterpret_cast<float*>(img_hi + off) = hi[0];
-      if (split) *reinterpret_cast<float*>(img_lo + off) = lo[0];
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(img_hi + off[u]) = make_float4(hi[0], hi[1 % VEC], hi[2 % VEC], hi[3 % VEC]);
+        if (split) *reinterpret_cast<float4*>(img_lo + off[u]) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
+      } else if (VEC == 2) {
+        *reinterpret_cast<float2*>(img_hi + off[u]) = make_float2(hi[0], hi[1 % VEC]);
+        if (split) *reinterpret_cast<float2*>(img_lo + off[u]) = make_float2(lo[0], lo[1 % VEC]);
+      } else {
+        *reinterpret_cast<float*>(img_hi + off[u]) = hi[0];
+        if (split) *reinterpret_cast<float*>(img_lo + off[u]) = lo[0];
+      }
     }
   }
 }
