@@ -57,81 +57,106 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // Fill one operand tile (rows x 32 k) for one k-chunk.  Tile image: 128-byte rows, 16-byte chunks XOR-swizzled by
 // (row & 7).  K-major: tile row = operand row.  MN-major: slabs of 32 operand rows; tile row = k index inside the chunk.
 template <int VEC>
-__device__ __forceinline__ void load_vec(const float* __restrict__ p, bool ok_all, bool ok_any, int n_valid, float (&v)[VEC]) {
-  if (ok_all) {
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, bool full, int n_valid, float (&v)[VEC]) {
+  if (full) {
     if (VEC == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(p)); v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w; }
     else if (VEC == 2) { const float2 q = __ldg(reinterpret_cast<const float2*>(p)); v[0] = q.x; v[1 % VEC] = q.y; }
     else v[0] = __ldg(p);
   } else {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = (ok_any && j < n_valid) ? __ldg(p + j) : 0.f;
+    for (int j = 0; j < VEC; ++j) v[j] = (j < n_valid) ? __ldg(p + j) : 0.f;
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(char* img_hi, char* img_lo, int off, const float (&v)[VEC], bool split) {
+  float hi[VEC], lo[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    hi[j] = split ? __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u) : v[j];
+    lo[j] = v[j] - hi[j];
+  }
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1 % VEC], hi[2 % VEC], hi[3 % VEC]);
+    if (split) *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
+  } else if (VEC == 2) {
+    *reinterpret_cast<float2*>(img_hi + off) = make_float2(hi[0], hi[1 % VEC]);
+    if (split) *reinterpret_cast<float2*>(img_lo + off) = make_float2(lo[0], lo[1 % VEC]);
+  } else {
+    *reinterpret_cast<float*>(img_hi + off) = hi[0];
+    if (split) *reinterpret_cast<float*>(img_lo + off) = lo[0];
   }
 }
 
-// Loads are issued in batches of kFillUnroll per thread before any of them is consumed, so one global-memory
-// latency is paid per batch instead of per vector.
-constexpr int kFillUnroll = 8;
-
+// K-major operand (global memory contiguous along k): tile row = operand row, 128 bytes (32 k) per row, 16-byte chunks
+// XOR-swizzled by (row & 7).  Thread -> (row within a pass, vector within the row); passes advance by a multiple of
+// 8 rows, so the swizzle term and the in-row offset are per-thread constants: one pointer add + one load + one store
+// per vector.  Loads are issued kBatch deep before the first store.
 template <int VEC>
-__device__ __forceinline__ void fill_tile(char* img_hi, char* img_lo, const float* __restrict__ g, long long ld, int src, int r0,
-                                          int r_end, int k0, int k_end, int rows, int ptid, bool split) {
-  constexpr int VPR = 32 / VEC;                           // vectors per 128-byte line
-  const int per = rows / VEC;
-  const int total = (src == TCG_SRC_K) ? rows * VPR : kGemmKC * per;
-  for (int base = ptid; base < total; base += kProdThreads * kFillUnroll) {
-    float v[kFillUnroll][VEC];
-    int off[kFillUnroll];
+__device__ __forceinline__ void fill_k(char* img_hi, char* img_lo, const float* __restrict__ g, long long ld, int r0, int r_end,
+                                       int k0, int k_end, int rows, int ptid, bool split) {
+  constexpr int VPR = 32 / VEC, STEP = kProdThreads / VPR, kBatch = 8;
+  const int cv = ptid % VPR, rb = ptid / VPR, e = cv * VEC;
+  const int soff0 = rb * 128 + ((((e >> 2) ^ (rb & 7)) << 4) | ((e & 3) << 2));
+  const int nk = k_end - (k0 + e);                       // valid elements of this thread's vector along k
+  const bool kfull = nk >= VEC;
+  const float* p0 = g + (long long)(r0 + rb) * ld + k0 + e;
+  const int npass = rows / STEP;
+  for (int pb = 0; pb < npass; pb += kBatch) {
+    float v[kBatch][VEC];
 #pragma unroll
-    for (int u = 0; u < kFillUnroll; ++u) {
-      const int i = base + u * kProdThreads;
-      off[u] = -1;
-      if (i < total) {
-        if (src == TCG_SRC_K) {
-          const int r = i / VPR, cv = i % VPR;
-          const int k = k0 + cv * VEC;
-          const bool row_ok = (r0 + r) < r_end;
-          load_vec<VEC>(g + (long long)(r0 + r) * ld + k, row_ok && k + VEC <= k_end, row_ok, k_end - k, v[u]);
-          const int e = cv * VEC;                         // first element inside the line
-          off[u] = r * 128 + ((((e >> 2) ^ (r & 7)) << 4) | ((e & 3) << 2));
-        } else {
-          const int kk = i / per, rv = i - kk * per;
-          const int r = rv * VEC;
-          const int k = k0 + kk;
-          const bool k_ok = k < k_end;
-          load_vec<VEC>(g + (long long)k * ld + r0 + r, k_ok && r0 + r + VEC <= r_end, k_ok, r_end - (r0 + r), v[u]);
-          const int slab = r >> 5, e = r & 31;
-          off[u] = slab * 4096 + kk * 128 + ((((e >> 2) ^ ((kk & 3) << 1)) << 4) | ((e & 3) << 2));
-        }
-      }
+    for (int u = 0; u < kBatch; ++u) {
+      const int ps = pb + u;
+      const bool ok = ps < npass && (r0 + rb + ps * STEP) < r_end;
+      if (ps < npass) load_vec<VEC>(p0 + (long long)ps * STEP * ld, ok && kfull, ok ? nk : 0, v[u]);
     }
 #pragma unroll
-    for (int u = 0; u < kFillUnroll; ++u) {
-      if (off[u] < 0) continue;
-      float hi[VEC], lo[VEC];
+    for (int u = 0; u < kBatch; ++u) {
+      const int ps = pb + u;
+      if (ps < npass) store_vec<VEC>(img_hi, img_lo, soff0 + ps * STEP * 128, v[u], split);
+    }
+  }
+}
+
+// MN-major operand (global memory contiguous along the operand-row index): slabs of 32 operand rows; tile row = k index
+// inside the chunk (32 per chunk), 32-byte granules XOR-swizzled by (k & 3) (SWIZZLE_128B_BASE32B).  Producer warp w
+// owns k rows w, w+8, w+16, w+24; lanes sweep the operand rows.
+template <int VEC>
+__device__ __forceinline__ void fill_mn(char* img_hi, char* img_lo, const float* __restrict__ g, long long ld, int r0, int r_end,
+                                        int k0, int k_end, int rows, int ptid, bool split) {
+  const int w = ptid >> 5, lane = ptid & 31;
+  const int per = rows / VEC;                            // vectors per k row
+  for (int rv = lane; rv < per; rv += 32) {
+    const int r = rv * VEC;
+    const int nr = r_end - (r0 + r);
+    const bool rfull = nr >= VEC;
+    const int slab = r >> 5, e = r & 31;
+    const float* p0 = g + (long long)(k0 + w) * ld + r0 + r;
+    float v[4][VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        hi[j] = split ? __uint_as_float(__float_as_uint(v[u][j]) & 0xFFFFE000u) : v[u][j];
-        lo[j] = v[u][j] - hi[j];
-      }
-      if (VEC == 4) {
-        *reinterpret_cast<float4*>(img_hi + off[u]) = make_float4(hi[0], hi[1 % VEC], hi[2 % VEC], hi[3 % VEC]);
-        if (split) *reinterpret_cast<float4*>(img_lo + off[u]) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
-      } else if (VEC == 2) {
-        *reinterpret_cast<float2*>(img_hi + off[u]) = make_float2(hi[0], hi[1 % VEC]);
-        if (split) *reinterpret_cast<float2*>(img_lo + off[u]) = make_float2(lo[0], lo[1 % VEC]);
-      } else {
-        *reinterpret_cast<float*>(img_hi + off[u]) = hi[0];
-        if (split) *reinterpret_cast<float*>(img_lo + off[u]) = lo[0];
-      }
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = (k0 + w + 8 * u) < k_end;
+      load_vec<VEC>(p0 + (long long)(8 * u) * ld, ok && rfull, ok ? nr : 0, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = w + 8 * u;
+      const int off = slab * 4096 + kk * 128 + ((((e >> 2) ^ ((kk & 3) << 1)) << 4) | ((e & 3) << 2));
+      store_vec<VEC>(img_hi, img_lo, off, v[u], split);
     }
   }
 }
 
 __device__ __forceinline__ void fill_dispatch(int vec, char* hi, char* lo, const float* g, long long ld, int src, int r0, int r_end,
                                               int k0, int k_end, int rows, int ptid, bool split) {
-  if (vec == 4) fill_tile<4>(hi, lo, g, ld, src, r0, r_end, k0, k_end, rows, ptid, split);
-  else if (vec == 2) fill_tile<2>(hi, lo, g, ld, src, r0, r_end, k0, k_end, rows, ptid, split);
-  else fill_tile<1>(hi, lo, g, ld, src, r0, r_end, k0, k_end, rows, ptid, split);
+  if (src == TCG_SRC_K) {
+    if (vec == 4) fill_k<4>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+    else if (vec == 2) fill_k<2>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+    else fill_k<1>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+  } else {
+    if (vec == 4) fill_mn<4>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+    else if (vec == 2) fill_mn<2>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+    else fill_mn<1>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+  }
 }
 
 __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, int vecA, int vecB) {
@@ -317,7 +342,7 @@ static int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return 0;
   if (p.passes != 1 && p.passes != 3) return fail(GNF_ERR_INVALID, "tensor-core GEMM: passes must be 1 or 3");
   p.BN = pick_bn(p.N);
-  if (p.b_src == TCG_SRC_MN) p.BN = (p.BN + 31) / 32 * 32;         // MN-major operands are staged in 32-row slabs
+  // every candidate is a multiple of 32: K-major fills advance 8/16/32 rows per pass, MN-major tiles are 32-row slabs
   const uint32_t stage_bytes = (uint32_t)(kGemmBM + p.BN) * 128u * (p.passes == 3 ? 2u : 1u);
   int stages = (int)((200u * 1024u) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
