@@ -56,106 +56,96 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // Fill one operand tile (rows x 32 k) for one k-chunk.  Tile image: 128-byte rows, 16-byte chunks XOR-swizzled by
 // (row & 7).  K-major: tile row = operand row.  MN-major: slabs of 32 operand rows; tile row = k index inside the chunk.
+// cp.async (LDGSTS) straight into the swizzled tile: no register staging, so a producer thread can have every
+// vector of several stages in flight.  src_bytes < VEC*4 zero-fills the remainder (ragged K / row tails).
 template <int VEC>
-__device__ __forceinline__ void load_vec(const float* __restrict__ p, bool full, int n_valid, float (&v)[VEC]) {
-  if (full) {
-    if (VEC == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(p)); v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w; }
-    else if (VEC == 2) { const float2 q = __ldg(reinterpret_cast<const float2*>(p)); v[0] = q.x; v[1 % VEC] = q.y; }
-    else v[0] = __ldg(p);
-  } else {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = (j < n_valid) ? __ldg(p + j) : 0.f;
-  }
+__device__ __forceinline__ void cp_async_vec(char* smem_dst, const float* gmem_src, int src_bytes) {
+  const uint32_t d = tc::smem_u32(smem_dst);
+  if (VEC == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+  else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
+// lo = x - trunc_tf32(x) for the 3xTF32 split.  The tensor core truncates the fp32 bits it reads (measured:
+// scripts/tf32_round_probe.py), so the raw fp32 tile IS the hi operand and only the lo tile has to be produced.
 template <int VEC>
-__device__ __forceinline__ void store_vec(char* img_hi, char* img_lo, int off, const float (&v)[VEC], bool split) {
-  float hi[VEC], lo[VEC];
+__device__ __forceinline__ void split_vec(const char* img_hi, char* img_lo, int off) {
+  float v[VEC];
+  if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(img_hi + off); v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w; }
+  else if (VEC == 2) { const float2 q = *reinterpret_cast<const float2*>(img_hi + off); v[0] = q.x; v[1 % VEC] = q.y; }
+  else v[0] = *reinterpret_cast<const float*>(img_hi + off);
+  float lo[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    hi[j] = split ? __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u) : v[j];
-    lo[j] = v[j] - hi[j];
-  }
-  if (VEC == 4) {
-    *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1 % VEC], hi[2 % VEC], hi[3 % VEC]);
-    if (split) *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
-  } else if (VEC == 2) {
-    *reinterpret_cast<float2*>(img_hi + off) = make_float2(hi[0], hi[1 % VEC]);
-    if (split) *reinterpret_cast<float2*>(img_lo + off) = make_float2(lo[0], lo[1 % VEC]);
-  } else {
-    *reinterpret_cast<float*>(img_hi + off) = hi[0];
-    if (split) *reinterpret_cast<float*>(img_lo + off) = lo[0];
-  }
+  for (int j = 0; j < VEC; ++j) lo[j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+  if (VEC == 4) *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
+  else if (VEC == 2) *reinterpret_cast<float2*>(img_lo + off) = make_float2(lo[0], lo[1 % VEC]);
+  else *reinterpret_cast<float*>(img_lo + off) = lo[0];
 }
 
 // K-major operand (global memory contiguous along k): tile row = operand row, 128 bytes (32 k) per row, 16-byte chunks
 // XOR-swizzled by (row & 7).  Thread -> (row within a pass, vector within the row); passes advance by a multiple of
-// 8 rows, so the swizzle term and the in-row offset are per-thread constants: one pointer add + one load + one store
-// per vector.  Loads are issued kBatch deep before the first store.
-template <int VEC>
+// 8 rows, so the swizzle term and the in-row offset are per-thread constants.
+// kSplitPass = false: issue the cp.async copies of the raw tile.  true: produce the lo tile from the landed raw tile.
+template <int VEC, bool kSplitPass>
 __device__ __forceinline__ void fill_k(char* img_hi, char* img_lo, const float* __restrict__ g, long long ld, int r0, int r_end,
-                                       int k0, int k_end, int rows, int ptid, bool split) {
-  constexpr int VPR = 32 / VEC, STEP = kProdThreads / VPR, kBatch = 8;
+                                       int k0, int k_end, int rows, int ptid) {
+  constexpr int VPR = 32 / VEC, STEP = kProdThreads / VPR;
   const int cv = ptid % VPR, rb = ptid / VPR, e = cv * VEC;
   const int soff0 = rb * 128 + ((((e >> 2) ^ (rb & 7)) << 4) | ((e & 3) << 2));
-  const int nk = k_end - (k0 + e);                       // valid elements of this thread's vector along k
-  const bool kfull = nk >= VEC;
-  const float* p0 = g + (long long)(r0 + rb) * ld + k0 + e;
   const int npass = rows / STEP;
-  for (int pb = 0; pb < npass; pb += kBatch) {
-    float v[kBatch][VEC];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int ps = pb + u;
-      const bool ok = ps < npass && (r0 + rb + ps * STEP) < r_end;
-      if (ps < npass) load_vec<VEC>(p0 + (long long)ps * STEP * ld, ok && kfull, ok ? nk : 0, v[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int ps = pb + u;
-      if (ps < npass) store_vec<VEC>(img_hi, img_lo, soff0 + ps * STEP * 128, v[u], split);
-    }
+  if (kSplitPass) {
+#pragma unroll 4
+    for (int ps = 0; ps < npass; ++ps) split_vec<VEC>(img_hi, img_lo, soff0 + ps * STEP * 128);
+    return;
+  }
+  int nk = k_end - (k0 + e);                             // valid elements of this thread's vector along k
+  nk = nk < 0 ? 0 : (nk > VEC ? VEC : nk);
+  const float* p0 = g + (long long)(r0 + rb) * ld + k0 + e;
+#pragma unroll 4
+  for (int ps = 0; ps < npass; ++ps) {
+    const bool ok = (r0 + rb + ps * STEP) < r_end && nk > 0;
+    cp_async_vec<VEC>(img_hi + soff0 + ps * STEP * 128, ok ? p0 + (long long)ps * STEP * ld : g, ok ? nk * 4 : 0);
   }
 }
 
 // MN-major operand (global memory contiguous along the operand-row index): slabs of 32 operand rows; tile row = k index
 // inside the chunk (32 per chunk), 32-byte granules XOR-swizzled by (k & 3) (SWIZZLE_128B_BASE32B).  Producer warp w
 // owns k rows w, w+8, w+16, w+24; lanes sweep the operand rows.
-template <int VEC>
+template <int VEC, bool kSplitPass>
 __device__ __forceinline__ void fill_mn(char* img_hi, char* img_lo, const float* __restrict__ g, long long ld, int r0, int r_end,
-                                        int k0, int k_end, int rows, int ptid, bool split) {
+                                        int k0, int k_end, int rows, int ptid) {
   const int w = ptid >> 5, lane = ptid & 31;
   const int per = rows / VEC;                            // vectors per k row
   for (int rv = lane; rv < per; rv += 32) {
     const int r = rv * VEC;
-    const int nr = r_end - (r0 + r);
-    const bool rfull = nr >= VEC;
     const int slab = r >> 5, e = r & 31;
+    int nr = r_end - (r0 + r);
+    nr = nr < 0 ? 0 : (nr > VEC ? VEC : nr);
     const float* p0 = g + (long long)(k0 + w) * ld + r0 + r;
-    float v[4][VEC];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool ok = (k0 + w + 8 * u) < k_end;
-      load_vec<VEC>(p0 + (long long)(8 * u) * ld, ok && rfull, ok ? nr : 0, v[u]);
-    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int kk = w + 8 * u;
       const int off = slab * 4096 + kk * 128 + ((((e >> 2) ^ ((kk & 3) << 1)) << 4) | ((e & 3) << 2));
-      store_vec<VEC>(img_hi, img_lo, off, v[u], split);
+      if (kSplitPass) {
+        split_vec<VEC>(img_hi, img_lo, off);
+      } else {
+        const bool ok = (k0 + kk) < k_end && nr > 0;
+        cp_async_vec<VEC>(img_hi + off, ok ? p0 + (long long)(8 * u) * ld : g, ok ? nr * 4 : 0);
+      }
     }
   }
 }
 
+template <bool kSplitPass>
 __device__ __forceinline__ void fill_dispatch(int vec, char* hi, char* lo, const float* g, long long ld, int src, int r0, int r_end,
-                                              int k0, int k_end, int rows, int ptid, bool split) {
+                                              int k0, int k_end, int rows, int ptid) {
   if (src == TCG_SRC_K) {
-    if (vec == 4) fill_k<4>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
-    else if (vec == 2) fill_k<2>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
-    else fill_k<1>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+    if (vec == 4) fill_k<4, kSplitPass>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid);
+    else if (vec == 2) fill_k<2, kSplitPass>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid);
+    else fill_k<1, kSplitPass>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid);
   } else {
-    if (vec == 4) fill_mn<4>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
-    else if (vec == 2) fill_mn<2>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
-    else fill_mn<1>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid, split);
+    if (vec == 4) fill_mn<4, kSplitPass>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid);
+    else if (vec == 2) fill_mn<2, kSplitPass>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid);
+    else fill_mn<1, kSplitPass>(hi, lo, g, ld, r0, r_end, k0, k_end, rows, ptid);
   }
 }
 
@@ -191,8 +181,22 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
 
   if (warp >= 5) {
     // ===================== producers =====================
+    // Software pipeline with a lag of kLag stages: the copies of chunk `it` are issued (cp.async, one commit group per
+    // chunk) before chunk it-kLag is finished (wait for its group, produce the lo tiles, proxy fence, signal the MMA).
+    const int kLag = p.stages >= 3 ? 2 : 1;              // the ring must hold the in-flight chunks plus one being consumed
     const int ptid = tid - (kEpiThreads + 32);
     long long it = 0;                                    // running k-chunk counter (stage ring position)
+    auto finish = [&](long long j) {                     // chunk j's copies have landed (caller waited on its group)
+      const int s = (int)(j % p.stages);
+      char* st = smem + (size_t)s * stage_bytes;
+      if (split) {
+        fill_dispatch<true>(vecA, st, st + a_bytes + b_bytes, nullptr, 0, p.a_src, 0, 0, 0, 0, kGemmBM, ptid);
+        fill_dispatch<true>(vecB, st + a_bytes, st + 2 * a_bytes + b_bytes, nullptr, 0, p.b_src, 0, 0, 0, 0, BN, ptid);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    };
     for (long long w = blockIdx.x; w < total; w += gridDim.x) {
       const int tm = (int)(w % tiles_m), tn = (int)((w / tiles_m) % tiles_n), sp = (int)(w / ((long long)tiles_m * tiles_n));
       const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
@@ -201,14 +205,18 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
         const uint32_t par = (uint32_t)((it / p.stages) & 1);
         mbar_wait(&empty[s], par ^ 1u);
         char* st = smem + (size_t)s * stage_bytes;
-        char* a_hi = st; char* b_hi = st + a_bytes; char* a_lo = st + a_bytes + b_bytes; char* b_lo = a_lo + a_bytes;
-        fill_dispatch(vecA, a_hi, a_lo, p.A, p.lda, p.a_src, tm * kGemmBM, p.M, k0, kend, kGemmBM, ptid, split);
-        fill_dispatch(vecB, b_hi, b_lo, p.B, p.ldb, p.b_src, tn * BN, p.N, k0, kend, BN, ptid, split);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+        fill_dispatch<false>(vecA, st, nullptr, p.A, p.lda, p.a_src, tm * kGemmBM, p.M, k0, kend, kGemmBM, ptid);
+        fill_dispatch<false>(vecB, st + a_bytes, nullptr, p.B, p.ldb, p.b_src, tn * BN, p.N, k0, kend, BN, ptid);
+        cp_async_commit();
+        if (it >= kLag) {
+          if (kLag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+          finish(it - kLag);
+        }
       }
     }
+    // drain
+    cp_async_wait<0>();
+    for (long long j = (it > kLag ? it - kLag : 0); j < it; ++j) finish(j);
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
