@@ -76,8 +76,9 @@ struct Philox {
     out.x = c0; out.y = c1; out.z = c2; out.w = c3;
     return out;
   }
-  // 24-bit uniform in the open interval (0,1): never 0, so -log(-log(u)) stays finite.
-  __host__ __device__ static inline float u01(unsigned bits) { return ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+  // 23-bit uniform strictly inside (0,1): (n + 0.5) * 2^-23 with n < 2^23 is exactly representable in fp32
+  // (n + 0.5 with n up to 2^24 - 1 is not: it would round up to 1.0 and make the Gumbel -log(-log(u)) infinite).
+  __host__ __device__ static inline float u01(unsigned bits) { return ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 };
 
 }  // namespace gnf

@@ -213,3 +213,31 @@ def test_philox_gate_noise_is_reproducible_and_uniform():
     assert 0. < float(a1.min()) and float(a1.max()) < 1.
     assert abs(float(a1.mean()) - .5) < .02 and abs(float(a2.mean()) - .5) < .02
     assert abs(float(((a1 - .5) * (a2 - .5)).mean())) < .01
+
+
+def test_philox_uniforms_stay_strictly_inside_unit_interval():
+    """33M draws: the generator must never return 0 or 1 (either makes the Gumbel gate infinite -> NaN loss)."""
+    gs = G.ops.GateSpec(G._lib.GATE_GUMBEL, G._lib.IMP_SOFT, 0., .5, seed=99, offset=3)
+    a1, a2 = G.ops.dag_dump_noise(gs, 4096, 64, "cuda")
+    for a in (a1, a2):
+        assert float(a.min()) > 0. and float(a.max()) < 1.
+        g = -torch.log(-torch.log(a))
+        assert torch.isfinite(g).all()
+
+
+@pytest.mark.parametrize("cfg,B,steps", [("cfg4", 100, 60), ("cfg2", 2500, 40), ("cfg5", 16, 6)])
+def test_training_stays_finite(cfg, B, steps):
+    """A short Adam run at the reference's hyper-parameters with the in-kernel Philox gate: loss and parameters stay finite."""
+    M = _mvo()
+    model = M.build(M.CONFIGS[cfg], "cuda")
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for it in range(steps):
+        x = torch.randn(B, M.CONFIGS[cfg]["d"], device="cuda", generator=g)
+        opt.zero_grad()
+        z, jac = model(x)
+        loss = model.loss(z, jac)
+        loss.backward()
+        opt.step()
+        assert torch.isfinite(loss.detach()), f"loss became {float(loss.detach())} at step {it}"
+    assert all(torch.isfinite(p).all() for p in model.parameters())
