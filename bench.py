@@ -206,9 +206,10 @@ def main():
     ap.add_argument("--nb-steps", type=int, default=None, help="quadrature steps S (default 20 train / 40 eval)")
     ap.add_argument("--precision", default="strict", choices=["strict", "tf32"],
                     help="strict: fp32 FFMA kernels; tf32: tensor-core (tcgen05) UMNN forward, ll tolerance 2e-3")
-    ap.add_argument("--gemm", default="ffma", choices=["ffma", "tf32x3", "tf32"],
+    ap.add_argument("--gemm", default="auto", choices=["ffma", "tf32x3", "tf32", "auto", "auto-fast"],
                     help="conditioner GEMM engine: fp32 FFMA, tensor-core 3xTF32 (fp32-equivalent) or single-pass TF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true", help="train mode: skip the additional log-lik eval measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -246,15 +247,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    G.ops.set_gemm_mode(args.gemm)
-    config["gemm_engine"] = args.gemm
     model = G.build_from_spec(spec, dev, seed=0)
     G.dist.broadcast_parameters(model)
     G.dist.decorrelate_gate_noise(model, rank)
-    for n in model.getNormalizers():
-        if hasattr(n, "nb_steps"):
-            n.nb_steps = S
-            n.precision = args.precision
     d = spec["d"]
     lr, wd = ADAM[cfg]
     bucket = G.dist.GradBucket(model.parameters())
@@ -264,6 +259,13 @@ def main():
     pool = [torch.randn(B, d, device=dev, generator=gen) for _ in range(n_pool)]
     host_pool = [torch.randn(B, d).pin_memory() for _ in range(n_pool)]
     flush_buf = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
 
     def train_step(x):
         bucket.zero()
@@ -279,99 +281,106 @@ def main():
             ll, _ = model.compute_ll(x)
         return ll.mean()
 
-    step = train_step if args.mode == "train" else eval_step
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(pool[i % n_pool])
-    barrier()
+    def measure(mode, precision, gemm, S_, steps, warmup, sample_clocks):
+        """One arm: W warm-up steps, K device-timed steps (CUDA events per step, L2 flushed between steps), then K
+        end-to-end steps (pinned host batch -> H2D -> step -> loss D2H).  Max over ranks."""
+        G.ops.set_gemm_mode(gemm)
+        for n in model.getNormalizers():
+            if hasattr(n, "nb_steps"):
+                n.nb_steps = S_
+                n.precision = precision
+        step = train_step if mode == "train" else eval_step
+        for i in range(warmup):
+            step(pool[i % n_pool])
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        l0 = G.ops.launch_count()
+        G.ops.enable_kernel_timing(True)
+        evs = []
+        barrier()
+        for i in range(steps):
+            flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(pool[i % n_pool])
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        launches = G.ops.launch_count() - l0
+        ktimes = G.ops.collect_kernel_timing()
+        G.ops.enable_kernel_timing(False)
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        barrier()
+        t0 = time.perf_counter()
+        last = 0.
+        for i in range(steps):
+            x = host_pool[i % n_pool].to(dev, non_blocking=True)
+            last = float(step(x).detach())
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        f_cond, f_int = flops_per_sample(spec, S_)
+        flops_step = (3 * f_cond + 4 * f_int if mode == "train" else f_cond + f_int) * B
+        roofline = None
+        if spec["norm"] == "monotonic":
+            kname = "gnf_umnn_bwd" if mode == "train" else ("gnf_umnn_fwd_tc" if precision == "tf32" else "gnf_umnn_fwd")
+            if ktimes.get(kname):
+                avg_ms = sum(ktimes[kname]) / len(ktimes[kname])
+                fl = umnn_kernel_flops(spec, S_, B * d, backward=(mode == "train"))
+                ach = fl / (avg_ms / 1e3) / 1e12
+                roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                            "frac": ach / peak_tf, "traffic": None, "avg_launch_ms": avg_ms, "flops_per_launch": fl,
+                            "peak_source": peak_src,
+                            "note": ("tcgen05 kind::tf32 kernel (the TF32 dense peak is half the bf16 peak the fraction is quoted against)"
+                                     if kname.endswith("_tc") else
+                                     "strict-fp32 FFMA kernel (no tensor-core instructions): fp32 CUDA-core ceiling is ~74 TFLOP/s; "
+                                     "fraction is quoted against the measured bf16 tensor peak as the contract asks"),
+                            "share_of_step": avg_ms / (dev_ms / steps)}
+        return {"value": world * B * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps,
+                "e2e": {"value": world * B * steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": B * d * 4,
+                        "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "achieved_tflops_step": flops_step / (dev_ms / steps / 1e3) / 1e12, "algorithmic_gflop_per_step": flops_step / 1e9,
+                "last_loss": last, "kernel_ms": {k: sum(v) / len(v) for k, v in ktimes.items() if v},
+                "nb_steps": S_, "precision": precision, "gemm_engine": gemm}
 
-    # -------- device-resident timing: per-step CUDA events, L2 flushed between steps --------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = G.ops.launch_count()
-    G.ops.enable_kernel_timing(True)
-    evs = []
-    barrier()
-    for i in range(args.steps):
-        flush_buf.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step(pool[i % n_pool])
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
-    launches = G.ops.launch_count() - l0
-    ktimes = G.ops.collect_kernel_timing()
-    G.ops.enable_kernel_timing(False)
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-
-    # -------- end-to-end: pinned host batch -> H2D -> step -> loss D2H, every step --------
-    barrier()
-    t0 = time.perf_counter()
-    last = 0.
-    for i in range(args.steps):
-        x = host_pool[i % n_pool].to(dev, non_blocking=True)
-        last = float(step(x))
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-
-    t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    config["gemm_engine"] = args.gemm
+    main_res = measure(args.mode, args.precision, args.gemm, S, args.steps, args.warmup, True)
+    extra = None
+    if args.mode == "train" and not args.no_eval:
+        # the metric's second half: log-likelihood evaluation (UCIExperiments.py:152-162: S = nb_steps + 20), in the
+        # fast mode (tensor-core UMNN forward + TF32 conditioner GEMMs, ll tolerance 2e-3)
+        extra = measure("eval", "tf32", "auto-fast", S + 20, args.steps, 3, False)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    value = world * B * args.steps / (dev_ms / 1e3)
-    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
-    f_cond, f_int = flops_per_sample(spec, S)
-    flops_step = (3 * f_cond + 4 * f_int if args.mode == "train" else f_cond + f_int) * B
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    roofline = None
-    if spec["norm"] == "monotonic":
-        kname = "gnf_umnn_bwd" if args.mode == "train" else ("gnf_umnn_fwd_tc" if args.precision == "tf32" else "gnf_umnn_fwd")
-        if ktimes.get(kname):
-            avg_ms = sum(ktimes[kname]) / len(ktimes[kname])
-            fl = umnn_kernel_flops(spec, S, B * d, backward=(args.mode == "train"))
-            ach = fl / (avg_ms / 1e3) / 1e12
-            roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": ach / peak_tf, "traffic": None, "avg_launch_ms": avg_ms, "flops_per_launch": fl,
-                        "peak_source": peak_src,
-                        "note": ("tcgen05 kind::tf32 kernel (TF32 dense peak is half the bf16 peak the fraction is quoted against)"
-                                 if kname.endswith("_tc") else
-                                 "strict-fp32 FFMA kernel (no tensor-core instructions): fp32 CUDA-core ceiling is ~74 TFLOP/s; "
-                                 "fraction is quoted against the measured bf16 tensor peak as the contract asks"),
-                        "share_of_step": avg_ms / (dev_ms / args.steps)}
-    else:
-        kname = "gnf_linear_fwd"
     cpu_baseline = None
     if not args.no_cpu_baseline:
         cpu_baseline, _ = time_cpu(cfg, B, args.mode, S, 5, 2, budget_s=25.)
-
-    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * d * 4,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "achieved_tflops_step": flops_step / (dev_ms / args.steps / 1e3) / 1e12,
-            "algorithmic_gflop_per_step": flops_step / 1e9, "last_loss": last,
-            "kernel_ms": {k: sum(v) / len(v) for k, v in ktimes.items() if v}}
+    line = {"metric": metric, "value": main_res["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "e2e": main_res["e2e"],
+            "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "roofline": main_res["roofline"],
+            "cpu_baseline": cpu_baseline, "achieved_tflops_step": main_res["achieved_tflops_step"],
+            "algorithmic_gflop_per_step": main_res["algorithmic_gflop_per_step"], "last_loss": main_res["last_loss"],
+            "kernel_ms": main_res["kernel_ms"]}
+    if extra is not None:
+        line["eval"] = {"metric": "loglik_eval_samples_per_s", "unit": "samples/s",
+                        "precision_mode": "tf32 (tcgen05 UMNN forward + single-pass TF32 conditioner GEMMs), ll tolerance 2e-3",
+                        **{k: extra[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "roofline", "achieved_tflops_step",
+                                                 "algorithmic_gflop_per_step", "nb_steps", "kernel_ms")}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -65,20 +65,34 @@ __device__ __forceinline__ void cp_async_vec(char* smem_dst, const float* gmem_s
   else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
-// lo = x - trunc_tf32(x) for the 3xTF32 split.  The tensor core truncates the fp32 bits it reads (measured:
-// scripts/tf32_round_probe.py), so the raw fp32 tile IS the hi operand and only the lo tile has to be produced.
+// 3xTF32 split of a landed raw fp32 tile, in place:  hi = rn_tf32(x) (overwrites the raw value), lo = rn_tf32(x - hi).
+// The tensor core truncates the fp32 bits it reads (measured: scripts/tf32_round_probe.py); feeding it operands that
+// already sit on the TF32 grid makes that truncation a no-op, and round-to-nearest keeps the representation error of
+// hi + lo at ~2^-22 |x| and unbiased (truncating both would leave a one-sided 2^-20 error that survives cancellation).
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 template <int VEC>
-__device__ __forceinline__ void split_vec(const char* img_hi, char* img_lo, int off) {
+__device__ __forceinline__ void split_vec(char* img_hi, char* img_lo, int off) {
   float v[VEC];
   if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(img_hi + off); v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w; }
   else if (VEC == 2) { const float2 q = *reinterpret_cast<const float2*>(img_hi + off); v[0] = q.x; v[1 % VEC] = q.y; }
   else v[0] = *reinterpret_cast<const float*>(img_hi + off);
-  float lo[VEC];
+  float hi[VEC], lo[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) lo[j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
-  if (VEC == 4) *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
-  else if (VEC == 2) *reinterpret_cast<float2*>(img_lo + off) = make_float2(lo[0], lo[1 % VEC]);
-  else *reinterpret_cast<float*>(img_lo + off) = lo[0];
+  for (int j = 0; j < VEC; ++j) { hi[j] = rn_tf32(v[j]); lo[j] = rn_tf32(v[j] - hi[j]); }
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1 % VEC], hi[2 % VEC], hi[3 % VEC]);
+    *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1 % VEC], lo[2 % VEC], lo[3 % VEC]);
+  } else if (VEC == 2) {
+    *reinterpret_cast<float2*>(img_hi + off) = make_float2(hi[0], hi[1 % VEC]);
+    *reinterpret_cast<float2*>(img_lo + off) = make_float2(lo[0], lo[1 % VEC]);
+  } else {
+    *reinterpret_cast<float*>(img_hi + off) = hi[0];
+    *reinterpret_cast<float*>(img_lo + off) = lo[0];
+  }
 }
 
 // K-major operand (global memory contiguous along k): tile row = operand row, 128 bytes (32 k) per row, 16-byte chunks
@@ -288,6 +302,9 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
             if (n + 16 <= p.N && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            } else if (n + 16 <= p.N && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) *reinterpret_cast<float2*>(y + j) = make_float2(o[j], o[j + 1]);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) if (n + j < p.N) y[j] = o[j];

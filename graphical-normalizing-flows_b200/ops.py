@@ -193,21 +193,38 @@ class PowerTraceFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # Conditioner MLP engine
 # ----------------------------------------------------------------------------------------------
-_GEMM_PASSES = 0     # 0: fp32 FFMA engine; 1: tcgen05 single-pass TF32; 3: tcgen05 3xTF32 (fp32-equivalent)
-_GEMM_MODES = {"ffma": 0, "tf32": 1, "tf32x3": 3}
+_GEMM_MODE = "ffma"
+_GEMM_MODES = ("ffma", "tf32", "tf32x3", "auto", "auto-fast")
 
 
 def set_gemm_mode(mode):
-    """Select the conditioner-MLP GEMM engine: 'ffma' (fp32 CUDA cores), 'tf32x3' (tensor cores, fp32-equivalent
-    3xTF32 split: strict), 'tf32' (tensor cores, single pass: ll tolerance 2e-3, not for gradient parity)."""
-    global _GEMM_PASSES
+    """Select the conditioner-MLP GEMM engine.
+      'ffma'      fp32 CUDA-core tile GEMM (strict);
+      'tf32x3'    tensor cores (tcgen05), 3xTF32 split, fp32-equivalent (strict);
+      'tf32'      tensor cores, single-pass TF32 (ll tolerance 2e-3; not for gradient parity);
+      'auto'      strict: tf32x3 where it beats the FFMA engine (large M*N*K, N and K >= 256), else ffma;
+      'auto-fast' tf32 where N and K >= 128, else ffma."""
+    global _GEMM_MODE
     if mode not in _GEMM_MODES:
-        raise ValueError(f"gemm mode must be one of {sorted(_GEMM_MODES)}")
-    _GEMM_PASSES = _GEMM_MODES[mode]
+        raise ValueError(f"gemm mode must be one of {_GEMM_MODES}")
+    _GEMM_MODE = mode
 
 
 def get_gemm_mode():
-    return {v: k for k, v in _GEMM_MODES.items()}[_GEMM_PASSES]
+    return _GEMM_MODE
+
+
+def _gemm_passes(M, N, K):
+    """0 = FFMA engine, 1 / 3 = tensor-core engine passes; thresholds from scripts/gemm_bench.py on B200."""
+    if _GEMM_MODE == "ffma":
+        return 0
+    if _GEMM_MODE == "tf32":
+        return 1
+    if _GEMM_MODE == "tf32x3":
+        return 3
+    if _GEMM_MODE == "auto":
+        return 3 if (min(N, K) >= 256 and float(M) * N * K >= 8e9) else 0
+    return 1 if min(N, K) >= 128 else 0
 
 
 def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=None):
@@ -219,9 +236,10 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
     if out is None:
         out = torch.empty(M, N, device=X.device, dtype=X.dtype)
         ldy = N
-    if _GEMM_PASSES:
+    passes = _gemm_passes(M, N, K)
+    if passes:
         _call("gnf_linear_fwd_tc", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
-              _GEMM_PASSES, stream_ptr())
+              passes, stream_ptr())
     else:
         _call("gnf_linear_fwd", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
               stream_ptr())
@@ -234,9 +252,10 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
     if out is None:
         out = torch.empty(M, K, device=dY.device, dtype=dY.dtype)
         lddx = K
-    if _GEMM_PASSES:
+    passes = _gemm_passes(M, N, K)
+    if passes:
         _call("gnf_linear_dgrad_tc", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
-              ptr(out), lddx, M, N, K, _GEMM_PASSES, stream_ptr())
+              ptr(out), lddx, M, N, K, passes, stream_ptr())
     else:
         _call("gnf_linear_dgrad", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
               ptr(out), lddx, M, N, K, stream_ptr())
@@ -246,8 +265,9 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
 
 def linear_wgrad(dY, lddy, X, ldx, M, N, K):
     dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
-    if _GEMM_PASSES:
-        _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, _GEMM_PASSES, stream_ptr())
+    passes = _gemm_passes(M, N, K)
+    if passes:
+        _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, passes, stream_ptr())
     else:
         _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr())
     _count()
