@@ -145,3 +145,31 @@ def test_train_step_vs_oracle_with_3xtf32_conditioner(gemm_mode, cfg, B):
     rep = M.compare(M.CONFIGS[cfg], B, "cuda", train=True)
     bad = {k: v for k, v in rep.items() if (k.startswith("grad.") and not v < 1e-3) or (k in ("ll", "loss") and not v < 1e-4)}
     assert not bad, f"out of tolerance: {bad}\n{rep}"
+
+
+@pytest.mark.parametrize("cfg,B", [("cfg4", 24), ("cfg2", 512)])
+def test_mixed_mode_training_gradients_vs_oracle(cfg, B):
+    """TF32 tensor-core UMNN forward + strict fp32 backward ("tf32" normalizer precision): per-sample ll within the
+    TF32 bar (2e-3) and every parameter gradient still within the 1e-3 bar of the fp32 CPU oracle."""
+    import model_vs_oracle as M
+    spec = M.CONFIGS[cfg]
+    model = M.build(spec, "cuda")
+    parity.set_modes(model, dict(stoch_gate=False))
+    for n in model.getNormalizers():
+        n.precision = "tf32"
+    x = torch.randn(B, spec["d"], generator=torch.Generator().manual_seed(5)).cuda()
+    model.zero_grad()
+    z, jac = model(x)
+    loss = model.loss(z, jac)
+    loss.backward()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    loss_o, z_o, jac_o, grads_o = M.O.train_step_grads(x.cpu(), sd, spec, [dict(stoch_gate=False)] * spec["nb_flow"], None)
+    ll = (model.z_log_density(z) + jac).detach().cpu()
+    ll_o = M.O.normal_log_density(z_o) + jac_o
+    assert float(((ll - ll_o).abs() / ll_o.abs().clamp_min(1e-6)).max()) < 2e-3
+    params = dict(model.named_parameters())
+    from helpers import rel_l2
+    rep = {k: rel_l2(params[k].grad.cpu(), g) for k, g in grads_o.items() if g is not None}
+    bad = {k: v for k, v in rep.items() if not v < 1e-3}
+    print("mixed-mode gradient errors:", {k.split("steps.0.")[-1]: float("%.2g" % v) for k, v in rep.items()})
+    assert not bad, f"gradients out of tolerance: {bad}"
