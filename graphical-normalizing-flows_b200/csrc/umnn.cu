@@ -9,12 +9,10 @@
 // [B(S+1)d, I] activation of the reference ever reaches HBM.  Weights are streamed from L2 in
 // 16-row K-panels with cp.async double buffering.
 //
-// Thread layout of a 64 x NP tile (NP = 32*TC = padded hidden width), 256 threads = 8 warps:
-//   ty = warp -> rows 8ty..8ty+7,  tx = lane -> cols tx + 32j (j < TC);  acc[8][TC] registers.
-// A warp reads the A operand as two broadcast float4 per k and the B operand as TC full 128-byte wavefronts
-// (32 distinct consecutive words), i.e. 2+TC shared-memory wavefronts per 8*TC warp-FFMAs: the 8-row thread tile
-// keeps the kernel FFMA-issue-bound rather than shared-memory-bandwidth-bound.
-// Activations are stored k-major, act[col][row] with row stride LDR = 68 floats.
+// Thread layout of a 64 x NP tile (NP = 16*TN = padded hidden width), 256 threads:
+//   ty = tid/16 -> rows 4ty..4ty+3,  tx = tid%16 -> cols tx + 16j (j < TN);  acc[4][TN] registers.
+// Activations are stored k-major, act[col][row] with row stride LDR = 68 floats, so the GEMM's
+// A-operand read is one broadcast float4 per k and the epilogue store is a float4 per column.
 #include "common.cuh"
 
 namespace gnf {
@@ -53,8 +51,11 @@ static int make_plan(const gnf_mlp_t* net, PackPlan* pl, int* TN_out) {
   int maxh = 0;
   for (int l = 1; l <= L; ++l) maxh = net->dims[l] > maxh ? net->dims[l] : maxh;
   if (net->dims[0] < 1 || net->dims[0] > 256 || maxh < 1 || maxh > 256) return fail(GNF_ERR_UNSUPPORTED, "umnn: layer widths must be in 1..256 (got in=%d, hidden max=%d)", net->dims[0], maxh);
-  const int TN = ceil_div(maxh, 32);                     // TC: number of 32-column groups
-  const int NP = 32 * TN;
+  const int want = ceil_div(maxh, 16);
+  const int opts[6] = {2, 4, 7, 10, 13, 16};
+  int TN = 16;
+  for (int i = 0; i < 6; ++i) if (opts[i] >= want) { TN = opts[i]; break; }
+  const int NP = 16 * TN;
   const int KP0 = round16(net->dims[0]);
   const int KB0 = (net->dims[0] + 31) / 32 * 32;
   if (KP0 > NP) return fail(GNF_ERR_UNSUPPORTED, "umnn: 1+cond_size (%d) wider than padded hidden width (%d)", net->dims[0], NP);
@@ -146,18 +147,18 @@ static void launch_pack(const gnf_mlp_t* net, const PackPlan& pl, float* ws, cud
 }
 
 // ------------------------------------------------------------------------------------------------
-// 64 x (32*TC) tile GEMM: acc = act_in^T-tile (k-major in smem) x W panels streamed from global.
-//   act_in : smem [K][kLDR];  Wg: global [npanels*16][32*TC] (zero padded);  wp: smem [2][16][32*TC]
+// 64 x (16*TN) tile GEMM: acc = act_in^T-tile (k-major in smem) x W panels streamed from global.
+//   act_in : smem [K][kLDR];  Wg: global [npanels*16][16*TN] (zero padded);  wp: smem [2][16][16*TN]
 // ------------------------------------------------------------------------------------------------
-template <int TC>
-__device__ __forceinline__ void tile_gemm(float (&acc)[8][TC], const float* __restrict__ act_in, const float* __restrict__ Wg, int npanels, float* __restrict__ wp) {
-  constexpr int NPo = 32 * TC;
+template <int TN>
+__device__ __forceinline__ void tile_gemm(float (&acc)[4][TN], const float* __restrict__ act_in, const float* __restrict__ Wg, int npanels, float* __restrict__ wp) {
+  constexpr int NPo = 16 * TN;
   constexpr int PANEL_F4 = kKC * NPo / 4;
-  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   auto issue = [&](int pi) {
     const float4* src = reinterpret_cast<const float4*>(Wg + (size_t)pi * kKC * NPo);
     float4* dst = reinterpret_cast<float4*>(wp + (pi & 1) * kKC * NPo);
@@ -169,42 +170,37 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[8][TC], const float* __re
     if (pi + 1 < npanels) { issue(pi + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     const float* w = wp + (pi & 1) * kKC * NPo + tx;
-    const float* a = act_in + (size_t)(pi * kKC) * kLDR + 8 * ty;
+    const float* a = act_in + (size_t)(pi * kKC) * kLDR + 4 * ty;
 #pragma unroll
     for (int kk = 0; kk < kKC; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(a + kk * kLDR);
-      const float4 a1 = *reinterpret_cast<const float4*>(a + kk * kLDR + 4);
+      const float4 av = *reinterpret_cast<const float4*>(a + kk * kLDR);
 #pragma unroll
-      for (int j = 0; j < TC; ++j) {
-        const float b = w[kk * NPo + 32 * j];
-        acc[0][j] = fmaf(a0.x, b, acc[0][j]);
-        acc[1][j] = fmaf(a0.y, b, acc[1][j]);
-        acc[2][j] = fmaf(a0.z, b, acc[2][j]);
-        acc[3][j] = fmaf(a0.w, b, acc[3][j]);
-        acc[4][j] = fmaf(a1.x, b, acc[4][j]);
-        acc[5][j] = fmaf(a1.y, b, acc[5][j]);
-        acc[6][j] = fmaf(a1.z, b, acc[6][j]);
-        acc[7][j] = fmaf(a1.w, b, acc[7][j]);
+      for (int j = 0; j < TN; ++j) {
+        const float b = w[kk * NPo + 16 * j];
+        acc[0][j] = fmaf(av.x, b, acc[0][j]);
+        acc[1][j] = fmaf(av.y, b, acc[1][j]);
+        acc[2][j] = fmaf(av.z, b, acc[2][j]);
+        acc[3][j] = fmaf(av.w, b, acc[3][j]);
       }
     }
     __syncthreads();
   }
 }
 
-// Epilogue: out[col][row] = relu(acc + bias[col])  (k-major store, two float4 over the thread's 8 rows)
-template <int TC>
-__device__ __forceinline__ void store_bias_relu(const float (&acc)[8][TC], const float* __restrict__ bias, float* __restrict__ act_out) {
-  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+// Epilogue: out[col][row] = relu(acc + bias[col])  (k-major store, float4 over the thread's 4 rows)
+template <int TN>
+__device__ __forceinline__ void store_bias_relu(const float (&acc)[4][TN], const float* __restrict__ bias, float* __restrict__ act_out) {
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
 #pragma unroll
-  for (int j = 0; j < TC; ++j) {
-    const int col = tx + 32 * j;
+  for (int j = 0; j < TN; ++j) {
+    const int col = tx + 16 * j;
     const float b = __ldg(bias + col);
-    float4 o0, o1;
-    o0.x = fmaxf(acc[0][j] + b, 0.f); o0.y = fmaxf(acc[1][j] + b, 0.f); o0.z = fmaxf(acc[2][j] + b, 0.f); o0.w = fmaxf(acc[3][j] + b, 0.f);
-    o1.x = fmaxf(acc[4][j] + b, 0.f); o1.y = fmaxf(acc[5][j] + b, 0.f); o1.z = fmaxf(acc[6][j] + b, 0.f); o1.w = fmaxf(acc[7][j] + b, 0.f);
-    float* dst = act_out + (size_t)col * kLDR + 8 * ty;
-    *reinterpret_cast<float4*>(dst) = o0;
-    *reinterpret_cast<float4*>(dst + 4) = o1;
+    float4 o;
+    o.x = fmaxf(acc[0][j] + b, 0.f);
+    o.y = fmaxf(acc[1][j] + b, 0.f);
+    o.z = fmaxf(acc[2][j] + b, 0.f);
+    o.w = fmaxf(acc[3][j] + b, 0.f);
+    *reinterpret_cast<float4*>(act_out + (size_t)col * kLDR + 4 * ty) = o;
   }
 }
 
@@ -229,7 +225,7 @@ struct UmnnFwdParams {
 
 template <int TN>
 __global__ void __launch_bounds__(kUThreads) umnn_fwd_kernel(UmnnFwdParams p) {
-  constexpr int NP = 32 * TN;
+  constexpr int NP = 16 * TN;
   GNF_SMEM(float, smem);
   float* act0 = smem;                       // [NP][kLDR]
   float* act1 = act0 + NP * kLDR;           // [NP][kLDR]
@@ -259,7 +255,7 @@ __global__ void __launch_bounds__(kUThreads) umnn_fwd_kernel(UmnnFwdParams p) {
     __syncthreads();
     float* cur = act0;
     float* nxt = act1;
-    float acc[8][TN];
+    float acc[4][TN];
     for (int l = 0; l < p.pk.L; ++l) {
       tile_gemm<TN>(acc, cur, p.pk.Wt[l], p.pk.kpad[l] / kKC, wp);
       store_bias_relu<TN>(acc, p.pk.bias[l], nxt);
@@ -319,11 +315,10 @@ struct UmnnBwdParams {
   UmnnPacked pk;
 };
 
-// dW[n][k] += sum_row dlt[n][row] * a[k][row]   for n < Nn, k < Kk ;  k columns covered = 32*TK.
-// Thread (ty = warp, tx = lane) owns n = ty + 8i (CH values of i per pass) and k = tx + 32j.
+// dW[n][k] += sum_row dlt[n][row] * a[k][row]   for n < Nn, k < Kk ; K range covered = 16*TK columns
 template <int CH, int TK>
 __device__ __forceinline__ void tile_wgrad(const float* __restrict__ dlt, const float* __restrict__ a, float* __restrict__ dW, int Nn, int Kk, int ldw, int n_groups) {
-  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   for (int i0 = 0; i0 < n_groups; i0 += CH) {
     float acc[CH][TK];
 #pragma unroll
@@ -335,30 +330,30 @@ __device__ __forceinline__ void tile_wgrad(const float* __restrict__ dlt, const 
       float4 dn[CH], ak[TK];
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        const int ni = ty + 8 * (i0 + i);
+        const int ni = ty + 16 * (i0 + i);
         dn[i] = (i0 + i < n_groups) ? *reinterpret_cast<const float4*>(dlt + (size_t)ni * kLDR + 4 * r4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < TK; ++j) ak[j] = *reinterpret_cast<const float4*>(a + (size_t)(tx + 32 * j) * kLDR + 4 * r4);
+      for (int j = 0; j < TK; ++j) ak[j] = *reinterpret_cast<const float4*>(a + (size_t)(tx + 16 * j) * kLDR + 4 * r4);
 #pragma unroll
       for (int i = 0; i < CH; ++i)
 #pragma unroll
         for (int j = 0; j < TK; ++j) {
-          float sacc = acc[i][j];
-          sacc = fmaf(dn[i].x, ak[j].x, sacc);
-          sacc = fmaf(dn[i].y, ak[j].y, sacc);
-          sacc = fmaf(dn[i].z, ak[j].z, sacc);
-          sacc = fmaf(dn[i].w, ak[j].w, sacc);
-          acc[i][j] = sacc;
+          float s = acc[i][j];
+          s = fmaf(dn[i].x, ak[j].x, s);
+          s = fmaf(dn[i].y, ak[j].y, s);
+          s = fmaf(dn[i].z, ak[j].z, s);
+          s = fmaf(dn[i].w, ak[j].w, s);
+          acc[i][j] = s;
         }
     }
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-      const int n = ty + 8 * (i0 + i);
+      const int n = ty + 16 * (i0 + i);
       if (i0 + i < n_groups && n < Nn) {
 #pragma unroll
         for (int j = 0; j < TK; ++j) {
-          const int k = tx + 32 * j;
+          const int k = tx + 16 * j;
           if (k < Kk) atomicAdd(dW + (size_t)n * ldw + k, acc[i][j]);
         }
       }
@@ -366,11 +361,11 @@ __device__ __forceinline__ void tile_wgrad(const float* __restrict__ dlt, const 
   }
 }
 
-template <int TN> struct WgradChunk { static constexpr int CH = ((4 * TN) % 5 == 0) ? 5 : 4; };   // 4*TN row groups of 8
+template <int TN> struct WgradChunk { static constexpr int CH = (TN <= 7) ? TN : (TN == 10 ? 5 : (TN == 13 ? 7 : 4)); };
 
 template <int TN>
 __global__ void __launch_bounds__(kUThreads) umnn_bwd_kernel(UmnnBwdParams p) {
-  constexpr int NP = 32 * TN;
+  constexpr int NP = 16 * TN;
   constexpr int CH = WgradChunk<TN>::CH;
   GNF_SMEM(float, smem);
   const int L = p.pk.L;
@@ -383,7 +378,7 @@ __global__ void __launch_bounds__(kUThreads) umnn_bwd_kernel(UmnnBwdParams p) {
   float* red = wp + 2 * kKC * NP;                           // [256]
   float* yout = red + 256;                                  // [64]
   float* dy = yout + 64;                                    // [64]
-  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int nodes = p.S + 2;  // S+1 quadrature nodes + one plain evaluation at x (the jac output)
   const long long ntiles = (p.Q + kTileM - 1) / kTileM;
   const float blast = __ldg(p.pk.blast_ptr);
@@ -408,7 +403,7 @@ __global__ void __launch_bounds__(kUThreads) umnn_bwd_kernel(UmnnBwdParams p) {
     __syncthreads();
     // ---- recompute forward, keeping every activation
     {
-      float acc[8][TN];
+      float acc[4][TN];
       for (int l = 0; l < L; ++l) {
         tile_gemm<TN>(acc, actb[l], p.pk.Wt[l], p.pk.kpad[l] / kKC, wp);
         store_bias_relu<TN>(acc, p.pk.bias[l], actb[l + 1]);
@@ -472,41 +467,36 @@ __global__ void __launch_bounds__(kUThreads) umnn_bwd_kernel(UmnnBwdParams p) {
         atomicAdd(p.db[l] + n, s);
       }
       if (l > 0) {
-        tile_wgrad<CH, TN>(dlt, actb[l], p.dW[l], Nn, Kk, Kk, 4 * TN);
+        tile_wgrad<CH, TN>(dlt, actb[l], p.dW[l], Nn, Kk, Kk, TN);
         __syncthreads();
-        float acc[8][TN];
+        float acc[4][TN];
         tile_gemm<TN>(acc, dlt, p.pk.Wn[l], round16(Nn) / kKC, wp);
         float* ain = actb[l];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          float4* ptr = reinterpret_cast<float4*>(ain + (size_t)(tx + 32 * j) * kLDR + 8 * ty);
-          const float4 a0 = ptr[0], a1 = ptr[1];
-          float4 o0, o1;
-          o0.x = a0.x > 0.f ? acc[0][j] : 0.f;
-          o0.y = a0.y > 0.f ? acc[1][j] : 0.f;
-          o0.z = a0.z > 0.f ? acc[2][j] : 0.f;
-          o0.w = a0.w > 0.f ? acc[3][j] : 0.f;
-          o1.x = a1.x > 0.f ? acc[4][j] : 0.f;
-          o1.y = a1.y > 0.f ? acc[5][j] : 0.f;
-          o1.z = a1.z > 0.f ? acc[6][j] : 0.f;
-          o1.w = a1.w > 0.f ? acc[7][j] : 0.f;
-          ptr[0] = o0;
-          ptr[1] = o1;
+          float4* ptr = reinterpret_cast<float4*>(ain + (size_t)(tx + 16 * j) * kLDR + 4 * ty);
+          const float4 a = *ptr;
+          float4 o;
+          o.x = a.x > 0.f ? acc[0][j] : 0.f;
+          o.y = a.y > 0.f ? acc[1][j] : 0.f;
+          o.z = a.z > 0.f ? acc[2][j] : 0.f;
+          o.w = a.w > 0.f ? acc[3][j] : 0.f;
+          *ptr = o;
         }
         __syncthreads();
       } else {
         // first layer: the 1+E input columns are handled in blocks of 32 (TK = 2 groups of 16)
-        for (int c0 = 0; c0 < KP0; c0 += 32) tile_wgrad<CH, 1>(dlt, actb[0] + (size_t)c0 * kLDR, p.dW[0] + c0, Nn, Kk - c0, Kk, 4 * TN);
+        for (int c0 = 0; c0 < KP0; c0 += 32) tile_wgrad<CH, 2>(dlt, actb[0] + (size_t)c0 * kLDR, p.dW[0] + c0, Nn, Kk - c0, Kk, TN);
         __syncthreads();
         for (int c0 = 0; c0 < KP0; c0 += 32) {
-          float acc2[8][1];
-          tile_gemm<1>(acc2, dlt, p.pk.Wn[0] + (size_t)(c0 / 32) * NP * 32, round16(Nn) / kKC, wp);
-          float4 o0, o1;
-          o0.x = acc2[0][0]; o0.y = acc2[1][0]; o0.z = acc2[2][0]; o0.w = acc2[3][0];
-          o1.x = acc2[4][0]; o1.y = acc2[5][0]; o1.z = acc2[6][0]; o1.w = acc2[7][0];
-          float* dst = actb[0] + (size_t)(c0 + tx) * kLDR + 8 * ty;
-          *reinterpret_cast<float4*>(dst) = o0;
-          *reinterpret_cast<float4*>(dst + 4) = o1;
+          float acc2[4][2];
+          tile_gemm<2>(acc2, dlt, p.pk.Wn[0] + (size_t)(c0 / 32) * NP * 32, round16(Nn) / kKC, wp);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float4 o;
+            o.x = acc2[0][j]; o.y = acc2[1][j]; o.z = acc2[2][j]; o.w = acc2[3][j];
+            *reinterpret_cast<float4*>(actb[0] + (size_t)(c0 + tx + 16 * j) * kLDR + 4 * ty) = o;
+          }
         }
         __syncthreads();
       }
@@ -548,7 +538,7 @@ static size_t bwd_smem_bytes(int NP, int KP0, int L) { return ((size_t)KP0 * kLD
 
 template <int TN>
 static int launch_fwd(const UmnnFwdParams& p, cudaStream_t s) {
-  const size_t smem = fwd_smem_bytes(32 * TN);
+  const size_t smem = fwd_smem_bytes(16 * TN);
   if (smem > 227 * 1024) return fail(GNF_ERR_UNSUPPORTED, "umnn fwd: shared memory %zu B exceeds 227 KB", smem);
 #ifndef GNF_EMU
   cudaFuncSetAttribute(umnn_fwd_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -562,8 +552,8 @@ static int launch_fwd(const UmnnFwdParams& p, cudaStream_t s) {
 }
 template <int TN>
 static int launch_bwd(const UmnnBwdParams& p, cudaStream_t s) {
-  const size_t smem = bwd_smem_bytes(32 * TN, p.pk.kb0, p.pk.L);
-  if (smem > 227 * 1024) return fail(GNF_ERR_UNSUPPORTED, "umnn bwd: %d hidden layers of padded width %d need %zu B of shared memory (> 227 KB)", p.pk.L, 32 * TN, smem);
+  const size_t smem = bwd_smem_bytes(16 * TN, p.pk.kb0, p.pk.L);
+  if (smem > 227 * 1024) return fail(GNF_ERR_UNSUPPORTED, "umnn bwd: %d hidden layers of padded width %d need %zu B of shared memory (> 227 KB)", p.pk.L, 16 * TN, smem);
 #ifndef GNF_EMU
   cudaFuncSetAttribute(umnn_bwd_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
@@ -606,14 +596,12 @@ int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, co
   fill_packed(net, pl, (float*)work, &p.pk);
   int e = 0;
   switch (TN) {
-    case 1: e = launch_fwd<1>(p, s); break;
     case 2: e = launch_fwd<2>(p, s); break;
-    case 3: e = launch_fwd<3>(p, s); break;
     case 4: e = launch_fwd<4>(p, s); break;
-    case 5: e = launch_fwd<5>(p, s); break;
-    case 6: e = launch_fwd<6>(p, s); break;
     case 7: e = launch_fwd<7>(p, s); break;
-    default: e = launch_fwd<8>(p, s); break;
+    case 10: e = launch_fwd<10>(p, s); break;
+    case 13: e = launch_fwd<13>(p, s); break;
+    default: e = launch_fwd<16>(p, s); break;
   }
   if (e) return e;
   return check_launch("gnf_umnn_fwd");
@@ -646,14 +634,12 @@ int gnf_umnn_bwd(const float* x, const float* h, const gnf_mlp_t* net, int S, co
   fill_packed(net, pl, (float*)work, &p.pk);
   int e = 0;
   switch (TN) {
-    case 1: e = launch_bwd<1>(p, s); break;
     case 2: e = launch_bwd<2>(p, s); break;
-    case 3: e = launch_bwd<3>(p, s); break;
     case 4: e = launch_bwd<4>(p, s); break;
-    case 5: e = launch_bwd<5>(p, s); break;
-    case 6: e = launch_bwd<6>(p, s); break;
     case 7: e = launch_bwd<7>(p, s); break;
-    default: e = launch_bwd<8>(p, s); break;
+    case 10: e = launch_bwd<10>(p, s); break;
+    case 13: e = launch_bwd<13>(p, s); break;
+    default: e = launch_bwd<16>(p, s); break;
   }
   if (e) return e;
   return check_launch("gnf_umnn_bwd");
