@@ -361,7 +361,13 @@ def main():
     if args.mode == "train" and not args.no_eval:
         # the metric's second half: log-likelihood evaluation (UCIExperiments.py:152-162: S = nb_steps + 20), in the
         # fast mode (tensor-core UMNN forward + TF32 conditioner GEMMs, ll tolerance 2e-3)
-        extra = measure("eval", "tf32", "auto-fast", S + 20, args.steps, 3, False)
+        try:
+            extra = measure("eval", "tf32", "auto-fast", S + 20, args.steps, 3, False)
+        except RuntimeError as err:      # e.g. integrand weights too large to stay resident in shared memory
+            if "umnn tc" not in str(err):
+                raise
+            G.ops.enable_kernel_timing(False)
+            extra = measure("eval", "strict", "auto-fast", S + 20, args.steps, 3, False)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -378,7 +384,10 @@ def main():
             "kernel_ms": main_res["kernel_ms"]}
     if extra is not None:
         line["eval"] = {"metric": "loglik_eval_samples_per_s", "unit": "samples/s",
-                        "precision_mode": "tf32 (tcgen05 UMNN forward + single-pass TF32 conditioner GEMMs), ll tolerance 2e-3",
+                        "precision_mode": ("tf32 (tcgen05 UMNN forward + single-pass TF32 conditioner GEMMs), ll tolerance 2e-3"
+                                           if extra["precision"] == "tf32" else
+                                           "strict fp32 UMNN forward (integrand too wide for the resident-weight tensor-core kernel) + "
+                                           "single-pass TF32 conditioner GEMMs"),
                         **{k: extra[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "roofline", "achieved_tflops_step",
                                                  "algorithmic_gflop_per_step", "nb_steps", "kernel_ms")}}
     print(json.dumps(line))
