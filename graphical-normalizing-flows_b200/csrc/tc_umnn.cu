@@ -297,13 +297,13 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
     const long long q = (c < cta_tiles) ? ((long long)blockIdx.x + c * gridDim.x) * kTcRows + t : p.Q;
     valid = q < p.Q;
     r = 0; kn = 0; xv = 0.f;
-    if (valid) { r = (int)(q / nodes); kn = (int)(q % nodes); xv = __ldg(p.x + r); }
+    if (valid) { r = (int)(q / nodes); kn = (int)(q % nodes); xv = ldg_pinned(p.x + r); }
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
       float val = 0.f;
       if (valid && k < K0P) {
-        if (k == 0) val = (xv * (__ldg(p.ccn + kn) + 1.f)) / 2.f;
-        else if (k <= p.E) val = __ldg(p.h + (size_t)r * p.E + (k - 1));
+        if (k == 0) val = (xv * (ldg_pinned(p.ccn + kn) + 1.f)) / 2.f;
+        else if (k <= p.E) val = ldg_pinned(p.h + (size_t)r * p.E + (k - 1));
       }
       pre[k] = val;
     }
@@ -340,9 +340,16 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
       fence_after_sync();
       const uint32_t wbase = img_addr + p.off[layer] * 4u;
       const int nk = p.kp[layer] / 8;
-      for (int ks = 0; ks < nk; ++ks) {
-        const uint64_t bdesc = make_smem_desc(wbase + (uint32_t)ks * 2u * NP * 16u, NP * 16u, 128u);
-        mma_tf32_ts(tmem_base + rD, tmem_base + rA + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+      uint64_t bdesc = make_smem_desc(wbase, NP * 16u, 128u);
+      constexpr uint64_t kDescStep = (2u * NP * 16u) >> 4;       // one k-step = two 16-byte K chunks of the image
+      uint32_t ta = tmem_base + rA;
+      const uint32_t td = tmem_base + rD;
+      mma_tf32_ts(td, ta, bdesc, idesc, 0u);
+#pragma unroll 4
+      for (int ks = 1; ks < nk; ++ks) {
+        bdesc += kDescStep;
+        ta += 8;
+        mma_tf32_ts(td, ta, bdesc, idesc, 1u);
       }
       mma_commit(&bars[1 + g]);
     }
@@ -353,35 +360,51 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
     fence_after_sync();
     const uint32_t R = tmem_base + lane_sel + rD;
     const float* bl = bias + layer * NP;
-    // whole accumulator row -> registers in one burst (NP/16 loads in flight, one wait)
-    uint32_t v[NP];
-#pragma unroll
-    for (int c = 0; c < NP; c += 16) tmem_ld16p(R + c, &v[c]);
+    // Software-pipelined epilogue over 32-column chunks (a 16-column tail when NP % 32 != 0): chunk c+1's TMEM load is
+    // in flight while chunk c is processed.  TMEM reads are the scarce resource (~64 B/clk/SM), so the loads are kept
+    // back to back; tcgen05.wait::ld waits for ALL outstanding loads, hence exactly one chunk of look-ahead.
+    constexpr int NC = (NP + 31) / 32;
+    uint32_t buf[2][32];
+    float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+    if (NP >= 32) tmem_ld32p(R, buf[0]); else tmem_ld16p(R, buf[0]);
     tmem_wait_ld();
-    if (layer < L - 1) {
 #pragma unroll
-      for (int c = 0; c < NP; c += 16) {
+    for (int ci = 0; ci < NC; ++ci) {
+      const int c = ci * 32;
+      const int w = (NP - c >= 32) ? 32 : 16;               // width of this chunk
+      uint32_t* cur = buf[ci & 1];
+      uint32_t* nxt = buf[(ci + 1) & 1];
+      if (ci + 1 < NC) {
+        if (NP - (c + 32) >= 32) tmem_ld32p(R + c + 32, nxt); else tmem_ld16p(R + c + 32, nxt);
+      }
+      if (layer < L - 1) {
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bl + c + j4);
-          v[c + j4 + 0] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 0]) + b4.x, 0.f));
-          v[c + j4 + 1] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 1]) + b4.y, 0.f));
-          v[c + j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 2]) + b4.z, 0.f));
-          v[c + j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[c + j4 + 3]) + b4.w, 0.f));
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          if (j4 < w) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bl + c + j4);
+            cur[j4 + 0] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 0]) + b4.x, 0.f));
+            cur[j4 + 1] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 1]) + b4.y, 0.f));
+            cur[j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 2]) + b4.z, 0.f));
+            cur[j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(cur[j4 + 3]) + b4.w, 0.f));
+          }
         }
-        tmem_st16p(R + c, &v[c]);
-      }
-    } else {
-      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+        if (w == 32) tmem_st32p(R + c, cur); else tmem_st16p(R + c, cur);
+      } else {
 #pragma unroll
-      for (int c = 0; c < NP; c += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bl + c);
-        const float4 w4 = *reinterpret_cast<const float4*>(wlast + c);
-        y0 = fmaf(fmaxf(__uint_as_float(v[c + 0]) + b4.x, 0.f), w4.x, y0);
-        y1 = fmaf(fmaxf(__uint_as_float(v[c + 1]) + b4.y, 0.f), w4.y, y1);
-        y2 = fmaf(fmaxf(__uint_as_float(v[c + 2]) + b4.z, 0.f), w4.z, y2);
-        y3 = fmaf(fmaxf(__uint_as_float(v[c + 3]) + b4.w, 0.f), w4.w, y3);
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          if (j4 < w) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bl + c + j4);
+            const float4 w4 = *reinterpret_cast<const float4*>(wlast + c + j4);
+            y0 = fmaf(fmaxf(__uint_as_float(cur[j4 + 0]) + b4.x, 0.f), w4.x, y0);
+            y1 = fmaf(fmaxf(__uint_as_float(cur[j4 + 1]) + b4.y, 0.f), w4.y, y1);
+            y2 = fmaf(fmaxf(__uint_as_float(cur[j4 + 2]) + b4.z, 0.f), w4.z, y2);
+            y3 = fmaf(fmaxf(__uint_as_float(cur[j4 + 3]) + b4.w, 0.f), w4.w, y3);
+          }
+        }
       }
+      if (ci + 1 < NC) tmem_wait_ld();
+    }
+    if (layer == L - 1) {
       float y = (y0 + y1) + (y2 + y3);
       y += blast;
       const float f = (y > 0.f ? y : expm1f(y)) + 1.05f;
