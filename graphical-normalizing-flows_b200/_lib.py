@@ -76,6 +76,8 @@ _PROTOS = {
     "gnf_umnn_tc_workspace_bytes": ([C.POINTER(MlpT)], _SZ),
     "gnf_umnn_fwd_tc": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P], C.c_int),
     "gnf_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
+    "gnf_tc_probe": ([_I, _I, _P, _P], C.c_int),
+    "gnf_tc_set_trace": ([_P], C.c_int),
     "gnf_reverse_cols": ([_P, _P, _I, _I, _P], C.c_int),
     "gnf_broadcast_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_axpy": ([_F, _P, _P, _SZ, _P], C.c_int),

@@ -92,7 +92,10 @@ struct TcFwdParams {
   int kp[GNF_MAX_LAYERS];
   unsigned off[GNF_MAX_LAYERS];     // float offsets inside the image
   unsigned off_bias, off_wlast, total_floats;
+  long long* trace;                 // debug: per-phase SM clock stamps of CTA 0 (NULL in production)
 };
+
+static long long* g_tc_trace = nullptr;
 
 template <int NP>
 __global__ void __launch_bounds__(kTcRows) umnn_fwd_tc_kernel(TcFwdParams p) {
@@ -235,21 +238,28 @@ __global__ void __launch_bounds__(kTcRows) umnn_fwd_tc_kernel(TcFwdParams p) {
 // ------------------------------------------------------------------------------------------------
 // v2: two tiles in flight per CTA, three rotating TMEM regions.
 //
-// Warpgroup g (128 threads) owns the CTA's tiles of parity g.  The tensor pipe executes the MMAs of the two
-// tiles alternately (global MMA sequence m = 0,1,2,...; m % 2 = warpgroup); while tile X's layer runs on the
-// tensor cores, tile Y's epilogue (TMEM -> registers -> bias/ReLU -> TMEM, IN PLACE) runs on the CUDA cores.
+// Warpgroup g (128 threads) owns the CTA's tiles of parity g; a ninth warp is the MMA issuer.  The tensor pipe
+// executes the MMAs of the two tiles alternately (global MMA sequence m = 0,1,2,...; m % 2 = warpgroup); while tile
+// X's layer runs on the tensor cores, tile Y's epilogue (TMEM -> registers -> bias/ReLU -> TMEM, IN PLACE) runs on
+// the CUDA cores.  Hand-shake per tile: epi_done[g] (epilogue warps -> issuer) and mma_done[g] (tcgen05.commit).
 // With the in-place epilogue a tile needs two regions only while its MMA runs (A and D) and one otherwise, so
 // three NP-column regions suffice:   A(m) = m % 3,  D(m) = (m + 2) % 3   (D(m) is the region freed by MMA m-1).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
 template <int NP>
-__global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p) {
+__global__ void __launch_bounds__(2 * kTcRows + 32) umnn_fwd_tc2_kernel(TcFwdParams p) {
   using namespace tc;
   GNF_SMEM(float, smem);
   float* img = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((p.total_floats + 3) / 4) * 4);   // [0]: weights, [1],[2]: MMA done (wg 0/1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  float* red_all = reinterpret_cast<float*>(bars + 4);                                   // [2][128]
-  const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5;
+  // [0]: weights landed, [1],[2]: MMA done (tile parity 0/1), [3],[4]: epilogue done / input staged (parity 0/1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((p.total_floats + 3) / 4) * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* red_all = reinterpret_cast<float*>(bars + 6);                                   // [2][128]
+  const int tid = threadIdx.x, g = (tid >> 7) & 1, t = tid & 127, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer = warp == 8;
   float* red = red_all + g * kTcRows;
   const int nodes = p.S + 1;
   const int L = p.L;
@@ -259,6 +269,8 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 4);                  // one arrive per epilogue warp
+    mbar_init(&bars[4], 4);
     fence_mbar_init();
   }
   fence_before_sync();
@@ -320,43 +332,67 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
     }
   };
 
+  const long long n_iter = n_local * L;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && (is_issuer ? lane == 0 : t == 0);
+  auto stamp = [&](long long i, int gg, int slot) {
+    if (tracing && i < 24) p.trace[(i * 2 + gg) * 8 + slot] = clock64();
+  };
+
+  if (is_issuer) {
+    // ===================== MMA issuer warp =====================
+    if (lane == 0) {
+      for (long long i = 0; i < n_iter; ++i) {
+        const int layer = (int)(i % L);
+        const uint32_t wbase = img_addr + p.off[layer] * 4u;
+        const int nk = p.kp[layer] / 8;
+        for (int gg = 0; gg < 2; ++gg) {
+          const long long m = 2 * i + gg;
+          const uint32_t rA = (uint32_t)(m % 3) * NP, rD = (uint32_t)((m + 2) % 3) * NP;
+          // the tile's layer input is staged in TMEM (its previous epilogue, or the tile prologue)
+          mbar_wait(&bars[3 + gg], (uint32_t)(i & 1));
+          stamp(i, gg, 0);
+          // D(m) is the A region of MMA m-1: that MMA must have finished reading it
+          if (m > 0) {
+            const long long io = (gg == 1) ? i : i - 1;
+            mbar_wait(&bars[1 + (1 - gg)], (uint32_t)(io & 1));
+          }
+          stamp(i, gg, 1);
+          fence_after_sync();
+          uint64_t bdesc = make_smem_desc(wbase, NP * 16u, 128u);
+          constexpr uint64_t kDescStep = (2u * NP * 16u) >> 4;   // one k-step = two 16-byte K chunks of the image
+          uint32_t ta = tmem_base + rA;
+          const uint32_t td = tmem_base + rD;
+          mma_tf32_ts(td, ta, bdesc, idesc, 0u);
+#pragma unroll 4
+          for (int ks = 1; ks < nk; ++ks) {
+            bdesc += kDescStep;
+            ta += 8;
+            mma_tf32_ts(td, ta, bdesc, idesc, 1u);
+          }
+          mma_commit(&bars[1 + gg]);
+          stamp(i, gg, 2);
+        }
+      }
+    }
+  } else {
+  // ===================== epilogue warpgroups =====================
   // prologue: first tile's input into region A(m = g) = g
   load_tile_row(0);
   store_input(tmem_base + lane_sel + (uint32_t)(g % 3) * NP);
   tmem_wait_st();
   fence_before_sync();
-  named_bar_sync(1 + g, kTcRows);
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cta(&bars[3 + g]);
 
-  const long long n_iter = n_local * L;
   for (long long i = 0; i < n_iter; ++i) {
     const int layer = (int)(i % L);
     const long long m = 2 * i + g;
-    const uint32_t rA = (uint32_t)(m % 3) * NP, rD = (uint32_t)((m + 2) % 3) * NP;
-    if (t == 0) {
-      if (m > 0) {   // the region we are about to overwrite as D is the A operand of MMA m-1 (other warpgroup)
-        const long long io = (g == 1) ? i : i - 1;
-        mbar_wait(&bars[1 + (1 - g)], (uint32_t)(io & 1));
-      }
-      fence_after_sync();
-      const uint32_t wbase = img_addr + p.off[layer] * 4u;
-      const int nk = p.kp[layer] / 8;
-      uint64_t bdesc = make_smem_desc(wbase, NP * 16u, 128u);
-      constexpr uint64_t kDescStep = (2u * NP * 16u) >> 4;       // one k-step = two 16-byte K chunks of the image
-      uint32_t ta = tmem_base + rA;
-      const uint32_t td = tmem_base + rD;
-      mma_tf32_ts(td, ta, bdesc, idesc, 0u);
-#pragma unroll 4
-      for (int ks = 1; ks < nk; ++ks) {
-        bdesc += kDescStep;
-        ta += 8;
-        mma_tf32_ts(td, ta, bdesc, idesc, 1u);
-      }
-      mma_commit(&bars[1 + g]);
-    }
+    const uint32_t rD = (uint32_t)((m + 2) % 3) * NP;
     // what this thread needs after the last layer: its own row's result context, then the next tile's input
     bool cur_valid = valid; int cur_r = r, cur_kn = kn; float cur_xv = xv;
     if (layer == L - 1) load_tile_row(i / L + 1);      // prefetch while the tensor cores work
     mbar_wait(&bars[1 + g], (uint32_t)(i & 1));
+    stamp(i, g, 3);
     fence_after_sync();
     const uint32_t R = tmem_base + lane_sel + rD;
     const float* bl = bias + layer * NP;
@@ -406,6 +442,14 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
     }
     if (layer == L - 1) {
       float y = (y0 + y1) + (y2 + y3);
+      // next tile's input row goes in place into this region (its A for MMA m+2); hand the region to the issuer
+      // BEFORE the reduction / atomics so that they stay off the tensor pipe's critical path
+      store_input(R);
+      tmem_wait_st();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&bars[3 + g]);
+      stamp(i, g, 4);
       y += blast;
       const float f = (y > 0.f ? y : expm1f(y)) + 1.05f;
       float wv = 0.f;
@@ -416,25 +460,29 @@ __global__ void __launch_bounds__(2 * kTcRows) umnn_fwd_tc2_kernel(TcFwdParams p
           if (p.logdet) atomicAdd(p.logdet + cur_r / p.d, logf(f));
         }
       }
+      named_bar_sync(1 + g, kTcRows);           // previous tile's readers of red[] are done
       red[t] = wv;
       named_bar_sync(1 + g, kTcRows);
       if (cur_valid && (cur_kn == 0 || t == 0)) {
-        float s = 0.f;
+        float sacc = 0.f;
         int rem = nodes - cur_kn;
         if (rem > kTcRows - t) rem = kTcRows - t;
-        for (int k = 0; k < rem; ++k) s += red[t + k];
-        float c = s * cur_xv / 2.f;
+        for (int k = 0; k < rem; ++k) sacc += red[t + k];
+        float c = sacc * cur_xv / 2.f;
         if (cur_kn == 0) c += __ldg(p.h + (size_t)cur_r * p.E);
         atomicAdd(p.z + cur_r, c);
         if (p.zrev) { const int b = cur_r / p.d, ii = cur_r % p.d; atomicAdd(p.zrev + (size_t)b * p.d + (p.d - 1 - ii), c); }
       }
-      // next tile's input row, in place in this region (its A for MMA m+2)
-      store_input(R);
+      stamp(i, g, 5);
+    } else {
+      tmem_wait_st();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&bars[3 + g]);
+      stamp(i, g, 4);
     }
-    tmem_wait_st();
-    fence_before_sync();
-    named_bar_sync(1 + g, kTcRows);
   }
+  }  // epilogue warpgroups
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -508,6 +556,68 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
   if (warp == 0) tmem_dealloc(tmem_base, alloc_cols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Micro-probe (measurement tool, not on the product path): TMEM read bandwidth, tcgen05.mma issue rate, and whether
+// the two overlap.  mode bit0: 128 threads stream tcgen05.ld.x32 over 256 columns `iters` times; bit1: one thread
+// issues `iters` x 19 TF32 MMAs (M128 x N160 x K8, A from TMEM, B from shared memory).  out[0..1] = elapsed clocks of
+// the load warps / the MMA thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160) tc_probe_kernel(int mode, int iters, long long* out) {
+  using namespace tc;
+  GNF_SMEM(float, smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 160 * 152);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (t == 0) { mbar_init(&bars[0], 1); fence_mbar_init(); }
+  for (int i = t; i < 160 * 152; i += 160) smem[i] = 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    if (mode & 1) {
+      uint32_t acc = 0;
+      const long long c0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 256; c += 32) {
+          uint32_t r[32];
+          tmem_ld32p(tmem_base + lane_sel + 256 + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc ^= r[j];
+        }
+      }
+      const long long c1 = clock64();
+      if (t == 0) out[0] = c1 - c0;
+      if (acc == 0x12345678u) out[3] = acc;
+    }
+  } else if (t == 128) {
+    if (mode & 2) {
+      const uint32_t idesc = make_idesc_tf32(128, 160);
+      const uint32_t wbase = smem_u32(smem);
+      const long long c0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        uint64_t bdesc = make_smem_desc(wbase, 160 * 16u, 128u);
+        for (int ks = 0; ks < 19; ++ks) {
+          mma_tf32_ts(tmem_base + 0, tmem_base + 160 + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+          bdesc += (2u * 160 * 16u) >> 4;
+        }
+      }
+      mma_commit(&bars[0]);
+      mbar_wait(&bars[0], 0);
+      const long long c1 = clock64();
+      out[1] = c1 - c0;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 template <int NP>
 static int launch_tc_fwd(const TcFwdParams& p, size_t smem, cudaStream_t s) {
   const long long ntiles = (p.Q + kTcRows - 1) / kTcRows;
@@ -518,7 +628,7 @@ static int launch_tc_fwd(const TcFwdParams& p, size_t smem, cudaStream_t s) {
       cudaFuncSetAttribute(umnn_fwd_tc2_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
       long long grid = kNumSMs;
       if (grid > (ntiles + 1) / 2) grid = (ntiles + 1) / 2;
-      GNF_LAUNCH(umnn_fwd_tc2_kernel<NP>, (unsigned)grid, 2 * kTcRows, smem2, s, p);
+      GNF_LAUNCH(umnn_fwd_tc2_kernel<NP>, (unsigned)grid, 2 * kTcRows + 32, smem2, s, p);
       return 0;
     }
   }
@@ -579,6 +689,7 @@ int gnf_umnn_fwd_tc(const float* x, const float* h, const gnf_mlp_t* net, int S,
   p.Q = (long long)R * (S + 1);
   for (int l = 0; l < GNF_MAX_LAYERS; ++l) { p.kp[l] = l < pl.L ? pl.kp[l] : 0; p.off[l] = l < pl.L ? (unsigned)pl.off[l] : 0; }
   p.off_bias = (unsigned)pl.off_bias; p.off_wlast = (unsigned)pl.off_wlast; p.total_floats = (unsigned)pl.total_floats;
+  p.trace = g_tc_trace;
   const size_t smem = ((pl.total_floats + 3) / 4 * 4) * sizeof(float) + 4 * sizeof(uint64_t) + kTcRows * sizeof(float);
   int e = 0;
   switch (pl.NP) {
@@ -601,6 +712,29 @@ int gnf_umnn_fwd_tc(const float* x, const float* h, const gnf_mlp_t* net, int S,
   }
   if (e) return e;
   return check_launch("gnf_umnn_fwd_tc");
+#endif
+}
+
+/* Debug: subsequent gnf_umnn_fwd_tc calls record SM-clock stamps of CTA 0's phases into `buf`
+ * (48 x 8 x int64, device); NULL disables.  Not thread safe; measurement tool only. */
+int gnf_tc_set_trace(long long* buf) {
+#ifndef GNF_EMU
+  gnf::g_tc_trace = buf;
+#else
+  (void)buf;
+#endif
+  return 0;
+}
+
+/* Measurement tool: see tc_probe_kernel.  out: 4 x int64 (device). */
+int gnf_tc_probe(int mode, int iters, long long* out, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  const size_t smem = 160 * 152 * sizeof(float) + 64;
+  cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  GNF_LAUNCH(tc_probe_kernel, 1, 160, smem, (cudaStream_t)stream, mode, iters, out);
+  return check_launch("gnf_tc_probe");
 #endif
 }
 

@@ -210,6 +210,11 @@ size_t gnf_umnn_tc_workspace_bytes(const gnf_mlp_t* net);
 int gnf_umnn_fwd_tc(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
                     float* z, float* zrev, float* jac, float* logdet, int R, int d, void* work, size_t work_bytes,
                     gnf_stream_t stream);
+/* Measurement tool (not on the product path): TMEM-read bandwidth / MMA issue rate / overlap probe on one CTA.
+ * mode bit0: stream tcgen05.ld; bit1: issue TF32 MMAs; out[0], out[1]: elapsed SM clocks of the two roles. */
+int gnf_tc_probe(int mode, int iters, long long* out, gnf_stream_t stream);
+/* Debug / measurement: later gnf_umnn_fwd_tc calls write per-phase SM-clock stamps of CTA 0 into buf (48*8 int64). */
+int gnf_tc_set_trace(long long* buf);
 /* Self-test of the tcgen05 conventions: C[128,N] = A[128,K] W[N,K]^T on one CTA (mode 0: A staged in TMEM,
  * mode 1: A staged in shared memory).  N, K <= 256. */
 int gnf_tc_selftest(const float* A, const float* W, float* C, int N, int K, int mode, gnf_stream_t stream);
