@@ -210,6 +210,8 @@ def main():
                     help="conditioner GEMM engine: fp32 FFMA, tensor-core 3xTF32 (fp32-equivalent) or single-pass TF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="train mode: skip the additional log-lik eval measurement")
+    ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the training step as one captured CUDA graph (auto: on for single-GPU training)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -286,9 +288,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(mode, precision, gemm, S_, steps, warmup, sample_clocks):
+    def measure(mode, precision, gemm, S_, steps, warmup, sample_clocks, use_graph=False):
         """One arm: W warm-up steps, K device-timed steps (CUDA events per step, L2 flushed between steps), then K
-        end-to-end steps (pinned host batch -> H2D -> step -> loss D2H).  Max over ranks."""
+        end-to-end steps (pinned host batch -> H2D -> step -> loss D2H).  Max over ranks.
+        use_graph: the timed steps replay ONE captured CUDA graph of the whole training step; the per-kernel times for
+        the roofline object are then taken from a short eager pass first (a replay has no per-launch host hooks)."""
         G.ops.set_gemm_mode(gemm)
         for n in model.getNormalizers():
             if hasattr(n, "nb_steps"):
@@ -298,11 +302,27 @@ def main():
         for i in range(warmup):
             step(pool[i % n_pool])
         barrier()
+        eager_ktimes, eager_launches = None, 0
+        if use_graph:
+            l0 = G.ops.launch_count()
+            G.ops.enable_kernel_timing(True)
+            n_eager = min(steps, 10)
+            for i in range(n_eager):
+                step(pool[i % n_pool])
+            eager_ktimes = G.ops.collect_kernel_timing()
+            G.ops.enable_kernel_timing(False)
+            eager_launches = (G.ops.launch_count() - l0) // n_eager
+            graphed = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=True, warmup=3)
+            step = graphed
+            for i in range(3):
+                step(pool[i % n_pool])
+            barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0 and sample_clocks:
             sampler.start()
         l0 = G.ops.launch_count()
-        G.ops.enable_kernel_timing(True)
+        if not use_graph:
+            G.ops.enable_kernel_timing(True)
         evs = []
         barrier()
         for i in range(steps):
@@ -313,9 +333,12 @@ def main():
             e1.record()
             evs.append((e0, e1))
         barrier()
-        launches = G.ops.launch_count() - l0
-        ktimes = G.ops.collect_kernel_timing()
-        G.ops.enable_kernel_timing(False)
+        if use_graph:
+            launches, ktimes = eager_launches * steps, eager_ktimes
+        else:
+            launches = G.ops.launch_count() - l0
+            ktimes = G.ops.collect_kernel_timing()
+            G.ops.enable_kernel_timing(False)
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         barrier()
         t0 = time.perf_counter()
@@ -353,10 +376,15 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "achieved_tflops_step": flops_step / (dev_ms / steps / 1e3) / 1e12, "algorithmic_gflop_per_step": flops_step / 1e9,
                 "last_loss": last, "kernel_ms": {k: sum(v) / len(v) for k, v in ktimes.items() if v},
-                "nb_steps": S_, "precision": precision, "gemm_engine": gemm}
+                "nb_steps": S_, "precision": precision, "gemm_engine": gemm, "cuda_graph": bool(use_graph)}
 
     config["gemm_engine"] = args.gemm
-    main_res = measure(args.mode, args.precision, args.gemm, S, args.steps, args.warmup, True)
+    use_graph = args.mode == "train" and (args.cuda_graph == "on" or (args.cuda_graph == "auto" and world == 1))
+    config["cuda_graph"] = use_graph
+    opt_kwargs = dict(lr=lr, weight_decay=wd, fused=True, capturable=True) if use_graph else None
+    if use_graph:
+        opt = torch.optim.Adam(model.parameters(), **opt_kwargs)
+    main_res = measure(args.mode, args.precision, args.gemm, S, args.steps, args.warmup, True, use_graph)
     extra = None
     if args.mode == "train" and not args.no_eval:
         # the metric's second half: log-likelihood evaluation (UCIExperiments.py:152-162: S = nb_steps + 20), in the

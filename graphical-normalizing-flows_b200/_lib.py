@@ -24,7 +24,7 @@ _SIMULATOR = False
 
 class GateT(C.Structure):
     _fields_ = [("mode", C.c_int32), ("temperature", C.c_float), ("seed", C.c_uint64), ("offset", C.c_uint64),
-                ("noise1", C.c_void_p), ("noise2", C.c_void_p)]
+                ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("offset_dev", C.c_void_p)]
 
 
 class MlpT(C.Structure):
@@ -80,6 +80,7 @@ _PROTOS = {
     "gnf_tc_set_trace": ([_P], C.c_int),
     "gnf_reverse_cols": ([_P, _P, _I, _I, _P], C.c_int),
     "gnf_broadcast_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
+    "gnf_counter_add": ([_P, C.c_uint64, _P], C.c_int),
     "gnf_axpy": ([_F, _P, _P, _SZ, _P], C.c_int),
 }
 

@@ -102,6 +102,7 @@ class DAGConditioner(Conditioner):
         self._noise_calls = 0
         self._noise_rank = 0
         self._replay_noise = None       # tests: tuple of [B,d,d] tensors replaying the reference's draws once
+        self._noise_counter = None      # device int64 counter used instead of the host call count (CUDA graphs)
 
     # ---- small host helpers -------------------------------------------------------------------
     def getAlpha(self):
@@ -155,6 +156,10 @@ class DAGConditioner(Conditioner):
             return ops.GateSpec(mode, imp, self.h_thresh, self.gumble_T, noise=tuple(noise))
         if self._noise_seed is None:
             self._noise_seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # follows torch.manual_seed
+        if self._noise_counter is not None:
+            # graph-capturable: the Philox offset lives on the device and is bumped inside the captured step
+            return ops.GateSpec(mode, imp, self.h_thresh, self.gumble_T, seed=self._noise_seed,
+                                offset=(self._noise_rank << 40), offset_dev=self._noise_counter)
         self._noise_calls += 1
         return ops.GateSpec(mode, imp, self.h_thresh, self.gumble_T, seed=self._noise_seed,
                             offset=(self._noise_rank << 40) + self._noise_calls)

@@ -119,6 +119,10 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ c, float* __rest
   }
 }
 
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *c += inc;
+}
+
 __global__ void axpy_kernel(float a, const float* __restrict__ x, float* __restrict__ y, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaf(a, x[i], y[i]);
 }
@@ -189,6 +193,12 @@ int gnf_broadcast_rows(const float* constants, float* h, int B, int d, int indep
   if (B == 0 || indep == 0) return 0;
   GNF_LAUNCH(broadcast_rows_kernel, flat_blocks((size_t)B * indep * H), 256, 0, (cudaStream_t)stream, constants, h, B, d, indep, H);
   return check_launch("gnf_broadcast_rows");
+}
+
+int gnf_counter_add(uint64_t* counter, uint64_t inc, gnf_stream_t stream) {
+  if (!counter) return fail(GNF_ERR_INVALID, "gnf_counter_add: bad arguments");
+  GNF_LAUNCH(counter_add_kernel, 1, 32, 0, (cudaStream_t)stream, reinterpret_cast<unsigned long long*>(counter), (unsigned long long)inc);
+  return check_launch("gnf_counter_add");
 }
 
 int gnf_axpy(float a, const float* x, float* y, size_t n, gnf_stream_t stream) {

@@ -15,6 +15,7 @@ struct GateCtx {
   const float* n1;  // replayed noise (nullable)
   const float* n2;
   uint64_t seed, offset;
+  const uint64_t* offset_dev;  // optional device-side addend to `offset`
   float T;
   int mode, d;
 };
@@ -25,7 +26,7 @@ __device__ __forceinline__ void gate_noise(const GateCtx& g, size_t idx, float& 
     b = g.n2 ? __ldg(g.n2 + idx) : 0.f;
     return;
   }
-  const uint4 r = Philox::gen(g.seed, (uint64_t)idx, g.offset);
+  const uint4 r = Philox::gen(g.seed, (uint64_t)idx, g.offset + (g.offset_dev ? *g.offset_dev : 0ull));
   if (g.mode == GNF_GATE_GUMBEL) {
     a = Philox::u01(r.x);
     b = Philox::u01(r.y);
@@ -101,7 +102,8 @@ static int make_gate(GateCtx* out, const float* x, const float* P, const gnf_gat
   if (gate->mode == GNF_GATE_GUMBEL && ((gate->noise1 == nullptr) != (gate->noise2 == nullptr)))
     return fail(GNF_ERR_INVALID, "Gumbel replay needs both noise tensors");
   out->x = x; out->P = P; out->n1 = gate->noise1; out->n2 = gate->noise2;
-  out->seed = gate->seed; out->offset = gate->offset; out->T = gate->temperature; out->mode = gate->mode; out->d = d;
+  out->seed = gate->seed; out->offset = gate->offset; out->offset_dev = gate->offset_dev;
+  out->T = gate->temperature; out->mode = gate->mode; out->d = d;
   return 0;
 }
 

@@ -1,0 +1,53 @@
+"""CUDA-graph capture of a whole training step (zero_grad -> forward -> loss -> backward -> [all-reduce] -> optimizer).
+
+The step of the small configs is launch-bound (tens of kernels of a few microseconds each): replaying one captured
+graph removes the per-launch gaps.  Everything inside the step is already asynchronous on the current stream and
+allocation-stable; the one host-side quantity that changed per step, the Philox offset of the DAG gate noise, is moved
+to a device counter (gnf_gate_t.offset_dev) that the captured step bumps itself.
+"""
+import torch
+
+from . import ops
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, bucket, example_x, allreduce=True, warmup=3):
+        self.model, self.opt, self.bucket = model, optimizer, bucket
+        self.static_x = example_x.clone()
+        dev = example_x.device
+        self.counters = []
+        for c in model.getConditioners():
+            if hasattr(c, "_noise_counter"):
+                if c._noise_seed is None:
+                    c._noise_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                c._noise_counter = torch.full((1,), c._noise_calls + 1, dtype=torch.int64, device=dev)
+                self.counters.append(c._noise_counter)
+        self.allreduce = allreduce
+
+        def body():
+            for cnt in self.counters:
+                ops.counter_add(cnt, 1)
+            bucket.zero()
+            z, jac = model(self.static_x)
+            loss = model.loss(z, jac)
+            loss.backward()
+            if allreduce:
+                bucket.allreduce_mean()
+            optimizer.step()
+            return loss.detach()
+
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = body()
+
+    def __call__(self, x):
+        self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

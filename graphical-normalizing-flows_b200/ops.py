@@ -412,9 +412,10 @@ def broadcast_rows(constants, h, indep):
 class GateSpec:
     """Host description of DAGConditioner's gating branch (DAGConditioner.py:126-153)."""
 
-    def __init__(self, mode, imp, h_thresh=0., T=1., seed=0, offset=0, noise=None):
+    def __init__(self, mode, imp, h_thresh=0., T=1., seed=0, offset=0, noise=None, offset_dev=None):
         self.mode, self.imp, self.h_thresh, self.T = mode, imp, float(h_thresh), float(T)
         self.seed, self.offset, self.noise = int(seed), int(offset), noise
+        self.offset_dev = offset_dev        # optional device int64 counter added to `offset` (CUDA-graph replays)
 
     def c_struct(self):
         g = L.GateT()
@@ -422,6 +423,7 @@ class GateSpec:
         n = self.noise or ()
         g.noise1 = n[0].data_ptr() if len(n) > 0 else None
         g.noise2 = n[1].data_ptr() if len(n) > 1 else None
+        g.offset_dev = self.offset_dev.data_ptr() if self.offset_dev is not None else None
         return g
 
 
@@ -429,7 +431,7 @@ def dag_dump_noise(gate, B, d, device):
     """Materialise the in-kernel Philox draws of a GateSpec (parity / debugging hook)."""
     n1 = torch.empty(B, d, d, device=device, dtype=torch.float32)
     n2 = torch.empty(B, d, d, device=device, dtype=torch.float32) if gate.mode == L.GATE_GUMBEL else None
-    g = GateSpec(gate.mode, gate.imp, gate.h_thresh, gate.T, gate.seed, gate.offset, None).c_struct()
+    g = GateSpec(gate.mode, gate.imp, gate.h_thresh, gate.T, gate.seed, gate.offset, None, gate.offset_dev).c_struct()
     _call("gnf_dag_dump_noise", C.byref(g), ptr(n1), ptr(n2), B, d, stream_ptr())
     _count()
     return (n1, n2) if n2 is not None else (n1,)
@@ -626,6 +628,12 @@ class UmnnFn(torch.autograd.Function):
         for l in range(n):
             out += [dWs[l], dbs[l]]
         return tuple(out)
+
+
+def counter_add(counter, inc=1):
+    """*counter += inc on the device (int64 tensor with one element)."""
+    _call("gnf_counter_add", ptr(counter), int(inc), stream_ptr())
+    _count()
 
 
 def tc_selftest(A, W, mode):

@@ -141,6 +141,8 @@ typedef struct {
   uint64_t offset;     /* Philox counter offset (advanced by the caller per forward) */
   const float* noise1; /* optional replay of the reference's draws: u1 (Gumbel) or n (noiser), [B,d,d] */
   const float* noise2; /* u2 (Gumbel), [B,d,d] */
+  const uint64_t* offset_dev; /* optional device counter added to `offset` (lets a captured CUDA graph draw fresh
+                                 noise on every replay: the counter is bumped by gnf_counter_add inside the graph) */
 } gnf_gate_t;
 
 /* Importance table P[d,d] and dP/dA[d,d] from A (DAGConditioner.py:118-124).
@@ -226,6 +228,8 @@ int gnf_tc_selftest(const float* A, const float* W, float* C, int N, int K, int 
 int gnf_reverse_cols(const float* src, float* dst, int B, int d, gnf_stream_t stream);
 /* CouplingConditioner: h[b,i,:] = constants[i,:] for i < indep (CouplingConditioner.py:33). h: [B,d,H]. */
 int gnf_broadcast_rows(const float* constants, float* h, int B, int d, int indep, int H, gnf_stream_t stream);
+/* *counter += inc  (device-side Philox offset for graph-captured training steps). */
+int gnf_counter_add(uint64_t* counter, uint64_t inc, gnf_stream_t stream);
 /* y[i] += a * x[i]  (flat gradient bucket packing / scaling for the data-parallel all-reduce). */
 int gnf_axpy(float a, const float* x, float* y, size_t n, gnf_stream_t stream);
 
