@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="train mode: skip the additional log-lik eval measurement")
     ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the training step as one captured CUDA graph (auto: on for single-GPU training)")
+                    help="replay the training step (incl. the NCCL gradient all-reduce) as one captured CUDA graph (auto = on)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -379,7 +379,7 @@ def main():
                 "nb_steps": S_, "precision": precision, "gemm_engine": gemm, "cuda_graph": bool(use_graph)}
 
     config["gemm_engine"] = args.gemm
-    use_graph = args.mode == "train" and (args.cuda_graph == "on" or (args.cuda_graph == "auto" and world == 1))
+    use_graph = args.mode == "train" and args.cuda_graph in ("on", "auto")
     config["cuda_graph"] = use_graph
     opt_kwargs = dict(lr=lr, weight_decay=wd, fused=True, capturable=True) if use_graph else None
     if use_graph:
