@@ -187,9 +187,12 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[4][TN], const float* __re
   }
 }
 
-// Epilogue: out[col][row] = relu(acc + bias[col])  (k-major store, float4 over the thread's 4 rows)
+// Epilogue: out[col][row] = relu(acc + bias[col])  (k-major store, float4 over the thread's 4 rows).
+// gsave (nullable): also keep the activations in global memory, row-major [tile row][gsave_ld], for a backward that
+// loads them instead of recomputing the forward (rows >= rows_valid are not written).
 template <int TN>
-__device__ __forceinline__ void store_bias_relu(const float (&acc)[4][TN], const float* __restrict__ bias, float* __restrict__ act_out) {
+__device__ __forceinline__ void store_bias_relu(const float (&acc)[4][TN], const float* __restrict__ bias, float* __restrict__ act_out,
+                                                float* __restrict__ gsave = nullptr, int gsave_ld = 0, int rows_valid = 0) {
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
@@ -201,6 +204,13 @@ __device__ __forceinline__ void store_bias_relu(const float (&acc)[4][TN], const
     o.z = fmaxf(acc[2][j] + b, 0.f);
     o.w = fmaxf(acc[3][j] + b, 0.f);
     *reinterpret_cast<float4*>(act_out + (size_t)col * kLDR + 4 * ty) = o;
+    if (gsave) {
+      float* gp = gsave + (size_t)(4 * ty) * gsave_ld + col;
+      if (4 * ty + 0 < rows_valid) gp[0] = o.x;
+      if (4 * ty + 1 < rows_valid) gp[(size_t)gsave_ld] = o.y;
+      if (4 * ty + 2 < rows_valid) gp[(size_t)2 * gsave_ld] = o.z;
+      if (4 * ty + 3 < rows_valid) gp[(size_t)3 * gsave_ld] = o.w;
+    }
   }
 }
 
@@ -218,6 +228,7 @@ __device__ __forceinline__ void last_layer(const float* __restrict__ act, const 
 struct UmnnFwdParams {
   const float* x; const float* h; const float* ccw; const float* ccn;
   float* z; float* zrev; float* jac; float* logdet;
+  float* saved;   // nullable: [Q][L*NP] hidden activations kept for the backward
   int R, d, E, S;
   long long Q;  // R*(S+1)
   UmnnPacked pk;
@@ -258,7 +269,13 @@ __global__ void __launch_bounds__(kUThreads) umnn_fwd_kernel(UmnnFwdParams p) {
     float acc[4][TN];
     for (int l = 0; l < p.pk.L; ++l) {
       tile_gemm<TN>(acc, cur, p.pk.Wt[l], p.pk.kpad[l] / kKC, wp);
-      store_bias_relu<TN>(acc, p.pk.bias[l], nxt);
+      if (p.saved) {
+        const long long left = p.Q - q0;
+        store_bias_relu<TN>(acc, p.pk.bias[l], nxt, p.saved + (size_t)q0 * (p.pk.L * NP) + (size_t)l * NP, p.pk.L * NP,
+                            left < kTileM ? (int)left : kTileM);
+      } else {
+        store_bias_relu<TN>(acc, p.pk.bias[l], nxt);
+      }
       float* tmp = cur; cur = nxt; nxt = tmp;
       __syncthreads();
     }
@@ -310,6 +327,7 @@ struct UmnnBwdParams {
   const float* gz; const float* gzrev; const float* gjac; const float* glogdet;
   float* dx; float* dh;
   float* dW[GNF_MAX_LAYERS]; float* db[GNF_MAX_LAYERS];
+  const float* saved;   // nullable: the forward's hidden activations [R*(S+1)][L*NP]; NULL -> recompute
   int R, d, E, S;
   long long Q;  // R*(S+2)
   UmnnPacked pk;
@@ -401,8 +419,32 @@ __global__ void __launch_bounds__(kUThreads) umnn_bwd_kernel(UmnnBwdParams p) {
       actb[0][(size_t)k * kLDR + row] = v;
     }
     __syncthreads();
-    // ---- recompute forward, keeping every activation
-    {
+    // ---- hidden activations of every layer: reload the ones the forward kept (180 GB of HBM buys back a third of
+    //      the backward's FLOPs), or recompute them like UMNN does when the caller passed no buffer
+    if (p.saved) {
+      const int row = t & 63, part = t >> 6;
+      const long long q = q0 + row;
+      const bool ok = q < p.Q;
+      long long qf = 0;
+      if (ok) {
+        const long long r = q / nodes;
+        const int kn = (int)(q % nodes);
+        qf = r * (p.S + 1) + (kn <= p.S ? kn : 0);       // the extra node evaluates the integrand at x = node 0
+      }
+      const float4* src = reinterpret_cast<const float4*>(p.saved + (size_t)qf * (L * NP));
+      for (int l = 0; l < L; ++l) {
+        float* dst = actb[l + 1] + row;
+#pragma unroll 2
+        for (int c4 = part; c4 < NP / 4; c4 += 4) {
+          const float4 v = ok ? __ldg(src + (size_t)l * (NP / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[(size_t)(4 * c4 + 0) * kLDR] = v.x;
+          dst[(size_t)(4 * c4 + 1) * kLDR] = v.y;
+          dst[(size_t)(4 * c4 + 2) * kLDR] = v.z;
+          dst[(size_t)(4 * c4 + 3) * kLDR] = v.w;
+        }
+      }
+      __syncthreads();
+    } else {
       float acc[4][TN];
       for (int l = 0; l < L; ++l) {
         tile_gemm<TN>(acc, actb[l], p.pk.Wt[l], p.pk.kpad[l] / kKC, wp);
@@ -577,8 +619,16 @@ size_t gnf_umnn_workspace_bytes(const gnf_mlp_t* net) {
   return pl.total * sizeof(float);
 }
 
+size_t gnf_umnn_saved_floats_per_node_row(const gnf_mlp_t* net) {
+  PackPlan pl;
+  int TN;
+  if (make_plan(net, &pl, &TN)) return 0;
+  return (size_t)(net->n_layers - 1) * pl.NP;
+}
+
 int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn, float* z,
-                 float* zrev, float* jac, float* logdet, int R, int d, void* work, size_t work_bytes, gnf_stream_t stream) {
+                 float* zrev, float* jac, float* logdet, float* saved, int R, int d, void* work, size_t work_bytes,
+                 gnf_stream_t stream) {
   if (!x || !h || !net || !ccw || !ccn || !z || !jac || R < 0 || d <= 0 || S < 1 || (R % d) != 0) return fail(GNF_ERR_INVALID, "gnf_umnn_fwd: bad arguments");
   PackPlan pl;
   int TN;
@@ -591,7 +641,7 @@ int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, co
   if (zrev) cudaMemsetAsync(zrev, 0, (size_t)R * sizeof(float), s);
   if (logdet) cudaMemsetAsync(logdet, 0, (size_t)(R / d) * sizeof(float), s);
   UmnnFwdParams p;
-  p.x = x; p.h = h; p.ccw = ccw; p.ccn = ccn; p.z = z; p.zrev = zrev; p.jac = jac; p.logdet = logdet;
+  p.x = x; p.h = h; p.ccw = ccw; p.ccn = ccn; p.z = z; p.zrev = zrev; p.jac = jac; p.logdet = logdet; p.saved = saved;
   p.R = R; p.d = d; p.E = net->dims[0] - 1; p.S = S; p.Q = (long long)R * (S + 1);
   fill_packed(net, pl, (float*)work, &p.pk);
   int e = 0;
@@ -608,8 +658,9 @@ int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, co
 }
 
 int gnf_umnn_bwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
-                 const float* jac, const float* gz, const float* gzrev, const float* gjac, const float* glogdet, float* dx,
-                 float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work, size_t work_bytes, gnf_stream_t stream) {
+                 const float* jac, const float* gz, const float* gzrev, const float* gjac, const float* glogdet,
+                 const float* saved, float* dx, float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work,
+                 size_t work_bytes, gnf_stream_t stream) {
   if (!x || !h || !net || !ccw || !ccn || !jac || !dx || !dh || !grads || R < 0 || d <= 0 || S < 1 || (R % d) != 0) return fail(GNF_ERR_INVALID, "gnf_umnn_bwd: bad arguments");
   PackPlan pl;
   int TN;
@@ -628,7 +679,7 @@ int gnf_umnn_bwd(const float* x, const float* h, const gnf_mlp_t* net, int S, co
   launch_pack(net, pl, (float*)work, s);
   UmnnBwdParams p;
   p.x = x; p.h = h; p.ccw = ccw; p.ccn = ccn; p.jac = jac; p.gz = gz; p.gzrev = gzrev; p.gjac = gjac; p.glogdet = glogdet;
-  p.dx = dx; p.dh = dh;
+  p.dx = dx; p.dh = dh; p.saved = saved;
   for (int l = 0; l < GNF_MAX_LAYERS; ++l) { p.dW[l] = grads->dW[l]; p.db[l] = grads->db[l]; }
   p.R = R; p.d = d; p.E = E; p.S = S; p.Q = (long long)R * (S + 2);
   fill_packed(net, pl, (float*)work, &p.pk);

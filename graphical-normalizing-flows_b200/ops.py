@@ -524,6 +524,10 @@ class DagMlpFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 _CC_CACHE = {}
 
+# The strict UMNN forward keeps its hidden activations for the backward when they fit in this many bytes (else the
+# backward recomputes them, as UMNN does).  0 disables.
+SAVE_ACTIVATIONS_MAX_BYTES = 16 << 30
+
 
 def cc_weights(nb_steps, device):
     """Clenshaw-Curtis weights / nodes, float64 numpy -> fp32, exactly as UMNN's compute_cc_weights
@@ -586,9 +590,21 @@ class UmnnFn(torch.autograd.Function):
         jac = torch.empty_like(x)
         zrev = torch.empty_like(x) if want_rev else None
         logdet = torch.empty(B, device=x.device, dtype=x.dtype)
-        _call("gnf_umnn_fwd_tc" if fast else "gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac), ptr(logdet),
-                                 R, d, ptr(ws), nbytes, stream_ptr())
+        saved = None
+        if fast:
+            _call("gnf_umnn_fwd_tc", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
+                  ptr(logdet), R, d, ptr(ws), nbytes, stream_ptr())
+        else:
+            # training: keep the hidden activations for the backward when they fit the budget (B200: 180 GB of HBM)
+            if any(ctx.needs_input_grad) and SAVE_ACTIVATIONS_MAX_BYTES > 0:
+                per_row = lib().gnf_umnn_saved_floats_per_node_row(C.byref(net))
+                need = R * (int(S) + 1) * per_row * 4
+                if 0 < need <= SAVE_ACTIVATIONS_MAX_BYTES:
+                    saved = torch.empty(R * (int(S) + 1) * per_row, device=x.device, dtype=torch.float32)
+            _call("gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
+                  ptr(logdet), ptr(saved), R, d, ptr(ws), nbytes, stream_ptr())
         _count(2)
+        ctx.saved_acts = saved
         ctx.save_for_backward(x, h, jac, *weights, *biases)
         ctx.S, ctx.want_rev, ctx.n = int(S), want_rev, len(weights)
         ctx.set_materialize_grads(False)
@@ -622,7 +638,8 @@ class UmnnFn(torch.autograd.Function):
             grads.dW[l] = dWs[l].data_ptr()
             grads.db[l] = dbs[l].data_ptr()
         _call("gnf_umnn_bwd", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev), ptr(gjac),
-                                 ptr(glogdet), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr())
+              ptr(glogdet), ptr(ctx.saved_acts), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr())
+        ctx.saved_acts = None
         _count(2)
         out = [dx, dh, None, None, None]
         for l in range(n):

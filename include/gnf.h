@@ -192,17 +192,21 @@ size_t gnf_umnn_workspace_bytes(const gnf_mlp_t* net);
 /* x: [R] (R = B*d rows, row r = b*d+i), h: [R,E] -> z[r] = int_0^x f(t;h_r)dt + h[r,0], jac[r] = f(x;h_r).
  * ccw / ccn: [S+1] Clenshaw-Curtis weights and nodes cos(k pi/S) (fp32, computed in float64 by the
  * caller exactly like UMNN's compute_cc_weights).  zrev (nullable): z with the d columns reversed.
- * logdet (nullable): [R/d], logdet[b] = sum_i log jac[b,i]. */
+ * logdet (nullable): [R/d], logdet[b] = sum_i log jac[b,i].
+ * saved (nullable): [R*(S+1), gnf_umnn_saved_floats_per_node_row(net)] buffer in which the forward keeps every hidden
+ * activation; handing it to gnf_umnn_bwd replaces the backward's forward recompute (UMNN's memory-saving choice) by a
+ * reload — HBM capacity traded for a third of the backward's FLOPs. */
+size_t gnf_umnn_saved_floats_per_node_row(const gnf_mlp_t* net);
 int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
-                 float* z, float* zrev, float* jac, float* logdet, int R, int d, void* work, size_t work_bytes,
-                 gnf_stream_t stream);
+                 float* z, float* zrev, float* jac, float* logdet, float* saved, int R, int d, void* work,
+                 size_t work_bytes, gnf_stream_t stream);
 /* Cotangents: gz [R], gzrev [R] (nullable), gjac [R] (nullable), glogdet [R/d] (nullable).
  * Gradient convention = UMNN's: dtheta, dh by quadrature of the integrand's gradients with weights
  * w_k*gz*x/2; dx by the Leibniz rule f(x)*gz; the jac output is differentiated by the plain chain rule. */
 int gnf_umnn_bwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
                  const float* jac, const float* gz, const float* gzrev, const float* gjac, const float* glogdet,
-                 float* dx, float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work, size_t work_bytes,
-                 gnf_stream_t stream);
+                 const float* saved, float* dx, float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work,
+                 size_t work_bytes, gnf_stream_t stream);
 
 /* Tensor-core ("fast", single-pass TF32 operands / fp32 TMEM accumulation) forward of the same integral:
  * tcgen05.mma with the activation chain resident in TMEM and all weights resident in shared memory.

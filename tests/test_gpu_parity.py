@@ -282,3 +282,26 @@ def test_cuda_graph_replays_draw_fresh_gate_noise():
     step = G.GraphedTrainStep(model, opt, bucket, x, allreduce=False, warmup=3)
     l1, l2 = float(step(x)), float(step(x))
     assert l1 != l2, "two replays on the same batch with lr=0 must differ through the stochastic gate noise"
+
+
+def test_umnn_backward_saved_activations_equals_recompute():
+    """The backward that reloads the forward's hidden activations and the one that recomputes them (UMNN's way) give the
+    same gradients (bit-identical activations; only the atomics' order differs)."""
+    M = _mvo()
+    model = M.build(M.CONFIGS["cfg4"], "cuda", seed=2)
+    parity.set_modes(model, dict(stoch_gate=False))
+    x = torch.randn(40, 63, device="cuda")
+    grads = []
+    old = G.ops.SAVE_ACTIVATIONS_MAX_BYTES
+    try:
+        for budget in (16 << 30, 0):
+            G.ops.SAVE_ACTIVATIONS_MAX_BYTES = budget
+            model.zero_grad()
+            z, jac = model(x)
+            model.loss(z, jac).backward()
+            grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+    finally:
+        G.ops.SAVE_ACTIVATIONS_MAX_BYTES = old
+    for k in grads[0]:
+        err = float((grads[0][k] - grads[1][k]).norm() / grads[1][k].norm().clamp_min(1e-20))
+        assert err < 1e-5, (k, err)
