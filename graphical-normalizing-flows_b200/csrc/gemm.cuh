@@ -26,6 +26,7 @@ struct TileCfg {
 };
 
 using TileBig = TileCfg<128, 128, 16, 8, 8>;   // 256 threads, 8x8 per thread
+using TileMid = TileCfg<128, 64, 16, 8, 4>;    // 256 threads, 8x4 per thread (32 < N <= 64)
 using TileSkinny = TileCfg<128, 32, 16, 4, 4>; // 256 threads, 4x4 per thread (N <= 32)
 
 template <class Cfg, class ALoad, class BLoad, class Epi>
@@ -208,6 +209,25 @@ struct EpiStore {  // C = acc
     for (int j = 0; j < nv; ++j) C[(size_t)m * ld + n + j] = v[j];
   }
 };
+
+template <class Cfg, class ALoad, class BLoad, class Epi>
+static inline void launch_gemm(const ALoad& al, const BLoad& bl, const Epi& epi, int M, int N, int K, int splits, cudaStream_t stream);
+
+// Pick the tile by output width: 128x128 (N > 64), 128x64 (32 < N <= 64), 128x32 (N <= 32).
+template <class ALoad, class BLoad, class Epi>
+static inline void launch_gemm_auto(const ALoad& al, const BLoad& bl, const Epi& epi, int M, int N, int K, bool split_k, cudaStream_t stream) {
+  auto splits = [&](int bm, int bn) {
+    if (!split_k) return 1;
+    const int tiles = ceil_div(M, bm) * ceil_div(N, bn);
+    int want = ceil_div(2 * kNumSMs, tiles);
+    const int maxs = ceil_div(K, 4 * 16);
+    if (want > maxs) want = maxs;
+    return want < 1 ? 1 : want;
+  };
+  if (N <= 32) launch_gemm<TileSkinny>(al, bl, epi, M, N, K, splits(128, 32), stream);
+  else if (N <= 64) launch_gemm<TileMid>(al, bl, epi, M, N, K, splits(128, 64), stream);
+  else launch_gemm<TileBig>(al, bl, epi, M, N, K, splits(128, 128), stream);
+}
 
 template <class Cfg, class ALoad, class BLoad, class Epi>
 static inline void launch_gemm(const ALoad& al, const BLoad& bl, const Epi& epi, int M, int N, int K, int splits,

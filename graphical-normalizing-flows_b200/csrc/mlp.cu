@@ -228,14 +228,6 @@ static inline int ew_blocks(size_t n) {
   if (b > (size_t)8 * kNumSMs) b = (size_t)8 * kNumSMs;
   return b < 1 ? 1 : (int)b;
 }
-static inline int pick_splits(int Mout, int Nout, int Kred, int BM, int BN, int BK) {
-  const int tiles = ceil_div(Mout, BM) * ceil_div(Nout, BN);
-  int want = ceil_div(2 * kNumSMs, tiles);
-  const int maxs = ceil_div(Kred, 4 * BK);
-  if (want > maxs) want = maxs;
-  return want < 1 ? 1 : want;
-}
-
 }  // namespace gnf
 
 using namespace gnf;
@@ -250,8 +242,7 @@ int gnf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float
   LoadRowMajorA al{X, ldx};
   LoadWeightT bl{W, ldw};
   EpiBiasAct epi{Y, ldy, bias, N, bias_period < 1 ? 1 : bias_period, relu};
-  if (N <= 32) launch_gemm<TileSkinny>(al, bl, epi, M, N, K, 1, s);
-  else launch_gemm<TileBig>(al, bl, epi, M, N, K, 1, s);
+  launch_gemm_auto(al, bl, epi, M, N, K, false, s);
   return check_launch("gnf_linear_fwd");
 }
 
@@ -263,8 +254,7 @@ int gnf_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const f
   LoadRowMajorA al{dY, lddy};        // A(m, n) reduction over n
   LoadRowMajorB bl{W, ldw};          // B(n, k) = W[n, k]
   EpiMaskStore epi{dX, lddx, act, ldact};
-  if (K <= 32) launch_gemm<TileSkinny>(al, bl, epi, M, K, N, 1, s);
-  else launch_gemm<TileBig>(al, bl, epi, M, K, N, 1, s);
+  launch_gemm_auto(al, bl, epi, M, K, N, false, s);
   return check_launch("gnf_linear_dgrad");
 }
 
@@ -277,8 +267,7 @@ int gnf_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* 
   LoadColMajorA al{dY, lddy};        // A(n, m) = dY[m, n]
   LoadRowMajorB bl{X, ldx};          // B(m, k) = X[m, k]
   EpiAtomicAdd epi{dW, lddw};
-  if (K <= 32) launch_gemm<TileSkinny>(al, bl, epi, N, K, M, pick_splits(N, K, M, 128, 32, 16), s);
-  else launch_gemm<TileBig>(al, bl, epi, N, K, M, pick_splits(N, K, M, 128, 128, 16), s);
+  launch_gemm_auto(al, bl, epi, N, K, M, true, s);
   return check_launch("gnf_linear_wgrad");
 }
 
@@ -351,8 +340,7 @@ int gnf_dag_l1_fwd(const float* x, const float* P, const gnf_gate_t* gate, const
   LoadWeightT bl{W1, ldw};
   EpiBiasAct epi{Y, ldy, T, N, bias_period < 1 ? 1 : bias_period, relu};
   const int M = B * d;
-  if (N <= 32) launch_gemm<TileSkinny>(al, bl, epi, M, N, d, 1, s);
-  else launch_gemm<TileBig>(al, bl, epi, M, N, d, 1, s);
+  launch_gemm_auto(al, bl, epi, M, N, d, false, s);
   return check_launch("gnf_dag_l1_fwd");
 }
 
@@ -368,8 +356,7 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
   LoadColMajorA al{dY, lddy};   // A(n, m) = dY[m, n]
   LoadDagB bl{g};               // B(m, j) = e[m, j]
   EpiAtomicAdd epi{dW1, ldw};
-  if (d <= 32) launch_gemm<TileSkinny>(al, bl, epi, N, d, M, pick_splits(N, d, M, 128, 32, 16), s);
-  else launch_gemm<TileBig>(al, bl, epi, N, d, M, pick_splits(N, d, M, 128, 128, 16), s);
+  launch_gemm_auto(al, bl, epi, N, d, M, true, s);
   return check_launch("gnf_dag_l1_wgrad");
 }
 
@@ -386,8 +373,7 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   LoadRowMajorA al{dY, lddy};   // A(m, n)
   LoadRowMajorB bl{W1, ldw};    // B(n, j) = W1[n, j]
   EpiDagDgrad epi{g, dx, dP};
-  if (d <= 32) launch_gemm<TileSkinny>(al, bl, epi, M, d, N, 1, s);
-  else launch_gemm<TileBig>(al, bl, epi, M, d, N, 1, s);
+  launch_gemm_auto(al, bl, epi, M, d, N, false, s);
   return check_launch("gnf_dag_l1_dgrad");
 }
 

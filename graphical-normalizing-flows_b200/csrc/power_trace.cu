@@ -11,28 +11,48 @@ namespace gnf {
 constexpr int kSmallD = 64;
 constexpr int kPTThreads = 512;
 
+// Shared-memory matrices are stored with a padded leading dimension kLD (zero padded to 64 x 64) so that a thread can
+// own a 2-row x 4-column register block: per k it reads two A scalars (broadcast within the warp) and one float4 of B.
+constexpr int kLD = kSmallD + 4;
+constexpr int kMatFloats = kSmallD * kLD;
+
 __device__ __forceinline__ void sm_matmul(float* __restrict__ C, const float* __restrict__ A, const float* __restrict__ Bm, int d) {
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const int r = e / d, c = e % d;
-    float s = 0.f;
-    for (int k = 0; k < d; ++k) s = fmaf(A[r * d + k], Bm[k * d + c], s);
-    C[e] = s;
+  const int rb = threadIdx.x >> 4, cb = threadIdx.x & 15;       // 32 row pairs x 16 column quads
+  const int r0 = 2 * rb, c0 = 4 * cb;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  if (r0 < d && c0 < d) {
+    const float* a0 = A + r0 * kLD;
+    const float* a1 = a0 + kLD;
+#pragma unroll 4
+    for (int k = 0; k < d; ++k) {
+      const float x0 = a0[k], x1 = a1[k];
+      const float4 b = *reinterpret_cast<const float4*>(Bm + k * kLD + c0);
+      acc[0][0] = fmaf(x0, b.x, acc[0][0]); acc[0][1] = fmaf(x0, b.y, acc[0][1]);
+      acc[0][2] = fmaf(x0, b.z, acc[0][2]); acc[0][3] = fmaf(x0, b.w, acc[0][3]);
+      acc[1][0] = fmaf(x1, b.x, acc[1][0]); acc[1][1] = fmaf(x1, b.y, acc[1][1]);
+      acc[1][2] = fmaf(x1, b.z, acc[1][2]); acc[1][3] = fmaf(x1, b.w, acc[1][3]);
+    }
   }
+  // rows / columns >= d of every operand are zero, so the padded part of C stays zero
+  *reinterpret_cast<float4*>(C + r0 * kLD + c0) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+  *reinterpret_cast<float4*>(C + (r0 + 1) * kLD + c0) = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
   __syncthreads();
 }
-__device__ __forceinline__ void sm_copy(float* __restrict__ C, const float* __restrict__ A, int n) {
-  for (int e = threadIdx.x; e < n; e += blockDim.x) C[e] = A[e];
+__device__ __forceinline__ void sm_copy(float* __restrict__ C, const float* __restrict__ A) {
+  for (int e = threadIdx.x; e < kMatFloats; e += blockDim.x) C[e] = A[e];
   __syncthreads();
 }
 
-// Returns a pointer (inside smem) to Bm^p.  bufs: Bm, Z0, Z1, R0, R1 each d*d floats.
+// Returns a pointer (inside smem) to Bm^p.  bufs: Bm, Z0, Z1, R0, R1 each kMatFloats floats.
 __device__ const float* sm_matrix_power(float* smem, int d, int p) {
-  const int n = d * d;
   float* Bm = smem;
-  float* Z[2] = {smem + n, smem + 2 * n};
-  float* R[2] = {smem + 3 * n, smem + 4 * n};
+  float* Z[2] = {smem + kMatFloats, smem + 2 * kMatFloats};
+  float* R[2] = {smem + 3 * kMatFloats, smem + 4 * kMatFloats};
   if (p == 0) {
-    for (int e = threadIdx.x; e < n; e += blockDim.x) R[0][e] = (e / d == e % d) ? 1.f : 0.f;
+    for (int e = threadIdx.x; e < kMatFloats; e += blockDim.x) {
+      const int r = e / kLD, c = e % kLD;
+      R[0][e] = (r == c && r < d) ? 1.f : 0.f;
+    }
     __syncthreads();
     return R[0];
   }
@@ -54,7 +74,7 @@ __device__ const float* sm_matrix_power(float* smem, int d, int p) {
     }
     if (bit) {
       if (res == nullptr) {
-        sm_copy(R[ri], z, n);
+        sm_copy(R[ri], z);
       } else {
         sm_matmul(R[ri], res, z, d);
       }
@@ -66,9 +86,14 @@ __device__ const float* sm_matrix_power(float* smem, int d, int p) {
 }
 
 __device__ __forceinline__ void sm_build_B(float* Bm, const float* __restrict__ A, int d, float alpha) {
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const float a = A[e];
-    Bm[e] = ((e / d == e % d) ? 1.f : 0.f) + alpha * (a * a);
+  for (int e = threadIdx.x; e < kMatFloats; e += blockDim.x) {
+    const int r = e / kLD, c = e % kLD;
+    float v = 0.f;
+    if (r < d && c < d) {
+      const float a = A[r * d + c];
+      v = ((r == c) ? 1.f : 0.f) + alpha * (a * a);
+    }
+    Bm[e] = v;
   }
   __syncthreads();
 }
@@ -79,7 +104,7 @@ __global__ void __launch_bounds__(kPTThreads) power_trace_small_fwd(const float*
   const float* M = sm_matrix_power(smem, d, p);
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int i = 0; i < d; ++i) s += M[i * d + i];
+    for (int i = 0; i < d; ++i) s += M[i * kLD + i];
     *t_out = s - (float)d;
   }
 }
@@ -96,7 +121,7 @@ __global__ void __launch_bounds__(kPTThreads) power_trace_small_bwd(const float*
   const float scale = (*gt) * (float)p * 2.f * alpha;
   for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
     const int i = e / d, j = e % d;
-    dA[e] = scale * A[e] * G[j * d + i];
+    dA[e] = scale * A[e] * G[j * kLD + i];
   }
 }
 
@@ -184,9 +209,9 @@ int gnf_power_trace_fwd(const float* A, int d, float alpha, int p, float* t_out,
   if (!A || !t_out || d <= 0 || p < 0) return fail(GNF_ERR_INVALID, "gnf_power_trace_fwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   if (d <= kSmallD) {
-    const size_t smem = (size_t)5 * d * d * sizeof(float);
+    const size_t smem = (size_t)5 * kMatFloats * sizeof(float);
 #ifndef GNF_EMU
-    cudaFuncSetAttribute(power_trace_small_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * kSmallD * kSmallD * sizeof(float)));
+    cudaFuncSetAttribute(power_trace_small_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * kMatFloats * sizeof(float)));
 #endif
     GNF_LAUNCH(power_trace_small_fwd, 1, kPTThreads, smem, s, A, d, alpha, p, t_out);
     return check_launch("gnf_power_trace_fwd");
@@ -204,9 +229,9 @@ int gnf_power_trace_bwd(const float* A, int d, float alpha, int p, const float* 
   if (!A || !gt || !dA || d <= 0 || p < 0) return fail(GNF_ERR_INVALID, "gnf_power_trace_bwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   if (d <= kSmallD) {
-    const size_t smem = (size_t)5 * d * d * sizeof(float);
+    const size_t smem = (size_t)5 * kMatFloats * sizeof(float);
 #ifndef GNF_EMU
-    cudaFuncSetAttribute(power_trace_small_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * kSmallD * kSmallD * sizeof(float)));
+    cudaFuncSetAttribute(power_trace_small_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * kMatFloats * sizeof(float)));
 #endif
     GNF_LAUNCH(power_trace_small_bwd, 1, kPTThreads, smem, s, A, d, alpha, p, gt, dA);
     return check_launch("gnf_power_trace_bwd");

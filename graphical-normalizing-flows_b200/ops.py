@@ -214,8 +214,9 @@ def get_gemm_mode():
     return _GEMM_MODE
 
 
-def _gemm_passes(M, N, K):
-    """0 = FFMA engine, 1 / 3 = tensor-core engine passes; thresholds from scripts/gemm_bench.py on B200."""
+def _gemm_passes(M, N, K, op="fwd"):
+    """0 = FFMA engine, 1 / 3 = tensor-core engine passes; thresholds from scripts/gemm_bench.py on B200
+    (the split-K FFMA wgrad is the slowest of the three FFMA GEMMs, so wgrad switches to 3xTF32 earlier)."""
     if _GEMM_MODE == "ffma":
         return 0
     if _GEMM_MODE == "tf32":
@@ -223,6 +224,8 @@ def _gemm_passes(M, N, K):
     if _GEMM_MODE == "tf32x3":
         return 3
     if _GEMM_MODE == "auto":
+        if op == "wgrad":
+            return 3 if (min(N, K) >= 256 and M >= 4096) else 0
         return 3 if (min(N, K) >= 256 and float(M) * N * K >= 8e9) else 0
     return 1 if min(N, K) >= 128 else 0
 
@@ -265,7 +268,7 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
 
 def linear_wgrad(dY, lddy, X, ldx, M, N, K):
     dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
-    passes = _gemm_passes(M, N, K)
+    passes = _gemm_passes(M, N, K, "wgrad")
     if passes:
         _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, passes, stream_ptr())
     else:
