@@ -76,6 +76,14 @@ _PROTOS = {
                       _P, _SZ, _P], C.c_int),
     "gnf_umnn_tc_workspace_bytes": ([C.POINTER(MlpT)], _SZ),
     "gnf_umnn_fwd_tc": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P], C.c_int),
+    "gnf_umnn_lw_saved_floats": ([C.POINTER(MlpT), _I, _I, _I], _SZ),
+    "gnf_umnn_lw_workspace_bytes": ([C.POINTER(MlpT), _I, _I, _I], _SZ),
+    "gnf_umnn_fwd_lw": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
+    "gnf_umnn_bwd_lw": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MlpGradT), _I, _I, _I,
+                         _P, _SZ, _P], C.c_int),
+    "gnf_tc_gemm_set_tma": ([_I], C.c_int),
+    "gnf_tc_gemm_set_fold": ([_I], C.c_int),
+    "gnf_tc_gemm_set_trace": ([_P], C.c_int),
     "gnf_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
     "gnf_tc_probe": ([_I, _I, _P, _P], C.c_int),
     "gnf_tc_set_trace": ([_P], C.c_int),

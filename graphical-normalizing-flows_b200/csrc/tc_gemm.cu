@@ -6,36 +6,31 @@
 // One persistent, warp-specialised kernel serves Linear forward, dgrad and wgrad:
 //   warps 0-3  epilogue   : thread t <-> accumulator row (TMEM lane) t; TMEM -> registers -> fused epilogue -> global
 //   warp  4    MMA issuer : one thread issues tcgen05.mma, commits to mbarriers
-//   warps 5-12 producers  : global -> registers -> (hi/lo split) -> 128B-swizzled UMMA shared-memory tiles
-// Operands are staged by the producer warps rather than by TMA tensor maps because every operand needs a
-// transformation on the way (hi/lo split, zero padding of ragged K / N tails), and because one code path can then
-// read either orientation (k-contiguous or row-contiguous global memory) coalesced and still hand the tensor core
-// a canonical K-major or MN-major tile.  A k-chunk is 32 fp32 = one 128-byte swizzle atom per tile row.
-// Accumulators are double buffered in TMEM (2 x <=256 columns) so a tile's epilogue overlaps the next tile's MMAs.
+//   warps 5-12 stagers    : (a) 16-byte-aligned operands: wait for the TMA tile, produce the hi/lo split in place;
+//                           (b) unaligned operands: cp.async the tile themselves (zero-filling ragged tails), then split
+//   warps 13,14 TMA issuers: one thread each (A tiles / B tiles) issues cp.async.bulk.tensor loads a ring ahead
+// Both operand orientations (k-contiguous or row-contiguous global memory) land as canonical 128B-swizzled UMMA tiles:
+// K-major = SWIZZLE_128B, MN-major = SWIZZLE_128B_BASE32B (TMA: CU_TENSOR_MAP_SWIZZLE_128B / _128B_ATOM_32B).
+// A k-chunk is 32 fp32 = one 128-byte swizzle atom per tile row.  Accumulators are double buffered in TMEM
+// (2 x <=256 columns) so a tile's epilogue overlaps the next tile's MMAs; the epilogue transposes 32x16 blocks through
+// shared memory so that global stores / ReLU-mask loads / atomics touch 64 contiguous bytes per row instead of 16.
 #include "tc_common.cuh"
+#include "tc_gemm.h"
+#ifndef GNF_EMU
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#endif
 
 #ifndef GNF_EMU
 namespace gnf {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmKC = 32;              // k-chunk: 32 fp32 = 128 bytes = one swizzle atom
-constexpr int kEpiThreads = 128, kProdThreads = 256, kGemmThreads = kEpiThreads + 32 + kProdThreads;
+constexpr int kEpiThreads = 128, kProdThreads = 256, kGemmThreads = kEpiThreads + 32 + kProdThreads + 64;
 constexpr int kMaxStages = 6;
-
-enum { TCG_EPI_BIAS_ACT = 0, TCG_EPI_MASK = 1, TCG_EPI_ATOMIC = 2 };
-enum { TCG_SRC_K = 0, TCG_SRC_MN = 1 };  // global memory contiguous along the reduction index / along the row index
-
-struct TcGemmParams {
-  // C[m, n] = sum_k A(m, k) * B(n, k);  A: Mrows x Kred,  B: Ncols x Kred
-  const float* A; long long lda; int a_src;    // TCG_SRC_K: A(m,k) = A[m*lda + k];  TCG_SRC_MN: A(m,k) = A[k*lda + m]
-  const float* B; long long ldb; int b_src;    // same convention with n in place of m
-  int M, N, K;
-  int BN, stages, passes, splits, k_per_split;
-  int epi;
-  float* C; long long ldc;
-  const float* bias; int bias_ld, bias_period, relu;   // TCG_EPI_BIAS_ACT
-  const float* act; long long ldact;                    // TCG_EPI_MASK
-};
+constexpr int kEpiLd = 20;                               // floats per staged epilogue row (16 + 4 pad: conflict-free STS.128)
+constexpr int kEpiStageBytes = 4 * 32 * kEpiLd * 4;      // one 32 x 16 block per epilogue warp
+constexpr size_t kSmemBudget = 227 * 1024;
 
 // K-major fp32 tiles use SWIZZLE_128B (16-byte chunks XOR (row & 7), 8-row atoms: SBO = 1024).  MN-major tiles of
 // a 32-bit type must use SWIZZLE_128B_BASE32B (32-byte granules XOR (row & 3), 4-row atoms: SBO = 512); LBO is the
@@ -70,9 +65,9 @@ __device__ __forceinline__ void cp_async_vec(char* smem_dst, const float* gmem_s
 // already sit on the TF32 grid makes that truncation a no-op, and round-to-nearest keeps the representation error of
 // hi + lo at ~2^-22 |x| and unbiased (truncating both would leave a one-sided 2^-20 error that survives cancellation).
 __device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  // cvt.rna.tf32.f32 (round to nearest, ties away) with two full-rate integer ops instead of the quarter-rate convert:
+  // add half an ulp of the 13 dropped mantissa bits to the magnitude, clear them.
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 template <int VEC>
 __device__ __forceinline__ void split_vec(char* img_hi, char* img_lo, int off) {
@@ -163,25 +158,42 @@ __device__ __forceinline__ void fill_dispatch(int vec, char* hi, char* lo, const
   }
 }
 
-__global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, int vecA, int vecB) {
+// One 2-D tiled TMA load: box (32 fp32 along the contiguous global index) x (box rows), completing on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   tc::smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_outer), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
+// Measurement: role r of CTA 0 stamps event i with the SM clock (rows of 256 stamps per role).
+constexpr int kTraceRoles = 8, kTraceLen = 256;
+__device__ __forceinline__ void trace_stamp(long long* trace, int role, long long i) {
+  if (trace && blockIdx.x == 0 && i < kTraceLen) trace[role * kTraceLen + i] = clock64();
+}
+
+__global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, int vecA, int vecB, const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB) {
   using namespace tc;
   GNF_SMEM(char, smem);
   const int BN = p.BN;
   const bool split = p.passes == 3;
   const uint32_t a_bytes = kGemmBM * 128u, b_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = (a_bytes + b_bytes) * (split ? 2u : 1u);
-  // stage layout: [A_hi][B_hi]([A_lo][B_lo])
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* full = bars;                       // [stages]  producers -> MMA   (count 8: one arrive per producer warp)
-  uint64_t* empty = bars + kMaxStages;         // [stages]  MMA -> producers   (tcgen05.commit)
-  uint64_t* tfull = bars + 2 * kMaxStages;     // [2]       MMA -> epilogue
+  // stage layout: [A_hi][B_hi]([A_lo][B_lo]); then the epilogue transpose blocks; then the barriers
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + kEpiStageBytes);
+  uint64_t* full = bars;                       // [stages]  stagers -> MMA     (count 8: one arrive per stager warp)
+  uint64_t* empty = bars + kMaxStages;         // [stages]  MMA -> loaders     (tcgen05.commit)
+  uint64_t* landed = bars + 2 * kMaxStages;    // [stages]  TMA -> stagers / MMA (transaction bytes)
+  uint64_t* tfull = bars + 3 * kMaxStages;     // [2]       MMA -> epilogue
   uint64_t* tempty = tfull + 2;                // [2]       epilogue -> MMA    (count 4: one arrive per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 32) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], kProdThreads / 32); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], kProdThreads / 32); mbar_init(&empty[s], 1); mbar_init(&landed[s], 2); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiThreads / 32); }
     fence_mbar_init();
   }
@@ -193,14 +205,36 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
   const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM, tiles_n = (p.N + BN - 1) / BN;
   const long long total = (long long)tiles_m * tiles_n * p.splits;
 
-  if (warp >= 5) {
-    // ===================== producers =====================
-    // Software pipeline with a lag of kLag stages: the copies of chunk `it` are issued (cp.async, one commit group per
-    // chunk) before chunk it-kLag is finished (wait for its group, produce the lo tiles, proxy fence, signal the MMA).
-    const int kLag = p.stages >= 3 ? 2 : 1;              // the ring must hold the in-flight chunks plus one being consumed
+  if (warp >= 13) {
+    // ===================== TMA issuers: warp 13 loads the A tiles, warp 14 the B tiles =====================
+    if (p.use_tma && lane == 0) {
+      const bool isA = warp == 13;
+      long long it = 0;
+      for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tm = (int)(w % tiles_m), tn = (int)((w / tiles_m) % tiles_n), sp = (int)(w / ((long long)tiles_m * tiles_n));
+        const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+        for (int k0 = kbeg; k0 < kend; k0 += kGemmKC, ++it) {
+          const int s = (int)(it % p.stages);
+          mbar_wait(&empty[s], (uint32_t)(((it / p.stages) & 1) ^ 1));
+          char* st = smem + (size_t)s * stage_bytes;
+          if (isA) {
+            mbar_expect_tx(&landed[s], a_bytes);
+            if (p.a_src == TCG_SRC_K) tma_load_2d(st, &tmA, k0, tm * kGemmBM, &landed[s]);
+            else for (int sl = 0; sl < kGemmBM / 32; ++sl) tma_load_2d(st + sl * 4096, &tmA, tm * kGemmBM + 32 * sl, k0, &landed[s]);
+            trace_stamp(p.trace, 0, it);
+          } else {
+            mbar_expect_tx(&landed[s], b_bytes);
+            if (p.b_src == TCG_SRC_K) tma_load_2d(st + a_bytes, &tmB, k0, tn * BN, &landed[s]);
+            else for (int sl = 0; sl < BN / 32; ++sl) tma_load_2d(st + a_bytes + sl * 4096, &tmB, tn * BN + 32 * sl, k0, &landed[s]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 5) {
+    // ===================== stagers =====================
     const int ptid = tid - (kEpiThreads + 32);
     long long it = 0;                                    // running k-chunk counter (stage ring position)
-    auto finish = [&](long long j) {                     // chunk j's copies have landed (caller waited on its group)
+    auto finish = [&](long long j) {                     // chunk j's raw tiles have landed: split, publish to the MMA warp
       const int s = (int)(j % p.stages);
       char* st = smem + (size_t)s * stage_bytes;
       if (split) {
@@ -211,26 +245,44 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
     };
-    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-      const int tm = (int)(w % tiles_m), tn = (int)((w / tiles_m) % tiles_n), sp = (int)(w / ((long long)tiles_m * tiles_n));
-      const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
-      for (int k0 = kbeg; k0 < kend; k0 += kGemmKC, ++it) {
-        const int s = (int)(it % p.stages);
-        const uint32_t par = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(&empty[s], par ^ 1u);
-        char* st = smem + (size_t)s * stage_bytes;
-        fill_dispatch<false>(vecA, st, nullptr, p.A, p.lda, p.a_src, tm * kGemmBM, p.M, k0, kend, kGemmBM, ptid);
-        fill_dispatch<false>(vecB, st + a_bytes, nullptr, p.B, p.ldb, p.b_src, tn * BN, p.N, k0, kend, BN, ptid);
-        cp_async_commit();
-        if (it >= kLag) {
-          if (kLag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-          finish(it - kLag);
+    if (p.use_tma) {
+      if (split) {                                       // single-pass TF32: the MMA warp consumes the landed tiles directly
+        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+          const int sp = (int)(w / ((long long)tiles_m * tiles_n));
+          const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+          for (int k0 = kbeg; k0 < kend; k0 += kGemmKC, ++it) {
+            mbar_wait(&landed[(int)(it % p.stages)], (uint32_t)((it / p.stages) & 1));
+            if (tid == kEpiThreads + 32) trace_stamp(p.trace, 1, it);
+            finish(it);
+            if (tid == kEpiThreads + 32) trace_stamp(p.trace, 2, it);
+          }
         }
       }
+    } else {
+      // Software pipeline with a lag of kLag stages: the copies of chunk `it` are issued (cp.async, one commit group per
+      // chunk) before chunk it-kLag is finished (wait for its group, produce the lo tiles, proxy fence, signal the MMA).
+      const int kLag = p.stages >= 3 ? 2 : 1;            // the ring must hold the in-flight chunks plus one being consumed
+      for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tm = (int)(w % tiles_m), tn = (int)((w / tiles_m) % tiles_n), sp = (int)(w / ((long long)tiles_m * tiles_n));
+        const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+        for (int k0 = kbeg; k0 < kend; k0 += kGemmKC, ++it) {
+          const int s = (int)(it % p.stages);
+          const uint32_t par = (uint32_t)((it / p.stages) & 1);
+          mbar_wait(&empty[s], par ^ 1u);
+          char* st = smem + (size_t)s * stage_bytes;
+          fill_dispatch<false>(vecA, st, nullptr, p.A, p.lda, p.a_src, tm * kGemmBM, p.M, k0, kend, kGemmBM, ptid);
+          fill_dispatch<false>(vecB, st + a_bytes, nullptr, p.B, p.ldb, p.b_src, tn * BN, p.N, k0, kend, BN, ptid);
+          cp_async_commit();
+          if (it >= kLag) {
+            if (kLag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+            finish(it - kLag);
+          }
+        }
+      }
+      // drain
+      cp_async_wait<0>();
+      for (long long j = (it > kLag ? it - kLag : 0); j < it; ++j) finish(j);
     }
-    // drain
-    cp_async_wait<0>();
-    for (long long j = (it > kLag ? it - kLag : 0); j < it; ++j) finish(j);
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -238,103 +290,245 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
       // per k-step (8 k) descriptor advance: K-major: 32 bytes inside the swizzle atom; MN-major: 8 tile rows = 1024 bytes
       const uint32_t a_step = (p.a_src == TCG_SRC_K) ? 2u : 64u, b_step = (p.b_src == TCG_SRC_K) ? 2u : 64u;
       const bool a_mn = p.a_src == TCG_SRC_MN, b_mn = p.b_src == TCG_SRC_MN;
+      uint64_t* ready = (p.use_tma && !split) ? landed : full;
       long long it = 0;
-      int tcount = 0;
-      for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
+      int gcount = 0;                                    // accumulator groups issued so far (buffer = gcount & 1)
+      for (long long w = blockIdx.x; w < total; w += gridDim.x) {
         const int sp = (int)(w / ((long long)tiles_m * tiles_n));
         const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
-        const int acc = tcount & 1;
-        mbar_wait(&tempty[acc], (uint32_t)(((tcount >> 1) & 1) ^ 1));
-        fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        bool first = true;
-        for (int k0 = kbeg; k0 < kend; k0 += kGemmKC, ++it) {
-          const int s = (int)(it % p.stages);
-          mbar_wait(&full[s], (uint32_t)((it / p.stages) & 1));
+        for (int kg = kbeg; kg < kend; kg += p.fold * kGemmKC, ++gcount) {
+          const int kg_end = min(kend, kg + p.fold * kGemmKC);
+          const int acc = gcount & 1;
+          mbar_wait(&tempty[acc], (uint32_t)(((gcount >> 1) & 1) ^ 1));
           fence_after_sync();
-          const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t da_hi = make_sw128_desc(st, a_mn), db_hi = make_sw128_desc(st + a_bytes, b_mn);
-          const uint64_t da_lo = make_sw128_desc(st + a_bytes + b_bytes, a_mn), db_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes, b_mn);
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)p.acc_stride;
+          bool first = true;
+          for (int k0 = kg; k0 < kg_end; k0 += kGemmKC, ++it) {
+            const int s = (int)(it % p.stages);
+            mbar_wait(&ready[s], (uint32_t)((it / p.stages) & 1));
+            fence_after_sync();
+            trace_stamp(p.trace, 3, it);
+            const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t da_hi = make_sw128_desc(st, a_mn), db_hi = make_sw128_desc(st + a_bytes, b_mn);
+            const uint64_t da_lo = make_sw128_desc(st + a_bytes + b_bytes, a_mn), db_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes, b_mn);
 #pragma unroll
-          for (int ks = 0; ks < kGemmKC / 8; ++ks) {
-            const uint64_t oa = (uint64_t)(a_step * ks), ob = (uint64_t)(b_step * ks);
-            mma_tf32_ss(d_tmem, da_hi + oa, db_hi + ob, idesc, first ? 0u : 1u);
-            first = false;
-            if (split) {
-              mma_tf32_ss(d_tmem, da_lo + oa, db_hi + ob, idesc, 1u);
-              mma_tf32_ss(d_tmem, da_hi + oa, db_lo + ob, idesc, 1u);
+            for (int ks = 0; ks < kGemmKC / 8; ++ks) {
+              const uint64_t oa = (uint64_t)(a_step * ks), ob = (uint64_t)(b_step * ks);
+              mma_tf32_ss(d_tmem, da_hi + oa, db_hi + ob, idesc, first ? 0u : 1u);
+              first = false;
+              if (split) {
+                mma_tf32_ss(d_tmem, da_lo + oa, db_hi + ob, idesc, 1u);
+                mma_tf32_ss(d_tmem, da_hi + oa, db_lo + ob, idesc, 1u);
+              }
             }
+            mma_commit(&empty[s]);
           }
-          mma_commit(&empty[s]);
+          mma_commit(&tfull[acc]);
+          trace_stamp(p.trace, 4, gcount);
         }
-        mma_commit(&tfull[acc]);
       }
     }
   } else {
     // ===================== epilogue =====================
-    const int t = tid;                                   // accumulator row / TMEM lane
+    // Thread t owns accumulator row t (TMEM lane t).  Each 16-column block goes through a per-warp 32 x 16 shared-memory
+    // block so that global accesses are row-contiguous: lane l <-> (row (l >> 2) + 8 i, 16-byte piece l & 3).
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    int tcount = 0;
+    float* stg = epi_stage + warp * 32 * kEpiLd;
+    float* my_row = stg + lane * kEpiLd;
+    const int piece = (lane & 3) * 4, rsub = lane >> 2;
+    // per-element side input of the epilogue, fetched one 16-column block ahead of its use:
+    //   aux_tile: ReLU-mask activations (dgrad) or a periodic bias table row (bias_period > 1), as a transposed 32 x 16 block
+    // whole-tile side inputs, loaded before the accumulator is waited for (their latency hides behind the main loop):
+    //   bias_row: one bias vector for every row: lane l holds bias[n0 + 32 i + l], broadcast by shuffles
+    //   bit_mask: the ReLU mask as one bit per element: the row owner holds its row's words
+    const bool bit_mask = p.epi == TCG_EPI_MASK && p.mask_bits != nullptr;
+    const bool aux_mask = p.epi == TCG_EPI_MASK && p.act != nullptr && !bit_mask;
+    const bool aux_bias = p.epi == TCG_EPI_BIAS_ACT && p.bias != nullptr && p.bias_period > 1;
+    const bool aux_tile = aux_mask || aux_bias;
+    const bool bias_row = p.epi == TCG_EPI_BIAS_ACT && p.bias != nullptr && p.bias_period <= 1;
+    int gcount = 0, tcount = 0;
     for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
-      const int tm = (int)(w % tiles_m), tn = (int)((w / tiles_m) % tiles_n);
-      const int acc = tcount & 1;
-      mbar_wait(&tfull[acc], (uint32_t)((tcount >> 1) & 1));
-      fence_after_sync();
-      const int m = tm * kGemmBM + t, n0 = tn * BN;
-      const uint32_t src = tmem_base + lane_sel + (uint32_t)acc * 256u;
-      uint32_t cur[16], nxt[16];
-      tmem_ld16_nowait(src, cur);
-      tmem_wait_ld();
-      for (int c = 0; c < BN; c += 16) {
-        if (c + 16 < BN) tmem_ld16_nowait(src + c + 16, nxt);
-        if (m < p.M) {
-          const int n = n0 + c;
-          if (p.epi == TCG_EPI_BIAS_ACT) {
-            float* y = p.C + (long long)m * p.ldc + n;
-            const float* bp = p.bias ? p.bias + (long long)(p.bias_period > 1 ? (m % p.bias_period) : 0) * p.bias_ld + n : nullptr;
-            float o[16];
+      const int tm = (int)(w % tiles_m), tn = (int)((w / tiles_m) % tiles_n), sp = (int)(w / ((long long)tiles_m * tiles_n));
+      const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+      const int ngroups = (kend - kbeg + p.fold * kGemmKC - 1) / (p.fold * kGemmKC);
+      const int m_warp = tm * kGemmBM + warp * 32, n0 = tn * BN;
+      const int n_lim = min(BN, p.N - n0);               // columns of this tile that exist
+      const uint32_t run = tmem_base + lane_sel + 2u * (uint32_t)p.acc_stride;   // running sum region (3xTF32 only)
+      const int m_row = m_warp + lane;
+      float breg[8];
+      uint32_t mw[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float r = __uint_as_float(cur[j]);
-              if (bp && n + j < p.N) r += __ldg(bp + j);
-              o[j] = p.relu ? fmaxf(r, 0.f) : r;
-            }
-            if (n + 16 <= p.N && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+      for (int i = 0; i < 8; ++i) {
+        breg[i] = (bias_row && 32 * i < n_lim && n0 + 32 * i + lane < p.N) ? __ldg(p.bias + n0 + 32 * i + lane) : 0.f;
+        mw[i] = (bit_mask && 32 * i < n_lim && m_row < p.M) ? __ldg(p.mask_bits + (long long)m_row * p.mask_ld + (n0 >> 5) + i) : 0u;
+      }
+      uint32_t obits = 0u;
+      // The tensor core accumulates with round-toward-zero: long in-core accumulation chains bias the result.  Every `fold`
+      // k-chunks the partial accumulator is therefore folded into a running sum with round-to-nearest adds (TMEM -> registers
+      // -> TMEM, this warp's own lanes), while the MMA warp already fills the other partial buffer.
+      for (int g = 0; g + 1 < ngroups; ++g, ++gcount) {
+        const int acc = gcount & 1;
+        mbar_wait(&tfull[acc], (uint32_t)((gcount >> 1) & 1));
+        fence_after_sync();
+        const uint32_t part = tmem_base + lane_sel + (uint32_t)acc * (uint32_t)p.acc_stride;
+        for (int c = 0; c < n_lim; c += 16) {
+          uint32_t a[16], b[16];
+          tmem_ld16_nowait(part + c, a);
+          if (g > 0) tmem_ld16_nowait(run + c, b);
+          tmem_wait_ld();
+          if (g > 0) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            } else if (n + 16 <= p.N && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+            for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b[j]));
+          }
+          tmem_st16u(run + c, a);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      const int acc = gcount & 1;
+      const uint32_t acc_par = (uint32_t)((gcount >> 1) & 1);
+      ++gcount;
+      auto load_aux = [&](int c, float4 (&a)[4], float& b1) {
+        const int n = n0 + c;
+        if (aux_tile) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) *reinterpret_cast<float2*>(y + j) = make_float2(o[j], o[j + 1]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n + j < p.N) y[j] = o[j];
-            }
-          } else if (p.epi == TCG_EPI_MASK) {
-            float* y = p.C + (long long)m * p.ldc + n;
-            const float* ap = p.act ? p.act + (long long)m * p.ldact + n : nullptr;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (n + j < p.N) {
-                float r = __uint_as_float(cur[j]);
-                if (ap && !(__ldg(ap + j) > 0.f)) r = 0.f;
-                y[j] = r;
+          for (int i = 0; i < 4; ++i) {
+            const int mr = m_warp + rsub + 8 * i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mr < p.M && n + piece < p.N) {
+              const float* ap = aux_mask ? p.act + (long long)mr * p.ldact + n + piece
+                                         : p.bias + (long long)(mr % p.bias_period) * p.bias_ld + n + piece;
+              if ((aux_mask ? p.act_vec : p.bias_vec) && n + piece + 4 <= p.N) v = __ldg(reinterpret_cast<const float4*>(ap));
+              else {
+                v.x = __ldg(ap);
+                if (n + piece + 1 < p.N) v.y = __ldg(ap + 1);
+                if (n + piece + 2 < p.N) v.z = __ldg(ap + 2);
+                if (n + piece + 3 < p.N) v.w = __ldg(ap + 3);
               }
             }
-          } else {
-            float* y = p.C + (long long)m * p.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (n + j < p.N) atomicAdd(y + j, __uint_as_float(cur[j]));
+            a[i] = v;
           }
         }
-        if (c + 16 < BN) {
+        (void)b1;
+      };
+      float4 aux_cur[4], aux_nxt[4];
+      float b_cur = 0.f, b_nxt = 0.f;
+      load_aux(0, aux_cur, b_cur);                       // independent of the accumulator: issued before the tile is complete
+      mbar_wait(&tfull[acc], acc_par);
+      fence_after_sync();
+      if (tid == 0) trace_stamp(p.trace, 5, tcount);
+      const uint32_t src = tmem_base + lane_sel + (uint32_t)acc * (uint32_t)p.acc_stride;
+      const bool folded = ngroups > 1;
+      uint32_t cur[16], nxt[16];
+      auto load_acc = [&](int c, uint32_t (&v)[16]) {    // last partial (+ running sum), 16 columns
+        tmem_ld16_nowait(src + c, v);
+        if (folded) {
+          uint32_t r[16];
+          tmem_ld16_nowait(run + c, r);
           tmem_wait_ld();
 #pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(r[j]));
+        }
+      };
+      load_acc(0, cur);
+      tmem_wait_ld();
+      for (int c = 0; c < n_lim; c += 16) {
+        const bool more = c + 16 < n_lim;
+        const bool tr = p.trace && tid == 0 && tcount == 1;
+        if (tr) trace_stamp(p.trace, 7, (c >> 4) * 6 + 0);
+        if (more) { load_acc(c + 16, nxt); load_aux(c + 16, aux_nxt, b_nxt); }
+        if (tr) trace_stamp(p.trace, 7, (c >> 4) * 6 + 1);
+        const int n = n0 + c;
+        float o[16];
+        if (aux_tile) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (rsub + 8 * i) * kEpiLd + piece) = aux_cur[i];
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 a = *reinterpret_cast<const float4*>(my_row + 4 * j4);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float r = __uint_as_float(cur[4 * j4 + e]);
+              if (aux_mask) o[4 * j4 + e] = av[e] > 0.f ? r : 0.f;
+              else o[4 * j4 + e] = p.relu ? fmaxf(r + av[e], 0.f) : r + av[e];
+            }
+          }
+          __syncwarp();
+        } else if (p.epi == TCG_EPI_BIAS_ACT) {
+          float bsel = breg[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) if ((c >> 5) == i) bsel = breg[i];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float r = __uint_as_float(cur[j]);
+            if (bias_row) r += __shfl_sync(0xffffffffu, bsel, (c & 31) + j);
+            o[j] = p.relu ? fmaxf(r, 0.f) : r;
+          }
+        } else if (bit_mask) {
+          uint32_t wsel = mw[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) if ((c >> 5) == i) wsel = mw[i];
+          wsel >>= (c & 31);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = ((wsel >> j) & 1u) ? __uint_as_float(cur[j]) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(cur[j]);
+        }
+        if (p.bits_out) {                                  // ReLU mask of the output, one bit per element, row-owner layout
+#pragma unroll
+          for (int j = 0; j < 16; ++j) obits |= (o[j] > 0.f ? 1u : 0u) << ((c & 31) + j);
+          if ((c & 31) == 16 || !more) {
+            if (m_row < p.M) p.bits_out[(long long)m_row * p.bits_ld + ((n0 + c) >> 5)] = obits;
+            obits = 0u;
+          }
+        }
+        if (tr) trace_stamp(p.trace, 7, (c >> 4) * 6 + 2);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<float4*>(my_row + 4 * j4) = make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+        __syncwarp();
+        if (tr) trace_stamp(p.trace, 7, (c >> 4) * 6 + 3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = rsub + 8 * i, mr = m_warp + row;
+          if (mr < p.M && n + piece < p.N) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + row * kEpiLd + piece);
+            float* y = p.C + (long long)mr * p.ldc + n + piece;
+            if (p.epi == TCG_EPI_ATOMIC) {
+              atomicAdd(y, v.x);
+              if (n + piece + 1 < p.N) atomicAdd(y + 1, v.y);
+              if (n + piece + 2 < p.N) atomicAdd(y + 2, v.z);
+              if (n + piece + 3 < p.N) atomicAdd(y + 3, v.w);
+            } else if (p.c_vec && n + piece + 4 <= p.N) {
+              *reinterpret_cast<float4*>(y) = v;
+            } else {
+              y[0] = v.x;
+              if (n + piece + 1 < p.N) y[1] = v.y;
+              if (n + piece + 2 < p.N) y[2] = v.z;
+              if (n + piece + 3 < p.N) y[3] = v.w;
+            }
+          }
+        }
+        __syncwarp();
+        if (tr) trace_stamp(p.trace, 7, (c >> 4) * 6 + 4);
+        if (more) {
+          tmem_wait_ld();
+          if (tr) trace_stamp(p.trace, 7, (c >> 4) * 6 + 5);
+#pragma unroll
           for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) aux_cur[i] = aux_nxt[i];
+          b_cur = b_nxt;
         }
       }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (tid == 0) trace_stamp(p.trace, 6, tcount);
     }
   }
   fence_before_sync();
@@ -349,12 +543,13 @@ static inline int vec_width(const float* p, long long ld) {
   return 1;
 }
 
-static int pick_bn(int N) {
+static int pick_bn(int N, int max_bn) {
   int best = 64;
   long long best_cost = -1;
   const int cands[7] = {64, 96, 128, 160, 192, 224, 256};
   for (int i = 0; i < 7; ++i) {
     const int bn = cands[i];
+    if (bn > max_bn) break;
     const long long padded = (long long)((N + bn - 1) / bn) * bn;
     // padded width is wasted tensor work; small tiles pay more A re-reads and more per-tile overhead
     const long long cost = padded * 8 + (long long)((N + bn - 1) / bn) * 160;
@@ -363,13 +558,52 @@ static int pick_bn(int N) {
   return best;
 }
 
-static int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda).
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// Tensor map of one GEMM operand.  K-major source: dims {K, rows}, box {32, tile_rows}, SWIZZLE_128B.
+// MN-major source: dims {rows, K}, box {32, 32} (one 32-row slab per load), SWIZZLE_128B with 32-byte atoms.
+static bool make_operand_map(CUtensorMap* map, const float* base, long long ld, int src, int rows, int K, int tile_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 4) != 0) return false;
+  cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2], estr[2] = {1, 1};
+  CUtensorMapSwizzle sw;
+  if (src == TCG_SRC_K) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; box[0] = 32; box[1] = (cuuint32_t)tile_rows; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
+  else { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 32; box[1] = 32; sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
+  if ((long long)dims[0] > ld) return false;
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static long long* g_tc_gemm_trace = nullptr;
+static int g_tc_gemm_fold = 2;      // k-chunks accumulated inside the tensor core before a round-to-nearest fold (3xTF32)
+static bool g_tc_gemm_tma = true;   // measurement switch (gnf_tc_gemm_set_tma): 0 forces the cp.async staging path
+
+int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return 0;
   if (p.passes != 1 && p.passes != 3) return fail(GNF_ERR_INVALID, "tensor-core GEMM: passes must be 1 or 3");
-  p.BN = pick_bn(p.N);
+  // 3xTF32: two partial accumulators + the round-to-nearest running sum must fit the 512 TMEM columns (3 x 160);
+  // single-pass TF32: two accumulators of up to 256 columns, no folding
+  p.BN = pick_bn(p.N, p.passes == 3 ? 160 : 256);
+  p.acc_stride = p.passes == 3 ? 160 : 256;
+  p.fold = p.passes == 3 ? g_tc_gemm_fold : (1 << 20);
   // every candidate is a multiple of 32: K-major fills advance 8/16/32 rows per pass, MN-major tiles are 32-row slabs
   const uint32_t stage_bytes = (uint32_t)(kGemmBM + p.BN) * 128u * (p.passes == 3 ? 2u : 1u);
-  int stages = (int)((200u * 1024u) / stage_bytes);
+  const size_t fixed = kEpiStageBytes + (3 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+  int stages = (int)((kSmemBudget - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM: tile does not fit shared memory");
   p.stages = stages;
@@ -385,12 +619,21 @@ static int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   p.k_per_split = ((kchunks + splits - 1) / splits) * kGemmKC;
   p.splits = (p.K + p.k_per_split - 1) / p.k_per_split;
   if (p.splits < 1) p.splits = 1;
+  p.c_vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc % 4) == 0) ? 1 : 0;
+  p.act_vec = (p.act && (reinterpret_cast<uintptr_t>(p.act) & 15) == 0 && (p.ldact % 4) == 0) ? 1 : 0;
+  p.bias_vec = (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (p.bias_ld % 4) == 0) ? 1 : 0;
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  p.use_tma = (g_tc_gemm_tma && make_operand_map(&tmA, p.A, p.lda, p.a_src, p.M, p.K, kGemmBM) &&
+               make_operand_map(&tmB, p.B, p.ldb, p.b_src, p.N, p.K, p.BN)) ? 1 : 0;
+  p.trace = g_tc_gemm_trace;
   const long long total = (long long)tiles * p.splits;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget); attr = true; }
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb));
+  GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB);
   return 0;
 }
 
@@ -429,6 +672,37 @@ int gnf_linear_dgrad_tc(const float* dY, int lddy, const float* W, int ldw, cons
   p.epi = TCG_EPI_MASK; p.C = dX; p.ldc = lddx; p.act = act; p.ldact = ldact;
   if (int e = launch_tc_gemm(p, (cudaStream_t)stream)) return e;
   return check_launch("gnf_linear_dgrad_tc");
+#endif
+}
+
+int gnf_tc_gemm_set_trace(long long* buf) {
+#ifdef GNF_EMU
+  (void)buf;
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  g_tc_gemm_trace = buf;
+  return 0;
+#endif
+}
+
+int gnf_tc_gemm_set_fold(int chunks) {
+#ifdef GNF_EMU
+  (void)chunks;
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (chunks < 1) return fail(GNF_ERR_INVALID, "gnf_tc_gemm_set_fold: need >= 1 k-chunk per fold");
+  g_tc_gemm_fold = chunks > (1 << 20) ? (1 << 20) : chunks;
+  return 0;
+#endif
+}
+
+int gnf_tc_gemm_set_tma(int enable) {
+#ifdef GNF_EMU
+  (void)enable;
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  g_tc_gemm_tma = enable != 0;
+  return 0;
 #endif
 }
 

@@ -532,6 +532,31 @@ _CC_CACHE = {}
 SAVE_ACTIVATIONS_MAX_BYTES = 16 << 30
 
 
+# Engine of the strict UMNN integral: 'fused' = one FFMA kernel per direction (umnn.cu), 'layerwise' = per-layer passes
+# with the hidden GEMMs on the GEMM engine selected by set_gemm_mode (umnn_lw.cu), 'auto' = layerwise whenever the GEMM
+# mode allows tensor cores, the integrand has a hidden x hidden layer worth a GEMM and the activations fit the budget.
+UMNN_ENGINE = "auto"
+UMNN_LAYERWISE_MIN_NODE_ROWS = 16384
+
+
+def _umnn_layerwise_passes(net, R, S, train):
+    """GEMM passes (0 FFMA / 1 TF32 / 3 3xTF32) for the layer-wise UMNN engine, or None for the fused FFMA kernels."""
+    if UMNN_ENGINE == "fused" or net.dims[0] < 2:
+        return None
+    passes = {"ffma": 0, "tf32": 1, "tf32x3": 3, "auto": 3, "auto-fast": 3}[_GEMM_MODE]
+    if UMNN_ENGINE == "auto":
+        hidden = [net.dims[l] for l in range(1, net.n_layers)]
+        if passes == 0 or net.n_layers < 3 or min(hidden) < 64 or R * (S + 2) < UMNN_LAYERWISE_MIN_NODE_ROWS:
+            return None
+    need = 4 * (lib().gnf_umnn_lw_saved_floats(C.byref(net), R, S, int(train)) +
+                (lib().gnf_umnn_lw_workspace_bytes(C.byref(net), R, S, int(train)) // 4))
+    if need == 0 or need > SAVE_ACTIVATIONS_MAX_BYTES:
+        if UMNN_ENGINE == "layerwise" and need == 0:
+            raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
+        return None
+    return passes
+
+
 def cc_weights(nb_steps, device):
     """Clenshaw-Curtis weights / nodes, float64 numpy -> fp32, exactly as UMNN's compute_cc_weights
     (SURVEY.md App. B); cached per (S, device)."""
@@ -594,18 +619,32 @@ class UmnnFn(torch.autograd.Function):
         zrev = torch.empty_like(x) if want_rev else None
         logdet = torch.empty(B, device=x.device, dtype=x.dtype)
         saved = None
+        train = any(ctx.needs_input_grad)
+        lw_passes = None if fast else _umnn_layerwise_passes(net, R, int(S), train)
         if fast:
             _call("gnf_umnn_fwd_tc", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
                   ptr(logdet), R, d, ptr(ws), nbytes, stream_ptr())
+        elif lw_passes is not None:
+            # layer-wise engine: hidden x hidden layers on the tensor-core GEMM engine, activations in HBM
+            saved = torch.empty(lib().gnf_umnn_lw_saved_floats(C.byref(net), R, int(S), int(train)), device=x.device,
+                                dtype=torch.float32)
+            nbytes = lib().gnf_umnn_lw_workspace_bytes(C.byref(net), R, int(S), 0)
+            ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+            _call("gnf_umnn_fwd_lw", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
+                  ptr(logdet), ptr(saved), int(train), lw_passes, R, d, ptr(ws), nbytes, stream_ptr())
+            _count(3 + len(weights))
+            if not train:
+                saved = None
         else:
             # training: keep the hidden activations for the backward when they fit the budget (B200: 180 GB of HBM)
-            if any(ctx.needs_input_grad) and SAVE_ACTIVATIONS_MAX_BYTES > 0:
+            if train and SAVE_ACTIVATIONS_MAX_BYTES > 0:
                 per_row = lib().gnf_umnn_saved_floats_per_node_row(C.byref(net))
                 need = R * (int(S) + 1) * per_row * 4
                 if 0 < need <= SAVE_ACTIVATIONS_MAX_BYTES:
                     saved = torch.empty(R * (int(S) + 1) * per_row, device=x.device, dtype=torch.float32)
             _call("gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
                   ptr(logdet), ptr(saved), R, d, ptr(ws), nbytes, stream_ptr())
+        ctx.lw_passes = lw_passes if (lw_passes is not None and train) else None
         _count(2)
         ctx.saved_acts = saved
         ctx.save_for_backward(x, h, jac, *weights, *biases)
@@ -640,8 +679,16 @@ class UmnnFn(torch.autograd.Function):
         for l in range(n):
             grads.dW[l] = dWs[l].data_ptr()
             grads.db[l] = dbs[l].data_ptr()
-        _call("gnf_umnn_bwd", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev), ptr(gjac),
-              ptr(glogdet), ptr(ctx.saved_acts), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr())
+        if ctx.lw_passes is not None:
+            nbytes = lib().gnf_umnn_lw_workspace_bytes(C.byref(net), R, ctx.S, 1)
+            ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+            _call("gnf_umnn_bwd_lw", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev),
+                  ptr(gjac), ptr(glogdet), ptr(ctx.saved_acts), ptr(dx), ptr(dh), C.byref(grads), ctx.lw_passes, R, d, ptr(ws),
+                  nbytes, stream_ptr())
+            _count(4 + 3 * n)
+        else:
+            _call("gnf_umnn_bwd", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev), ptr(gjac),
+                  ptr(glogdet), ptr(ctx.saved_acts), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr())
         ctx.saved_acts = None
         _count(2)
         out = [dx, dh, None, None, None]

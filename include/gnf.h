@@ -109,6 +109,15 @@ int gnf_linear_dgrad_tc(const float* dY, int lddy, const float* W, int ldw, cons
                         int lddx, int M, int N, int K, int passes, gnf_stream_t stream);
 int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
                         int passes, gnf_stream_t stream);
+/* Measurement switch: 0 makes the tensor-core GEMM stage every operand with cp.async (the path taken anyway by operands
+ * whose base / leading dimension are not 16-byte aligned) instead of TMA tensor maps.  Default 1. */
+int gnf_tc_gemm_set_tma(int enable);
+/* 3xTF32 accuracy knob: k-chunks (of 32) accumulated inside the tensor core (round-toward-zero accumulation) before the
+ * partial sum is folded into a round-to-nearest running sum.  Default 2; a huge value disables folding. */
+int gnf_tc_gemm_set_fold(int chunks);
+/* Measurement: later tensor-core GEMM launches write SM-clock stamps of CTA 0's warp roles into buf (8 x 256 int64, device;
+ * rows: TMA issue, stager landed, stager published, MMA chunk ready, MMA tile committed, epilogue start, epilogue end). */
+int gnf_tc_gemm_set_trace(long long* buf);
 
 /* MaskedLinear's `mask * weight` (AutoregressiveConditioner.py:24-25) fused with the output-row
  * permutation that turns MADE's view(B,out,d).permute(0,2,1) (:108-109) into a plain row-major
@@ -216,6 +225,23 @@ size_t gnf_umnn_tc_workspace_bytes(const gnf_mlp_t* net);
 int gnf_umnn_fwd_tc(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
                     float* z, float* zrev, float* jac, float* logdet, int R, int d, void* work, size_t work_bytes,
                     gnf_stream_t stream);
+/* Layer-wise flavour of the same integral and of its backward: every integrand layer is one pass over all node-rows,
+ * the hidden x hidden layers run on the tensor-core GEMM engine (passes = 3: 3xTF32, fp32-equivalent; 1: TF32;
+ * 0: the strict FFMA tile GEMM), the conditioning half of the first layer is evaluated once per row instead of once
+ * per quadrature node, and hidden activations live in HBM between the passes.
+ * saved: [gnf_umnn_lw_saved_floats(net, R, S, train)] floats, written by the forward (L planes [Q, NP] + y [Q]);
+ * train != 0 adds the node-row that carries the chain rule of the jac output and is required by gnf_umnn_bwd_lw.
+ * Outputs, cotangents and gradient conventions are those of gnf_umnn_fwd / gnf_umnn_bwd. */
+size_t gnf_umnn_lw_saved_floats(const gnf_mlp_t* net, int R, int S, int train);
+size_t gnf_umnn_lw_workspace_bytes(const gnf_mlp_t* net, int R, int S, int backward);
+int gnf_umnn_fwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
+                    float* z, float* zrev, float* jac, float* logdet, float* saved, int train, int passes, int R, int d,
+                    void* work, size_t work_bytes, gnf_stream_t stream);
+int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
+                    const float* jac, const float* gz, const float* gzrev, const float* gjac, const float* glogdet,
+                    const float* saved, float* dx, float* dh, const gnf_mlp_grad_t* grads, int passes, int R, int d,
+                    void* work, size_t work_bytes, gnf_stream_t stream);
+
 /* Measurement tool (not on the product path): TMEM-read bandwidth / MMA issue rate / overlap probe on one CTA.
  * mode bit0: stream tcgen05.ld; bit1: issue TF32 MMAs; out[0], out[1]: elapsed SM clocks of the two roles. */
 int gnf_tc_probe(int mode, int iters, long long* out, gnf_stream_t stream);

@@ -1,0 +1,28 @@
+"""Warp-role timeline of the tcgen05 GEMM engine (CTA 0) for one shape; run on the GPU box.
+usage: gemm_trace.py M N K op(fwd|dgrad|wgrad) passes(1|3)"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import torch
+import gnf_b200 as G
+lib = G._lib.lib()
+M, N, K = (int(v) for v in sys.argv[1:4])
+op, passes = sys.argv[4], int(sys.argv[5])
+G.ops.set_gemm_mode("tf32" if passes == 1 else "tf32x3")
+X = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** .5; b = torch.randn(N, device="cuda")
+dY = torch.randn(M, N, device="cuda")
+fn = {"fwd": lambda: G.ops.linear_fwd(X, W, b, relu=True), "dgrad": lambda: G.ops.linear_dgrad(dY, N, W, X, M),
+      "wgrad": lambda: G.ops.linear_wgrad(dY, N, X, K, M, N, K)}[op]
+for _ in range(3): fn()
+buf = torch.zeros(8 * 256, dtype=torch.int64, device="cuda")
+lib.gnf_tc_gemm_set_trace(C.c_void_p(buf.data_ptr()))
+fn(); torch.cuda.synchronize()
+lib.gnf_tc_gemm_set_trace(None)
+t = buf.cpu().view(8, 256)
+t0 = int(t[t > 0].min())
+names = ["tma issued", "stager landed", "stager published", "mma chunk ready", "mma tile committed", "epi start", "epi end",
+         "epi tile1 chunk phases (start, acc+aux issued, computed, staged, stored, next acc ready) x chunks"]
+print(f"M={M} N={N} K={K} {op} passes={passes}: SM clocks relative to the first stamp")
+for r, n in enumerate(names):
+    v = [int(x) - t0 for x in t[r] if int(x) > 0][:(66 if r == 7 else 24)]
+    print(f"{n:20s}", v)

@@ -27,3 +27,15 @@ def emu():
 def test_golden_case_in_simulator(emu, name):
     torch.set_num_threads(1)
     parity.run_case(name, "cpu")
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "mono" in n])
+def test_golden_monotonic_case_layerwise_engine_in_simulator(emu, name):
+    """The layer-wise UMNN engine (umnn_lw.cu) with the FFMA GEMMs: per-layer passes, once-per-row conditioning half of
+    the first layer, first-layer reductions, against the reference's golden vectors."""
+    torch.set_num_threads(1)
+    G.ops.UMNN_ENGINE = "layerwise"
+    try:
+        parity.run_case(name, "cpu")
+    finally:
+        G.ops.UMNN_ENGINE = "auto"

@@ -87,7 +87,8 @@ def gemm_mode():
 
 
 SHAPES = [(1, 1, 1), (127, 33, 65), (300, 630, 126), (1000, 30, 630), (64, 2, 1024), (513, 210, 21), (6300, 630, 630),
-          (256, 1024, 784)]
+          (256, 1024, 784), (300, 160, 160), (1000, 152, 64), (513, 212, 20), (129, 4, 36), (2200, 150, 150),
+          (138600, 152, 148), (6300, 632, 632)]
 
 
 @pytest.mark.parametrize("M_,N,K", SHAPES)
@@ -175,3 +176,90 @@ def test_mixed_mode_training_gradients_vs_oracle(cfg, B):
     bad = {k: v for k, v in rep.items() if not v < 1e-2}
     print("mixed-mode gradient errors:", {k.split("steps.0.")[-1]: float("%.2g" % v) for k, v in rep.items()})
     assert not bad, f"gradients out of tolerance: {bad}"
+
+
+# ---------------- layer-wise UMNN engine (umnn_lw.cu): hidden layers on the GEMM engine, activations in HBM ----------------
+@pytest.fixture
+def umnn_engine():
+    def set_engine(engine, gemm="auto"):
+        G.ops.UMNN_ENGINE = engine
+        G.ops.set_gemm_mode(gemm)
+    yield set_engine
+    G.ops.UMNN_ENGINE = "auto"
+    G.ops.set_gemm_mode("ffma")
+
+
+def _strict_check(rep):
+    bad = {k: v for k, v in rep.items() if (k.startswith("grad.") and not v < 1e-3) or (k in ("ll", "loss") and not v < 1e-4)}
+    assert not bad, f"out of tolerance: {bad}\n{rep}"
+
+
+@pytest.mark.parametrize("gemm", ["ffma", "tf32x3"])
+@pytest.mark.parametrize("name", [n for n in __import__("helpers").golden_names() if n.endswith("mono") or "mono_" in n])
+def test_umnn_layerwise_golden_vectors(umnn_engine, name, gemm):
+    """Reference-generated golden vectors through the layer-wise engine (strict bars), FFMA and 3xTF32 GEMMs."""
+    umnn_engine("layerwise", gemm)
+    parity.run_case(name, "cuda", 1e-4, 1e-3)
+
+
+@pytest.mark.parametrize("cfg,B", [("cfg2", 256), ("cfg3", 48), ("cfg4", 12), ("cfg4", 100)])
+def test_umnn_layerwise_train_step_vs_oracle(umnn_engine, cfg, B):
+    """Strict bars (ll 1e-4, per-tensor gradients 1e-3) against the CPU oracle with the 3xTF32 layer-wise engine."""
+    import model_vs_oracle as M
+    umnn_engine("layerwise", "auto")
+    _strict_check(M.compare(M.CONFIGS[cfg], B, "cuda", train=True))
+
+
+@pytest.mark.parametrize("cfg,B,S", [("cfg4", 20, 40), ("cfg2", 33, 29), ("cfg3", 64, 40)])
+def test_umnn_layerwise_eval_vs_oracle(umnn_engine, cfg, B, S):
+    import model_vs_oracle as M
+    umnn_engine("layerwise", "auto")
+    _strict_check(M.compare(M.CONFIGS[cfg], B, "cuda", train=False, nb_steps=S))
+
+
+def test_umnn_layerwise_vs_float64_quadrature(umnn_engine):
+    """cfg4's integrand (30 -> 150 x 3 -> 1, S = 20) on 6300 rows, random inputs and cotangents: forward values and every
+    gradient of the layer-wise 3xTF32 engine against the oracle's quadrature evaluated in float64 (on the GPU), next to the
+    fused FFMA kernels.  Measured on B200: fused <= 1e-6, layer-wise <= 3e-5 (its long fp32 reductions over 138 600
+    node-rows), both far inside the 1e-3 gradient bar."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import gnf_oracle as O
+    torch.manual_seed(0)
+    B, d, S = 100, 63, 20
+    norm = G.MonotonicNormalizer([150, 150, 150], 30, nb_steps=S, solver="CC").to("cuda")
+    x, h = torch.randn(B, d, device="cuda"), torch.randn(B, d, 30, device="cuda")
+    cz, cj = torch.randn(B, d, device="cuda"), torch.randn(B, d, device="cuda")
+    sd64 = {"n." + k: v.detach().double().requires_grad_(True) for k, v in norm.state_dict().items()}
+    x64, h64 = x.double().requires_grad_(True), h.double().requires_grad_(True)
+    z, jac = O.monotonic_normalizer(x64, h64, sd64, "n.integrand_net.net", 4, S)
+    ((z * cz.double()).sum() + (torch.log(jac) * cj.double()).sum()).backward()
+    ref = {"x": x64.grad, "h": h64.grad, "z": z.detach(), "jac": jac.detach()}
+    ref.update({k[2:]: v.grad for k, v in sd64.items()})
+    for engine, gemm, tol in (("fused", "ffma", 1e-5), ("layerwise", "tf32x3", 2e-4)):
+        umnn_engine(engine, gemm)
+        xg, hg = x.clone().requires_grad_(True), h.clone().requires_grad_(True)
+        norm.zero_grad()
+        z32, j32 = norm(xg, hg)
+        ((z32 * cz).sum() + (torch.log(j32) * cj).sum()).backward()
+        got = {"x": xg.grad, "h": hg.grad, "z": z32.detach(), "jac": j32.detach()}
+        got.update({k: p.grad for k, p in norm.named_parameters()})
+        for k, r in ref.items():
+            err = float((got[k].double() - r).norm() / r.norm().clamp_min(1e-30))
+            assert err < (1e-6 if k in ("z", "jac") else tol), (engine, k, err)
+
+
+def test_umnn_layerwise_auto_engine_selection(umnn_engine):
+    """'auto' keeps the fused kernels in strict-FFMA mode and for tiny problems, and switches to the layer-wise engine
+    when tensor cores are allowed and the problem is large enough."""
+    import model_vs_oracle as M
+    _umnn_layerwise_passes, _mlp_struct = G.ops._umnn_layerwise_passes, G.ops._mlp_struct
+    model = M.build(M.CONFIGS["cfg4"], "cuda")
+    net_params = list(model.getNormalizers()[0].integrand_net.parameters())
+    net = _mlp_struct(net_params[0::2], net_params[1::2])
+    umnn_engine("auto", "ffma")
+    assert _umnn_layerwise_passes(net, 6300, 20, True) is None
+    umnn_engine("auto", "auto")
+    assert _umnn_layerwise_passes(net, 6300, 20, True) == 3
+    assert _umnn_layerwise_passes(net, 63, 20, True) is None
