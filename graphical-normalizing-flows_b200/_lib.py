@@ -81,6 +81,12 @@ _PROTOS = {
     "gnf_umnn_fwd_lw": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
     "gnf_umnn_bwd_lw": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MlpGradT), _I, _I, _I,
                          _P, _SZ, _P], C.c_int),
+    "gnf_umnn_lw_set_rw": ([_I], C.c_int),
+    "gnf_linear_rw_workspace_bytes": ([_I, _I], _SZ),
+    "gnf_linear_rw_set_trace": ([_P], C.c_int),
+    "gnf_linear_rw_set_debug": ([_I], C.c_int),
+    "gnf_linear_fwd_rw": ([_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
+    "gnf_linear_dgrad_rw": ([_P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
     "gnf_tc_gemm_set_tma": ([_I], C.c_int),
     "gnf_tc_gemm_set_fold": ([_I], C.c_int),
     "gnf_tc_gemm_set_trace": ([_P], C.c_int),

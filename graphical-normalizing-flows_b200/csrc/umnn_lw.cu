@@ -15,6 +15,7 @@
 // 0) carries the plain chain rule of the jac output, exactly like the fused backward.
 #include "common.cuh"
 #include "tc_gemm.h"
+#include "tc_rw.h"
 
 namespace gnf {
 
@@ -284,8 +285,11 @@ __global__ void lw_finish_dh_kernel(float* __restrict__ dh, int E, const float* 
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) dh[(size_t)r * E] += lw_gz_total(gz, gzrev, r, d);
 }
 
+static int g_lw_use_rw = 1;   // measurement switch (gnf_umnn_lw_set_rw): 0 = hidden GEMMs on the generic tensor-core engine
+
 struct LwPlan {
   int L, NP, E, nodes;
+  int rw;          // hidden layers fit the resident-weight tensor-core kernel (tc_rw.cu)
   long long Q;
   size_t off_P, off_Wp[GNF_MAX_LAYERS], off_dA, off_dB, off_D, total;  // workspace offsets in floats
 };
@@ -309,7 +313,15 @@ static int lw_plan(const gnf_mlp_t* net, int R, int S, int train, int backward, 
   const size_t plane = (size_t)pl->Q * pl->NP;
   pl->off_P = off; off += (size_t)R * pl->NP;            // forward: P;  backward: D (same shape)
   pl->off_D = pl->off_P;
-  for (int l = 1; l < L; ++l) { pl->off_Wp[l] = off; off += (size_t)pl->NP * pl->NP; }
+#ifdef GNF_EMU
+  pl->rw = 0;
+#else
+  pl->rw = 1;                                              // every hidden layer, both directions (dgrad swaps N and K)
+  for (int l = 1; l < L; ++l)
+    if (!rw_supported(net->dims[l + 1], net->dims[l]) || !rw_supported(net->dims[l], net->dims[l + 1])) pl->rw = 0;
+#endif
+  // per hidden layer: the zero-padded weight copy (generic engines) or the hi/lo TF32 images + bias (resident-weight kernel)
+  for (int l = 1; l < L; ++l) { pl->off_Wp[l] = off; off += (size_t)2 * pl->NP * pl->NP + pl->NP; }
   pl->off_dA = pl->off_dB = 0;
   if (backward) {
     pl->off_dA = off; off += plane;
@@ -329,11 +341,19 @@ static inline int lw_blocks(long long work_items, int per_block, int max_per_sm)
 // Y = act(X W^T + b) / dX = (dY W) o relu'(act) / dW = dY^T X through the selected GEMM engine.
 // passes: 0 = strict FFMA tile GEMM, 1 = TF32, 3 = 3xTF32 (tcgen05).
 static int lw_fwd_gemm(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int M, int N, int K,
-                       int relu, uint32_t* bits_out, int bits_ld, int passes, cudaStream_t s) {
+                       int relu, uint32_t* bits_out, int bits_ld, int passes, int rw_np, cudaStream_t s) {
   if (passes == 0) return gnf_linear_fwd(X, ldx, W, ldw, bias, 1, Y, ldy, M, N, K, relu, (gnf_stream_t)s);
 #ifdef GNF_EMU
   return fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
 #else
+  if (rw_np) {                                           // W = packed hi/lo images + bias (rw_pack_image)
+    RwGemmParams r = {};
+    r.A = X; r.lda = ldx; r.C = Y; r.ldc = ldy; r.image = W;
+    r.M = M; r.NP = rw_np; r.KP = (K + 7) / 8 * 8; r.passes = passes; r.epi = RW_EPI_BIAS_ACT; r.relu = relu;
+    r.bits_out = bits_out; r.bits_ld = bits_ld;
+    if (int e = launch_rw_gemm(r, s)) return e;
+    return check_launch("gnf_umnn_fwd_lw (resident-weight GEMM)");
+  }
   TcGemmParams p = {};
   p.A = X; p.lda = ldx; p.a_src = TCG_SRC_K;
   p.B = W; p.ldb = ldw; p.b_src = TCG_SRC_K;
@@ -345,11 +365,19 @@ static int lw_fwd_gemm(const float* X, int ldx, const float* W, int ldw, const f
 #endif
 }
 static int lw_dgrad_gemm(const float* dY, int lddy, const float* W, int ldw, const float* act, int ldact, const uint32_t* mask_bits,
-                         int mask_ld, float* dX, int lddx, int M, int N, int K, int passes, cudaStream_t s) {
+                         int mask_ld, float* dX, int lddx, int M, int N, int K, int passes, int rw_np, cudaStream_t s) {
   if (passes == 0) return gnf_linear_dgrad(dY, lddy, W, ldw, act, ldact, dX, lddx, M, N, K, (gnf_stream_t)s);
 #ifdef GNF_EMU
   return fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
 #else
+  if (rw_np) {                                           // W = packed hi/lo images of the TRANSPOSED weights
+    RwGemmParams r = {};
+    r.A = dY; r.lda = lddy; r.C = dX; r.ldc = lddx; r.image = W;
+    r.M = M; r.NP = rw_np; r.KP = (N + 7) / 8 * 8; r.passes = passes; r.epi = RW_EPI_MASK;   // reduction over the out-features
+    r.mask_bits = mask_bits; r.mask_ld = mask_ld; r.act = act; r.ldact = ldact;
+    if (int e = launch_rw_gemm(r, s)) return e;
+    return check_launch("gnf_umnn_bwd_lw (resident-weight GEMM)");
+  }
   TcGemmParams p = {};
   p.A = dY; p.lda = lddy; p.a_src = TCG_SRC_K;
   p.B = W; p.ldb = ldw; p.b_src = TCG_SRC_MN;
@@ -365,10 +393,20 @@ static int lw_wgrad_gemm(const float* dY, int lddy, const float* X, int ldx, flo
   return gnf_linear_wgrad_tc(dY, lddy, X, ldx, dW, lddw, M, N, K, passes, (gnf_stream_t)s);
 }
 
-static void lw_pad_weights(const gnf_mlp_t* net, const LwPlan& pl, float* ws, cudaStream_t s) {
-  for (int l = 1; l < pl.L; ++l)
+// Per-call weight staging of the hidden layers: hi/lo TF32 images for the resident-weight kernel (transposed for the
+// dgrad direction), else zero-padded copies for the generic engines.
+static void lw_pad_weights(const gnf_mlp_t* net, const LwPlan& pl, float* ws, int use_rw, int transpose, cudaStream_t s) {
+  for (int l = 1; l < pl.L; ++l) {
+#ifndef GNF_EMU
+    if (use_rw) {
+      if (transpose) rw_pack_image(net->W[l], net->dims[l], net->dims[l], net->dims[l + 1], 1, nullptr, ws + pl.off_Wp[l], pl.NP, (net->dims[l + 1] + 7) / 8 * 8, s);
+      else rw_pack_image(net->W[l], net->dims[l], net->dims[l + 1], net->dims[l], 0, net->b[l], ws + pl.off_Wp[l], pl.NP, (net->dims[l] + 7) / 8 * 8, s);
+      continue;
+    }
+#endif
     GNF_LAUNCH(lw_pad_weight_kernel, lw_blocks((long long)pl.NP * pl.NP, 256, 2), 256, 0, s, net->W[l], net->dims[l + 1], net->dims[l],
                ws + pl.off_Wp[l], pl.NP, pl.NP);
+  }
 }
 
 }  // namespace gnf
@@ -376,6 +414,11 @@ static void lw_pad_weights(const gnf_mlp_t* net, const LwPlan& pl, float* ws, cu
 using namespace gnf;
 
 extern "C" {
+
+int gnf_umnn_lw_set_rw(int enable) {
+  g_lw_use_rw = enable != 0;
+  return 0;
+}
 
 size_t gnf_umnn_lw_saved_floats(const gnf_mlp_t* net, int R, int S, int train) {
   LwPlan pl;
@@ -409,7 +452,8 @@ int gnf_umnn_fwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   // P = h W0[:,1:]^T + b0  (once per row r; strict fp32 on the FFMA engine: R x N1 x E is tiny)
   float* P = ws + pl.off_P;
   if (int e = gnf_linear_fwd(h, E, net->W[0] + 1, 1 + E, net->b[0], 1, P, NP, R, net->dims[1], E, 0, stream)) return e;
-  lw_pad_weights(net, pl, ws, s);
+  const int use_rw = (pl.rw && passes != 0 && g_lw_use_rw) ? 1 : 0;
+  lw_pad_weights(net, pl, ws, use_rw, 0, s);
   // ReLU bit masks of a_1 .. a_{L-1} (what the backward's dgrad epilogues consume), kept only when training on the tensor cores
   const int WB = NP / 32;
   const size_t bplane = (size_t)pl.Q * WB;
@@ -419,7 +463,7 @@ int gnf_umnn_fwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   for (int l = 1; l < L; ++l) {
     uint32_t* bo = (bits && l + 1 < L) ? bits + (size_t)l * bplane : nullptr;     // mask of a_{l+1}
     if (int e = lw_fwd_gemm(saved + (size_t)(l - 1) * plane, NP, ws + pl.off_Wp[l], NP, net->b[l], saved + (size_t)l * plane, NP,
-                            (int)pl.Q, net->dims[l + 1], net->dims[l], 1, bo, WB, passes, s)) return e;
+                            (int)pl.Q, net->dims[l + 1], net->dims[l], 1, bo, WB, passes, use_rw ? NP : 0, s)) return e;
   }
   float* ysave = saved + (size_t)L * plane;
   GNF_LAUNCH(lw_out_fwd_kernel, lw_blocks(R, 8, 8), 256, 0, s, saved + (size_t)(L - 1) * plane, net->W[L], net->b[L], net->dims[L], x, h,
@@ -448,7 +492,8 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   const size_t plane = (size_t)pl.Q * NP;
   LwGeom g;
   g.R = R; g.d = d; g.E = E; g.S = S; g.nodes = pl.nodes; g.NP = NP; g.L = L; g.Q = pl.Q;
-  lw_pad_weights(net, pl, ws, s);
+  const int use_rw = (pl.rw && passes != 0 && g_lw_use_rw) ? 1 : 0;
+  lw_pad_weights(net, pl, ws, use_rw, 1, s);
   float* dcur = ws + pl.off_dA;
   float* dnxt = ws + pl.off_dB;
   const int red_threads = (NP / 4) * kLwRL;
@@ -462,7 +507,7 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
     const float* a_l = saved + (size_t)(l - 1) * plane;
     if (int e = lw_wgrad_gemm(dcur, NP, a_l, NP, grads->dW[l], net->dims[l], (int)pl.Q, net->dims[l + 1], net->dims[l], passes, s)) return e;
     const uint32_t* mb = passes != 0 ? reinterpret_cast<const uint32_t*>(saved + (size_t)L * plane + pl.Q) + (size_t)(l - 1) * pl.Q * (NP / 32) : nullptr;
-    if (int e = lw_dgrad_gemm(dcur, NP, ws + pl.off_Wp[l], NP, a_l, NP, mb, NP / 32, dnxt, NP, (int)pl.Q, net->dims[l + 1], net->dims[l], passes, s)) return e;
+    if (int e = lw_dgrad_gemm(dcur, NP, ws + pl.off_Wp[l], NP, a_l, NP, mb, NP / 32, dnxt, NP, (int)pl.Q, net->dims[l + 1], net->dims[l], passes, use_rw ? NP : 0, s)) return e;
     if (l > 1) {
       if (int e = gnf_colsum(dnxt, NP, grads->db[l - 1], (int)pl.Q, net->dims[l], 1, stream)) return e;
     }

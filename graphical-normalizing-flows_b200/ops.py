@@ -697,6 +697,49 @@ class UmnnFn(torch.autograd.Function):
         return tuple(out)
 
 
+def _pad32(v):
+    return (v + 31) // 32 * 32
+
+
+def linear_fwd_rw(X, W, bias, relu, passes=3, want_bits=False):
+    """Y = act(X[:, :K] @ W^T + bias) on the resident-weight tensor-core kernel (tc_rw.cu).  X: [M, pad32(K)] with zero
+    padding columns; returns Y [M, pad32(N)] (padding columns 0) and, if want_bits, the ReLU bit mask [M, pad32(N)/32]."""
+    require(X, "X"), require(W, "W")
+    N, K = W.shape
+    M = X.shape[0]
+    if X.shape[1] != _pad32(K):
+        raise ValueError(f"X must have pad32(K) = {_pad32(K)} columns")
+    nbytes = lib().gnf_linear_rw_workspace_bytes(N, K)
+    if nbytes == 0:
+        raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
+    ws = torch.empty(nbytes // 4, device=X.device, dtype=torch.float32)
+    Y = torch.empty(M, _pad32(N), device=X.device, dtype=torch.float32)
+    bits = torch.empty(M, _pad32(N) // 32, device=X.device, dtype=torch.int32) if want_bits else None
+    _call("gnf_linear_fwd_rw", ptr(X), X.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(Y), Y.stride(0), ptr(bits), M, N, K,
+          int(relu), int(passes), ptr(ws), nbytes, stream_ptr())
+    _count(2)
+    return (Y, bits) if want_bits else Y
+
+
+def linear_dgrad_rw(dY, W, act=None, mask_bits=None, passes=3):
+    """dX = (dY[:, :N] @ W) o relu'(.) on the resident-weight kernel.  dY: [M, pad32(N)] (zero padding); act [M, pad32(K)]
+    or mask_bits [M, pad32(K)/32] select the ReLU mask; returns dX [M, pad32(K)]."""
+    require(dY, "dY"), require(W, "W")
+    N, K = W.shape
+    M = dY.shape[0]
+    if dY.shape[1] != _pad32(N):
+        raise ValueError(f"dY must have pad32(N) = {_pad32(N)} columns")
+    nbytes = lib().gnf_linear_rw_workspace_bytes(K, N)
+    if nbytes == 0:
+        raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
+    ws = torch.empty(nbytes // 4, device=dY.device, dtype=torch.float32)
+    dX = torch.empty(M, _pad32(K), device=dY.device, dtype=torch.float32)
+    _call("gnf_linear_dgrad_rw", ptr(dY), dY.stride(0), ptr(W), W.stride(0), ptr(act), act.stride(0) if act is not None else 0,
+          ptr(mask_bits), ptr(dX), dX.stride(0), M, N, K, int(passes), ptr(ws), nbytes, stream_ptr())
+    _count(2)
+    return dX
+
+
 def counter_add(counter, inc=1):
     """*counter += inc on the device (int64 tensor with one element)."""
     _call("gnf_counter_add", ptr(counter), int(inc), stream_ptr())

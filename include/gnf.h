@@ -242,6 +242,30 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
                     const float* saved, float* dx, float* dh, const gnf_mlp_grad_t* grads, int passes, int R, int d,
                     void* work, size_t work_bytes, gnf_stream_t stream);
 
+/* Measurement switch: 0 routes the layer-wise engine's hidden GEMMs to the generic tensor-core engine (gnf_linear_*_tc)
+ * instead of the resident-weight kernel below.  Default 1. */
+int gnf_umnn_lw_set_rw(int enable);
+
+/* Resident-weight tensor-core layer GEMM (tc_rw.cu) -- the hidden x hidden layers of IntegrandNet
+ * (MonotonicNormalizer.py:12-38) over all quadrature node-rows, forward and dgrad.  The layer's weights (N, K <= 160) are
+ * split into TF32 hi / lo images once per call and stay resident in shared memory; the activations stream global ->
+ * registers -> TMEM (no shared-memory staging), TS-form tcgen05.mma, row-owner epilogue.  passes as gnf_linear_*_tc.
+ * Operand contract (what the layer-wise engine's padded planes satisfy): X / dY / Y / dX rows 32-byte aligned (leading dimensions multiples of 8), X / dY with
+ * round_up(K or N, 32) readable columns whose padding is zero; Y / dX receive round_up(N or K, 32) columns per row.
+ * bits_out (nullable): ReLU bit mask of Y, [M][round_up(N,32)/32] words; mask_bits (nullable, same layout) or act select
+ * the ReLU mask of dgrad.  work: gnf_linear_rw_workspace_bytes(N, K) bytes (0 = shape unsupported, see gnf_last_error). */
+size_t gnf_linear_rw_workspace_bytes(int N, int K);
+/* Measurement: later resident-weight GEMM launches write SM-clock stamps of CTA 0 into buf (4 x 256 int64, device; rows:
+ * MMA issuer, loader of even chunks, loader of odd chunks, epilogue).  NULL disables. */
+int gnf_linear_rw_set_trace(long long* buf);
+/* Measurement: bit0 skips the kernel's global stores, bit1 its global loads, bit2 its MMAs (results are then garbage). */
+int gnf_linear_rw_set_debug(int bits);
+int gnf_linear_fwd_rw(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, uint32_t* bits_out,
+                      int M, int N, int K, int relu, int passes, void* work, size_t work_bytes, gnf_stream_t stream);
+int gnf_linear_dgrad_rw(const float* dY, int lddy, const float* W, int ldw, const float* act, int ldact,
+                        const uint32_t* mask_bits, float* dX, int lddx, int M, int N, int K, int passes, void* work,
+                        size_t work_bytes, gnf_stream_t stream);
+
 /* Measurement tool (not on the product path): TMEM-read bandwidth / MMA issue rate / overlap probe on one CTA.
  * mode bit0: stream tcgen05.ld; bit1: issue TF32 MMAs; out[0], out[1]: elapsed SM clocks of the two roles. */
 int gnf_tc_probe(int mode, int iters, long long* out, gnf_stream_t stream);
