@@ -23,14 +23,14 @@
 //     coalesced (4 rows x 128 B per instruction) global layout into the row-owner layout and back, conflict-free;
 //   * epilogue thread t owns row t: tcgen05.ld 32 columns -> bias + ReLU (or ReLU-mask bits) -> staged store, the ReLU
 //     bit mask of the output row as one word per 32 columns.
-// Roles: warps 0-3 epilogue, warps 4-11 loaders (two per TMEM lane quarter, alternating 32-column chunks; lane 0 of
-// warp 4 also issues the MMAs right after its own hand-over: 12 warps = 168 registers per thread, a 13th would cost 40).
-// A and D are single-buffered in TMEM (A_hi 160 + A_lo 160 + D 160 columns), so both are held as briefly as possible:
-// every loader thread has exactly ONE load group outstanding -- its next chunk -- issued as soon as the current one is
-// staged (deeper per-thread prefetch was measured slower: the 6 scoreboards alias and the oldest chunk then waits for
-// the newest), the memory parallelism coming from the eight loader warps; an epilogue thread drains four of its five
-// accumulator blocks into registers at once (tcgen05.ld.x32) and hands D back after the first block is stored, so the
-// next tile's MMAs overlap the rest of the epilogue and the next tile's loads overlap the MMAs.
+// Roles: warps 0-3 epilogue, warps 4-11 loaders (two per TMEM lane quarter, alternating 32-column chunks), warp 12 the
+// MMA issuer (one thread; it shared a loader warp at first, and that warp's serial load -> issue -> load chain was the
+// whole tile period: profiles/r01z_rw_gemm_trace.txt).  A and D are single-buffered in TMEM (A_hi 160 + A_lo 160 + D 160
+// columns), so both are held as briefly as possible: every loader thread has exactly ONE load group outstanding -- its
+// next chunk -- issued as soon as the current one is staged, converts it to the row-owner layout and splits it BEFORE
+// waiting for A to be free; an epilogue thread drains three accumulator blocks into registers at once (tcgen05.ld.x32)
+// and hands D back as soon as the last block is read, so the next tile's MMAs overlap most of the epilogue and the
+// next tile's loads overlap the MMAs.
 #include "tc_common.cuh"
 #include "tc_rw.h"
 
@@ -42,7 +42,7 @@ constexpr int kRwEpiWarps = 4, kRwLoadWarps = 8;
 constexpr int kRwEpiStageFloats = 32 * 32;                     // epilogue warp: one 32-row x 32-column transposition block
 constexpr int kRwLoadStageFloats = 32 * 16;                    // loader warp: one 32-row x 16-column block (two passes per chunk)
 constexpr int kRwStageFloatsTotal = kRwEpiWarps * kRwEpiStageFloats + kRwLoadWarps * kRwLoadStageFloats;
-constexpr int kRwThreads = (kRwEpiWarps + kRwLoadWarps) * 32;   // 12 warps: 168 registers per thread
+constexpr int kRwThreads = 16 * 32;   // 4 epilogue + 8 loader + 1 MMA issuer warp (+3 idle: registers come in 4-warp granules): 128 registers per thread
 constexpr int kRwColAhi = 0, kRwColAlo = 160, kRwColD = 320;   // TMEM columns
 constexpr int kRwMaxK = 160, kRwMaxN = 160;
 constexpr int kRwMaxChunks = kRwMaxK / 32;
@@ -134,46 +134,48 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
   const bool split = p.passes == 3;
   const int sub = lane >> 3, piece = lane & 7;               // coalesced view of a 32 x 32 block: lane <-> (row 4i + sub, 16-byte piece)
 
-  if (warp >= kRwEpiWarps) {
-    // ===================== loaders (+ the MMA issuer: lane 0 of the first loader warp) =====================
-    const int lw = warp - kRwEpiWarps, quarter = lw & 3, half = lw >> 2;     // chunk parity this warp serves
-    const bool issuer = lw == 0 && lane == 0;
-    float* stage = stage_all + kRwEpiWarps * kRwEpiStageFloats + lw * kRwLoadStageFloats;
-    const uint32_t idesc = make_idesc_tf32(kRwRows, NP);
-    const uint32_t whi = smem_u32(smem), wlo = whi + (uint32_t)NP * (uint32_t)KP * 4u;
-    const uint64_t dhi0 = make_smem_desc(whi, (uint32_t)NP * 16u, 128u), dlo0 = make_smem_desc(wlo, (uint32_t)NP * 16u, 128u);
-    const uint64_t dstep = (uint64_t)((2u * (uint32_t)NP * 16u) >> 4);        // one k-step (8 k) = two 16-byte K chunks of the image
-    const uint32_t tD = tmem_base + kRwColD, tAhi = tmem_base + kRwColAhi, tAlo = tmem_base + kRwColAlo;
-    const uint32_t tA = tmem_base + lane_sel;
-    RwTrace trm = {(p.trace && blockIdx.x == 0 && issuer) ? p.trace : nullptr, 0};
-    RwTrace tr = {(p.trace && blockIdx.x == 0 && lane == 0 && quarter == 0) ? p.trace + (1 + half) * kRwTraceLen : nullptr, 0};
-    if (issuer) mbar_wait(w_full, 0);
-    // correction products of chunk c as soon as all four lane quarters have handed it over; after the last chunk the
-    // a_hi * b_hi chain and the two commits (A free for the loaders, D full for the epilogue)
-    auto issue_chunk = [&](long long tl, int c) {
-      if (c == 0) {
+  if (warp >= kRwEpiWarps + kRwLoadWarps) {
+    // ===================== MMA issuer (one thread) =====================
+    if (warp == kRwEpiWarps + kRwLoadWarps && lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(kRwRows, NP);
+      const uint32_t whi = smem_u32(smem), wlo = whi + (uint32_t)NP * (uint32_t)KP * 4u;
+      const uint64_t dhi0 = make_smem_desc(whi, (uint32_t)NP * 16u, 128u), dlo0 = make_smem_desc(wlo, (uint32_t)NP * 16u, 128u);
+      const uint64_t dstep = (uint64_t)((2u * (uint32_t)NP * 16u) >> 4);      // one k-step (8 k) = two 16-byte K chunks of the image
+      const uint32_t tD = tmem_base + kRwColD, tAhi = tmem_base + kRwColAhi, tAlo = tmem_base + kRwColAlo;
+      RwTrace trm = {(p.trace && blockIdx.x == 0) ? p.trace : nullptr, 0};
+      mbar_wait(w_full, 0);
+      for (long long tl = 0; tl < n_local; ++tl) {
         trm.stamp();                                         // per tile: start, D free, chunk c issued (x NCH), all issued
         if (tl > 0) mbar_wait(d_empty, (uint32_t)((tl - 1) & 1));
         trm.stamp();
-      }
-      mbar_wait(&a_full[c], (uint32_t)(tl & 1));
-      fence_after_sync();
-      const int k0 = c * 4, k1 = (p.debug & 4) ? k0 + (c == 0 ? 1 : 0) : ((k0 + 4 < nksteps) ? k0 + 4 : nksteps);
-      if (split) {
-        for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAlo + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
-        for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dlo0 + dstep * kk, idesc, 1u);
-      } else {
-        for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
-      }
-      trm.stamp();
-      if (c == NCH - 1) {
+        // correction products of chunk c as soon as all four lane quarters have handed it over; after the last chunk the
+        // a_hi * b_hi chain and the two commits (A free for the loaders, D full for the epilogue)
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          mbar_wait(&a_full[c], (uint32_t)(tl & 1));
+          fence_after_sync();
+          const int k0 = c * 4, k1 = (p.debug & 4) ? k0 + (c == 0 ? 1 : 0) : ((k0 + 4 < nksteps) ? k0 + 4 : nksteps);
+          if (split) {
+            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAlo + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
+            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dlo0 + dstep * kk, idesc, 1u);
+          } else {
+            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
+          }
+          trm.stamp();
+        }
         if (split && !(p.debug & 4))
           for (int kk = 0; kk < nksteps; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, 1u);
         mma_commit(a_empty);
         mma_commit(d_full);
         trm.stamp();
       }
-    };
+    }
+  } else if (warp >= kRwEpiWarps) {
+    // ===================== loaders =====================
+    const int lw = warp - kRwEpiWarps, quarter = lw & 3, half = lw >> 2;     // chunk parity this warp serves
+    float* stage = stage_all + kRwEpiWarps * kRwEpiStageFloats + lw * kRwLoadStageFloats;
+    const uint32_t tA = tmem_base + lane_sel;
+    RwTrace tr = {(p.trace && blockIdx.x == 0 && lane == 0 && quarter == 0) ? p.trace + (1 + half) * kRwTraceLen : nullptr, 0};
     const int n_my = (NCH - half + 1) / 2;                   // chunks per tile served by this warp (0 for odd warps when NCH == 1)
     // the thread's share (coalesced view) of one 32-column chunk: 8 x 16 bytes, rows 4i + sub.  Exactly one load group
     // is outstanding per thread (its next chunk); memory parallelism comes from the eight loader warps.
@@ -235,11 +237,6 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
       __syncwarp();
       if (lane == 0) rw_mbar_arrive(&a_full[c]);
       tr.stamp();
-      if (issuer) {
-        issue_chunk(tl, c);
-        if (c + 1 < NCH) issue_chunk(tl, c + 1);
-      }
-      __syncwarp();
     }
   } else {
     // ===================== epilogue =====================
@@ -249,7 +246,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
     const bool bit_mask = p.epi == RW_EPI_MASK && p.mask_bits != nullptr;
     const bool act_mask = p.epi == RW_EPI_MASK && !bit_mask && p.act != nullptr;
     RwTrace tr = {(p.trace && blockIdx.x == 0 && tid == 0) ? p.trace + 3 * kRwTraceLen : nullptr, 0};
-    constexpr int W = NB < 4 ? NB : 4;                       // accumulator blocks held in registers at once
+    constexpr int W = NB < 3 ? NB : 3;                       // accumulator blocks held in registers at once (128 registers per thread)
     for (long long tl = 0; tl < n_local; ++tl) {
       tr.stamp();                                            // per tile: start, D full, first window drained, each block stored
       const long long row = ((long long)blockIdx.x + tl * gridDim.x) * kRwRows + warp * 32 + lane;
@@ -261,8 +258,8 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
       mbar_wait(d_full, (uint32_t)(tl & 1));
       fence_after_sync();
       tr.stamp();
-      // drain up to four 32-column blocks of the accumulator row into registers at once; D goes back to the MMA issuer as
-      // soon as the last block has been read (for NB = 5: after the first block is stored), not after the last store
+      // drain up to three 32-column blocks of the accumulator row into registers at once; D goes back to the MMA issuer as
+      // soon as the last block has been read (for NB = 5: after the second block is staged), not after the last store
       uint32_t acc[W][32];
 #pragma unroll
       for (int ci = 0; ci < W; ++ci) tmem_ld32p(tD + ci * 32, acc[ci]);

@@ -215,8 +215,10 @@ def get_gemm_mode():
 
 
 def _gemm_passes(M, N, K, op="fwd"):
-    """0 = FFMA engine, 1 / 3 = tensor-core engine passes; thresholds from scripts/gemm_bench.py on B200
-    (the split-K FFMA wgrad is the slowest of the three FFMA GEMMs, so wgrad switches to 3xTF32 earlier)."""
+    """0 = FFMA engine, 1 / 3 = tensor-core engine passes; thresholds from scripts/gemm_bench.py on B200 with
+    TMA-loadable operands (16-byte aligned rows: activations are allocated with padded row strides and weights get a
+    padded copy, see _rows / _tma_weight): 3xTF32 beats the FFMA engine from ~0.4 GFLOP-sized layers on, e.g.
+    6300 x 632 x 632: 78 vs 144 us, 10000 x 212 x 212: 37 vs 55 us (profiles/r01y_gemm_bench_generic.txt)."""
     if _GEMM_MODE == "ffma":
         return 0
     if _GEMM_MODE == "tf32":
@@ -225,9 +227,30 @@ def _gemm_passes(M, N, K, op="fwd"):
         return 3
     if _GEMM_MODE == "auto":
         if op == "wgrad":
-            return 3 if (min(N, K) >= 256 and M >= 4096) else 0
-        return 3 if (min(N, K) >= 256 and float(M) * N * K >= 8e9) else 0
+            return 3 if (min(N, K) >= 128 and M >= 4096) else 0
+        return 3 if (min(N, K) >= 128 and float(M) * N * K >= 4e8) else 0
     return 1 if min(N, K) >= 128 else 0
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _rows(M, N, like):
+    """[M, N] activation buffer whose rows start 16-byte aligned (row stride padded to 4 floats): what the tensor-core
+    engine's TMA tensor maps need; every kernel takes the row stride explicitly."""
+    t = torch.empty(M, _pad4(N), device=like.device, dtype=like.dtype)
+    return t if t.shape[1] == N else t[:, :N]
+
+
+def _tma_weight(W):
+    """W itself if its rows are 16-byte aligned, else a copy with the row stride padded to 4 floats (630 -> 632): the
+    unaligned staging path of the tensor-core engine is 2x slower than TMA (148 vs 78 us at 6300 x 630 x 630)."""
+    if W.stride(0) % 4 == 0 and W.data_ptr() % 16 == 0:
+        return W
+    Wp = _rows(W.shape[0], W.shape[1], W)
+    Wp.copy_(W)
+    return Wp
 
 
 def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=None):
@@ -237,10 +260,11 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
     K = W.shape[1] if K is None else K
     ldx = X.stride(0) if ldx is None else ldx
     if out is None:
-        out = torch.empty(M, N, device=X.device, dtype=X.dtype)
-        ldy = N
+        out = _rows(M, N, X)
+        ldy = out.stride(0)
     passes = _gemm_passes(M, N, K)
     if passes:
+        W = _tma_weight(W)
         _call("gnf_linear_fwd_tc", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
               passes, stream_ptr())
     else:
@@ -253,10 +277,11 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
 def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
     N, K = W.shape
     if out is None:
-        out = torch.empty(M, K, device=dY.device, dtype=dY.dtype)
-        lddx = K
+        out = _rows(M, K, dY)
+        lddx = out.stride(0)
     passes = _gemm_passes(M, N, K)
     if passes:
+        W = _tma_weight(W)
         _call("gnf_linear_dgrad_tc", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
               ptr(out), lddx, M, N, K, passes, stream_ptr())
     else:
@@ -304,7 +329,7 @@ def _mlp_backward(gout, ldg, acts, x_in, ldx, K0, weights, need_dx, first_layer_
             a_prev = acts[l - 1]
             dWs[l] = linear_wgrad(delta, ldd, a_prev, a_prev.stride(0), M, N, K)
             delta = linear_dgrad(delta, ldd, W, a_prev, M)
-            ldd = K
+            ldd = delta.stride(0)
         else:
             dWs[0] = linear_wgrad(delta, ldd, x_in, ldx, M, N, K0)
             dx = linear_dgrad(delta, ldd, W, None, M) if need_dx else None
@@ -327,7 +352,10 @@ class MlpFn(torch.autograd.Function):
         acts = []
         cur, ldx, K = x, x.stride(0), K0
         for l in range(n):
-            cur = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), K=K, ldx=ldx)
+            out = None
+            if l == n - 1:   # the result leaves the Function: plain contiguous rows
+                out = torch.empty(x.shape[0], weights[l].shape[0], device=x.device, dtype=x.dtype)
+            cur = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), K=K, ldx=ldx, out=out, ldy=weights[l].shape[0])
             ldx, K = cur.stride(0), cur.shape[1]
             if l < n - 1:
                 acts.append(cur)
@@ -467,9 +495,9 @@ class DagMlpFn(torch.autograd.Function):
         T = torch.empty(d if hot else 1, N1, device=x.device, dtype=x.dtype)
         _call("gnf_dag_bias_table", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st)
         g = gate.c_struct()
-        y = torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
+        y = _rows(B * d, N1, x) if n > 1 else torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
         _call("gnf_dag_l1_fwd", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
-                                   ptr(y), N1, B, d, N1, int(n > 1), st)
+                                   ptr(y), y.stride(0), B, d, N1, int(n > 1), st)
         _count(3)
         acts = []
         cur = y
