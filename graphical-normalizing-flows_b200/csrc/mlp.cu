@@ -373,7 +373,9 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   LoadRowMajorA al{dY, lddy};   // A(m, n)
   LoadRowMajorB bl{W1, ldw};    // B(n, j) = W1[n, j]
   EpiDagDgrad epi{g, dx, dP};
-  launch_gemm_auto(al, bl, epi, M, d, N, false, s);
+  // N = d <= 64 gives one column of tiles (50 CTAs at cfg4): split the reduction over the layer width.  The epilogue is
+  // linear in the accumulator and already reduces with atomics, so partial sums need no second pass.
+  launch_gemm_auto(al, bl, epi, M, d, N, true, s);
   return check_launch("gnf_dag_l1_dgrad");
 }
 

@@ -32,12 +32,26 @@ def enable_kernel_timing(flag):
     _TIMING = bool(flag)
     if flag:
         _TIMES.clear()
+        _FLOPS.clear()
 
 
 def collect_kernel_timing():
     """{entry point: [ms per call]} — synchronises."""
     torch.cuda.synchronize()
     return {k: [a.elapsed_time(b) for a, b in v] for k, v in _TIMES.items()}
+
+
+_FLOPS = {}
+
+
+def collect_call_flops():
+    """{entry point: [algorithmic FLOPs per call]} for the GEMM entry points timed since enable_kernel_timing(True)."""
+    return {k: list(v) for k, v in _FLOPS.items()}
+
+
+def _note_flops(name, flops):
+    if _TIMING:
+        _FLOPS.setdefault(name, []).append(float(flops))
 
 
 def _call(name, *args):
@@ -265,6 +279,7 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
     passes = _gemm_passes(M, N, K)
     if passes:
         W = _tma_weight(W)
+        _note_flops("gnf_linear_fwd_tc", 2. * M * N * K)
         _call("gnf_linear_fwd_tc", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
               passes, stream_ptr())
     else:
@@ -282,6 +297,7 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
     passes = _gemm_passes(M, N, K)
     if passes:
         W = _tma_weight(W)
+        _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K)
         _call("gnf_linear_dgrad_tc", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
               ptr(out), lddx, M, N, K, passes, stream_ptr())
     else:
@@ -295,6 +311,7 @@ def linear_wgrad(dY, lddy, X, ldx, M, N, K):
     dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
     passes = _gemm_passes(M, N, K, "wgrad")
     if passes:
+        _note_flops("gnf_linear_wgrad_tc", 2. * M * N * K)
         _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, passes, stream_ptr())
     else:
         _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr())
@@ -557,7 +574,7 @@ _CC_CACHE = {}
 
 # The strict UMNN forward keeps its hidden activations for the backward when they fit in this many bytes (else the
 # backward recomputes them, as UMNN does).  0 disables.
-SAVE_ACTIVATIONS_MAX_BYTES = 16 << 30
+SAVE_ACTIVATIONS_MAX_BYTES = 48 << 30
 
 
 # Engine of the strict UMNN integral: 'fused' = one FFMA kernel per direction (umnn.cu), 'layerwise' = per-layer passes
