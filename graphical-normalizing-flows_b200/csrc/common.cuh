@@ -7,7 +7,9 @@
 
 #ifdef GNF_EMU
 #include "cpu_emu.h"
+#define GNF_NOINLINE
 #else
+#define GNF_NOINLINE __noinline__
 #include <cuda_runtime.h>
 #define GNF_SMEM(T, name)                                              \
   extern __shared__ __align__(1024) unsigned char _gnf_smem_raw[];     \

@@ -37,8 +37,11 @@ __device__ __forceinline__ void gate_noise(const GateCtx& g, size_t idx, float& 
   }
 }
 
+// NOT inlined: the tile GEMM calls this once per element of its fully unrolled register tiles (32-64 call sites per
+// kernel); inlined, Philox + six transcendentals per site made the layer-1 kernels 0.2-0.4 MB of code and ncu showed
+// 23-53 % of their warp samples stalled on instruction fetch (stall_no_inst).
 template <bool kGrad>
-__device__ __forceinline__ float gate_e(const GateCtx& g, int b, int i, int j, float* de_dx, float* de_dP) {
+__device__ GNF_NOINLINE float gate_e(const GateCtx& g, int b, int i, int j, float* de_dx, float* de_dP) {
   const float p = __ldg(g.P + (size_t)i * g.d + j);
   const float xv = __ldg(g.x + (size_t)b * g.d + j);
   if (g.mode == GNF_GATE_TABLE) {

@@ -41,29 +41,29 @@ __global__ void lw_pad_weight_kernel(const float* __restrict__ W, int N, int K, 
 
 // a1[q][c] = relu(t_q * W0[c][0] + P[r][c]) for c < N1, 0 in the padding columns.  bits (nullable): ReLU mask of a1, one bit per
 // element, [Q][NP/32] words (8 consecutive lanes own one word: nibbles combined by shuffles).
-__global__ void __launch_bounds__(256) lw_layer1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ccn,
-                                                             const float* __restrict__ P, const float* __restrict__ W0, int ldw0,
-                                                             int N1, float* __restrict__ a1, uint32_t* __restrict__ bits, LwGeom g) {
-  GNF_SMEM(float, w1s);
-  for (int c = threadIdx.x; c < g.NP; c += blockDim.x) w1s[c] = c < N1 ? __ldg(W0 + (size_t)c * ldw0) : 0.f;
-  __syncthreads();
-  const int C4 = g.NP / 4;                               // multiple of 8: a warp covers whole 32-column words
-  const long long total = g.Q * C4;
-  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
-    const long long i = base + threadIdx.x;
-    const bool valid = i < total;
-    const long long q = valid ? i / C4 : 0;
-    const int c = valid ? (int)(i % C4) * 4 : 0;
+// Block = (NP/4) column quads x kLwRL row lanes: a thread's column quad is fixed, rows advance by a grid stride (the first
+// version decoded a flat 64-bit element index with two 64-bit divisions per float4: 43 us for an 89 MB plane).
+__global__ void lw_layer1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ccn, const float* __restrict__ P,
+                                     const float* __restrict__ W0, int ldw0, int N1, float* __restrict__ a1,
+                                     uint32_t* __restrict__ bits, LwGeom g) {
+  const int C4 = g.NP / 4;                               // multiple of 8: 8 consecutive lanes cover one 32-column word of one row
+  const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, c = 4 * c4;
+  float w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = (c + e < N1) ? __ldg(W0 + (size_t)(c + e) * ldw0) : 0.f;
+  const int Q = (int)g.Q;
+  for (int q0 = blockIdx.x * kLwRL; q0 < Q; q0 += gridDim.x * kLwRL) {   // uniform trip count per block: the shuffles below are warp-wide
+    const int q = q0 + rl;
+    const bool valid = q < Q;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-      const int r = (int)(q / g.nodes), kn = (int)(q % g.nodes);
+      const int r = q / g.nodes, kn = q - r * g.nodes;
       const float t = lw_node_abscissa(__ldg(x + r), ccn, kn, g.S);
       const float4 pv = __ldg(reinterpret_cast<const float4*>(P + (size_t)r * g.NP + c));
-      const float4 wv = *reinterpret_cast<const float4*>(w1s + c);
-      o.x = (c + 0 < N1) ? fmaxf(fmaf(t, wv.x, pv.x), 0.f) : 0.f;
-      o.y = (c + 1 < N1) ? fmaxf(fmaf(t, wv.y, pv.y), 0.f) : 0.f;
-      o.z = (c + 2 < N1) ? fmaxf(fmaf(t, wv.z, pv.z), 0.f) : 0.f;
-      o.w = (c + 3 < N1) ? fmaxf(fmaf(t, wv.w, pv.w), 0.f) : 0.f;
+      o.x = (c + 0 < N1) ? fmaxf(fmaf(t, w[0], pv.x), 0.f) : 0.f;
+      o.y = (c + 1 < N1) ? fmaxf(fmaf(t, w[1], pv.y), 0.f) : 0.f;
+      o.z = (c + 2 < N1) ? fmaxf(fmaf(t, w[2], pv.z), 0.f) : 0.f;
+      o.w = (c + 3 < N1) ? fmaxf(fmaf(t, w[3], pv.w), 0.f) : 0.f;
       *reinterpret_cast<float4*>(a1 + (size_t)q * g.NP + c) = o;
     }
     if (bits) {
@@ -77,21 +77,24 @@ __global__ void __launch_bounds__(256) lw_layer1_fwd_kernel(const float* __restr
 }
 
 // One warp per row r; 8 lanes per node-row (4 node-rows in flight per warp), float4 loads, shuffle reductions.
-__global__ void __launch_bounds__(256) lw_out_fwd_kernel(const float* __restrict__ aL, const float* __restrict__ wl, const float* __restrict__ bl,
-                                                          int NL, const float* __restrict__ x, const float* __restrict__ h,
-                                                          const float* __restrict__ ccw, float* __restrict__ z, float* __restrict__ zrev,
-                                                          float* __restrict__ jac, float* __restrict__ logdet, float* __restrict__ ysave,
-                                                          LwGeom g) {
+// J = NP / 32 float4 per lane and node-row (compile time: the first version kept 8 x 4 weight registers and 8 guarded
+// loads for any width -- 104 registers, 21 % occupancy, 61 us for an 89 MB plane).
+template <int J>
+__global__ void __launch_bounds__(256, 4) lw_out_fwd_kernel(const float* __restrict__ aL, const float* __restrict__ wl, const float* __restrict__ bl,
+                                                             int NL, const float* __restrict__ x, const float* __restrict__ h,
+                                                             const float* __restrict__ ccw, float* __restrict__ z, float* __restrict__ zrev,
+                                                             float* __restrict__ jac, float* __restrict__ logdet, float* __restrict__ ysave,
+                                                             LwGeom g) {
   const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
-  const int J = g.NP / 32;
-  float w[8][4];
+  float4 w[J];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = (j * 8 + sub) * 4 + e;
-      w[j][e] = (j < J && c < NL) ? __ldg(wl + c) : 0.f;
-    }
+  for (int j = 0; j < J; ++j) {
+    const int c = (j * 8 + sub) * 4;
+    w[j].x = (c + 0 < NL) ? __ldg(wl + c + 0) : 0.f;
+    w[j].y = (c + 1 < NL) ? __ldg(wl + c + 1) : 0.f;
+    w[j].z = (c + 2 < NL) ? __ldg(wl + c + 2) : 0.f;
+    w[j].w = (c + 3 < NL) ? __ldg(wl + c + 3) : 0.f;
+  }
   const float blast = __ldg(bl);
   const int wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < g.R; r += gridDim.x * wpb) {
@@ -101,20 +104,24 @@ __global__ void __launch_bounds__(256) lw_out_fwd_kernel(const float* __restrict
       const int kn = kn0 + grp;
       const bool valid = kn < g.nodes;
       const long long q = (long long)r * g.nodes + kn;
-      float acc = 0.f;
+      float4 v[J];
       if (valid) {
-        const float* row = aL + (size_t)q * g.NP;
+        const float4* row = reinterpret_cast<const float4*>(aL + (size_t)q * g.NP) + sub;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < J) {
-            const int c = (j * 8 + sub) * 4;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
-            if (c + 0 < NL) acc = fmaf(v.x, w[j][0], acc);
-            if (c + 1 < NL) acc = fmaf(v.y, w[j][1], acc);
-            if (c + 2 < NL) acc = fmaf(v.z, w[j][2], acc);
-            if (c + 3 < NL) acc = fmaf(v.w, w[j][3], acc);
-          }
-        }
+        for (int j = 0; j < J; ++j) v[j] = __ldg(row + 8 * j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // the FFMA engine leaves the padding columns of a plane unwritten: select, do not multiply by a zero weight
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c = (j * 8 + sub) * 4;
+        if (c + 0 < NL) acc = fmaf(v[j].x, w[j].x, acc);
+        if (c + 1 < NL) acc = fmaf(v[j].y, w[j].y, acc);
+        if (c + 2 < NL) acc = fmaf(v[j].z, w[j].z, acc);
+        if (c + 3 < NL) acc = fmaf(v[j].w, w[j].w, acc);
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -235,14 +242,24 @@ __global__ void lw_layer1_bwd_kernel(const float* __restrict__ d1, const float* 
   for (int r = r0; r < r1; ++r) {
     const float xv = __ldg(x + r);
     float Dp[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int kn = rl; kn < g.nodes; kn += kLwRL) {
-      const long long q = (long long)r * g.nodes + kn;
-      const float t = lw_node_abscissa(xv, ccn, kn, g.S);
-      const float4 dv = __ldg(reinterpret_cast<const float4*>(d1 + (size_t)q * g.NP + c));
-      const float v[4] = {c + 0 < N1 ? dv.x : 0.f, c + 1 < N1 ? dv.y : 0.f, c + 2 < N1 ? dv.z : 0.f, c + 3 < N1 ? dv.w : 0.f};
+    for (int kn0 = rl; kn0 < g.nodes; kn0 += 4 * kLwRL) {   // this row lane's node-rows, four loads in flight
+      float4 dv[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { Dp[e] += v[e]; sT[e] = fmaf(v[e], t, sT[e]); }
-      if (kn == g.S + 1) atomicAdd(dts, (v[0] * w[0] + v[1] * w[1]) + (v[2] * w[2] + v[3] * w[3]));
+      for (int u = 0; u < 4; ++u) {
+        const int kn = kn0 + u * kLwRL;
+        dv[u] = (kn < g.nodes) ? __ldg(reinterpret_cast<const float4*>(d1 + ((size_t)r * g.nodes + kn) * g.NP + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kn = kn0 + u * kLwRL;
+        if (kn < g.nodes) {
+          const float t = lw_node_abscissa(xv, ccn, kn, g.S);
+          const float v[4] = {c + 0 < N1 ? dv[u].x : 0.f, c + 1 < N1 ? dv[u].y : 0.f, c + 2 < N1 ? dv[u].z : 0.f, c + 3 < N1 ? dv[u].w : 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { Dp[e] += v[e]; sT[e] = fmaf(v[e], t, sT[e]); }
+          if (kn == g.S + 1) atomicAdd(dts, (v[0] * w[0] + v[1] * w[1]) + (v[2] * w[2] + v[3] * w[3]));
+        }
+      }
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) red[rl * g.NP + c + e] = Dp[e];
@@ -458,7 +475,7 @@ int gnf_umnn_fwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   const int WB = NP / 32;
   const size_t bplane = (size_t)pl.Q * WB;
   uint32_t* bits = (train && passes != 0 && L > 1) ? reinterpret_cast<uint32_t*>(saved + (size_t)L * plane + pl.Q) : nullptr;
-  GNF_LAUNCH(lw_layer1_fwd_kernel, lw_blocks(pl.Q * (NP / 4), 256 * 4, 8), 256, NP * sizeof(float), s, x, ccn, P, net->W[0], 1 + E,
+  GNF_LAUNCH(lw_layer1_fwd_kernel, lw_blocks(pl.Q, kLwRL * 4, 6), (NP / 4) * kLwRL, 0, s, x, ccn, P, net->W[0], 1 + E,
              net->dims[1], saved, bits, g);
   for (int l = 1; l < L; ++l) {
     uint32_t* bo = (bits && l + 1 < L) ? bits + (size_t)l * bplane : nullptr;     // mask of a_{l+1}
@@ -466,8 +483,13 @@ int gnf_umnn_fwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
                             (int)pl.Q, net->dims[l + 1], net->dims[l], 1, bo, WB, passes, use_rw ? NP : 0, s)) return e;
   }
   float* ysave = saved + (size_t)L * plane;
-  GNF_LAUNCH(lw_out_fwd_kernel, lw_blocks(R, 8, 8), 256, 0, s, saved + (size_t)(L - 1) * plane, net->W[L], net->b[L], net->dims[L], x, h,
-             ccw, z, zrev, jac, logdet, ysave, g);
+  {
+    const float* aLp = saved + (size_t)(L - 1) * plane;
+    const int nb = lw_blocks(R, 8, 8);
+#define LW_OUT_FWD(J) case J: GNF_LAUNCH(lw_out_fwd_kernel<J>, nb, 256, 0, s, aLp, net->W[L], net->b[L], net->dims[L], x, h, ccw, z, zrev, jac, logdet, ysave, g); break;
+    switch (NP / 32) { LW_OUT_FWD(1) LW_OUT_FWD(2) LW_OUT_FWD(3) LW_OUT_FWD(4) LW_OUT_FWD(5) LW_OUT_FWD(6) LW_OUT_FWD(7) default: LW_OUT_FWD(8) }
+#undef LW_OUT_FWD
+  }
   return check_launch("gnf_umnn_fwd_lw");
 }
 
@@ -517,7 +539,7 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   float* D = ws + pl.off_D;
   // db0 = colsum(D) comes out of the reduction kernel below (for L == 1 the output pass has already put colsum(delta_1) there)
   cudaMemsetAsync(grads->db[0], 0, (size_t)net->dims[1] * sizeof(float), s);
-  GNF_LAUNCH(lw_layer1_bwd_kernel, lw_blocks(R, 8, 2), red_threads, red_smem, s, dcur, x, ccn, net->W[0], 1 + E, net->dims[1], jac, gz,
+  GNF_LAUNCH(lw_layer1_bwd_kernel, lw_blocks(R, 4, 5), red_threads, red_smem, s, dcur, x, ccn, net->W[0], 1 + E, net->dims[1], jac, gz,
              gzrev, D, grads->dW[0], grads->db[0], dx, g);
   if (int e = gnf_linear_wgrad(D, NP, h, E, grads->dW[0] + 1, 1 + E, R, net->dims[1], E, stream)) return e;
   if (int e = gnf_linear_dgrad(D, NP, net->W[0] + 1, 1 + E, nullptr, 0, dh, E, R, net->dims[1], E, stream)) return e;
