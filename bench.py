@@ -280,11 +280,11 @@ def main():
         pass
 
     def train_step(x):
-        bucket.zero()
+        bucket.begin_step()
         z, jac = model(x)
         loss = model.loss(z, jac)
         loss.backward()
-        bucket.allreduce_mean()
+        bucket.finish_step()
         opt.step()
         return loss
 

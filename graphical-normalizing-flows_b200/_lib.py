@@ -97,6 +97,8 @@ _PROTOS = {
     "gnf_broadcast_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_counter_add": ([_P, C.c_uint64, _P], C.c_int),
     "gnf_axpy": ([_F, _P, _P, _SZ, _P], C.c_int),
+    "gnf_dag_loss_fwd": ([_P, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gnf_dag_loss_bwd": ([_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -138,6 +138,40 @@ static inline int flat_blocks(size_t n) {
   return b < 1 ? 1 : (int)b;
 }
 
+// DAGConditioner.loss (DAGConditioner.py:268-271) in one launch:
+//   out = dag_const * (lambd * t + c / 2 * t^2) + l1_weight * mean(|A|)        (t = power trace, all scalars on the device)
+// evaluated in fp32 in the reference's order, so that t^2 overflows to inf exactly where the reference does.
+__global__ void dag_loss_fwd_kernel(const float* __restrict__ A, int n, const float* __restrict__ t, const float* __restrict__ lambd,
+                                    const float* __restrict__ c, const float* __restrict__ dag_const, const float* __restrict__ l1w,
+                                    float* __restrict__ out) {
+  GNF_SMEM(float, red);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += fabsf(A[i]);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float tv = *t;
+    *out = *dag_const * (*lambd * tv + *c / 2.f * (tv * tv)) + *l1w * (red[0] / (float)n);
+  }
+}
+
+// dA[i] = g * l1_weight * sign(A[i]) / n;  dt = g * dag_const * (lambd + c * t)
+__global__ void dag_loss_bwd_kernel(const float* __restrict__ A, int n, const float* __restrict__ t, const float* __restrict__ lambd,
+                                    const float* __restrict__ c, const float* __restrict__ dag_const, const float* __restrict__ l1w,
+                                    const float* __restrict__ g, float* __restrict__ dA, float* __restrict__ dt) {
+  const float gv = *g;
+  const float k = gv * *l1w / (float)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float a = A[i];
+    dA[i] = a > 0.f ? k : (a < 0.f ? -k : 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *dt = gv * *dag_const * (*lambd + *c * *t);
+}
+
 }  // namespace gnf
 
 using namespace gnf;
@@ -199,6 +233,20 @@ int gnf_counter_add(uint64_t* counter, uint64_t inc, gnf_stream_t stream) {
   if (!counter) return fail(GNF_ERR_INVALID, "gnf_counter_add: bad arguments");
   GNF_LAUNCH(counter_add_kernel, 1, 32, 0, (cudaStream_t)stream, reinterpret_cast<unsigned long long*>(counter), (unsigned long long)inc);
   return check_launch("gnf_counter_add");
+}
+
+int gnf_dag_loss_fwd(const float* A, int d, const float* t, const float* lambd, const float* c, const float* dag_const,
+                     const float* l1_weight, float* out, gnf_stream_t stream) {
+  if (!A || !t || !lambd || !c || !dag_const || !l1_weight || !out || d <= 0) return fail(GNF_ERR_INVALID, "gnf_dag_loss_fwd: bad arguments");
+  GNF_LAUNCH(dag_loss_fwd_kernel, 1, 256, 256 * sizeof(float), (cudaStream_t)stream, A, d * d, t, lambd, c, dag_const, l1_weight, out);
+  return check_launch("gnf_dag_loss_fwd");
+}
+
+int gnf_dag_loss_bwd(const float* A, int d, const float* t, const float* lambd, const float* c, const float* dag_const,
+                     const float* l1_weight, const float* gout, float* dA, float* dt, gnf_stream_t stream) {
+  if (!A || !t || !lambd || !c || !dag_const || !l1_weight || !gout || !dA || !dt || d <= 0) return fail(GNF_ERR_INVALID, "gnf_dag_loss_bwd: bad arguments");
+  GNF_LAUNCH(dag_loss_bwd_kernel, flat_blocks((size_t)d * d), 256, 0, (cudaStream_t)stream, A, d * d, t, lambd, c, dag_const, l1_weight, gout, dA, dt);
+  return check_launch("gnf_dag_loss_bwd");
 }
 
 int gnf_axpy(float a, const float* x, float* y, size_t n, gnf_stream_t stream) {

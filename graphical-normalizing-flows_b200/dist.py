@@ -42,6 +42,33 @@ class GradBucket:
     def zero(self):
         self.flat.zero_()
 
+    # ---- step protocol without accumulation kernels -------------------------------------------------------------
+    # With p.grad aliasing the bucket, autograd ADDS every incoming gradient into it: one zero fill + one elementwise add per
+    # parameter tensor and step (16 launches, 2.5 % of the cfg4 step).  begin_step() drops the gradients instead, so that
+    # autograd simply adopts the tensors the backward kernels produced; finish_step() packs them into the flat bucket only
+    # when there is something to all-reduce (one multi-tensor copy), and leaves p.grad pointing at the averaged slices.
+    def begin_step(self):
+        for p in self.params:
+            p.grad = None
+
+    def finish_step(self):
+        if not is_dist():
+            return
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        views = self._views()
+        torch._foreach_copy_(views, grads)
+        self.allreduce_mean()
+        for p, v in zip(self.params, views):
+            p.grad = v
+
+    def _views(self):
+        out, off = [], 0
+        for p in self.params:
+            n = p.numel()
+            out.append(self.flat[off:off + n].view_as(p))
+            off += n
+        return out
+
     def check_aliasing(self):
         """True while every p.grad still lives inside the bucket (optimizers with set_to_none break it)."""
         lo = self.flat.data_ptr()

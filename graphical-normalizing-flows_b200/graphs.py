@@ -27,12 +27,12 @@ class GraphedTrainStep:
         def body():
             for cnt in self.counters:
                 ops.counter_add(cnt, 1)
-            bucket.zero()
+            bucket.begin_step()
             z, jac = model(self.static_x)
             loss = model.loss(z, jac)
             loss.backward()
             if allreduce:
-                bucket.allreduce_mean()
+                bucket.finish_step()
             optimizer.step()
             return loss.detach()
 

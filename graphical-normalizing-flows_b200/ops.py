@@ -204,6 +204,33 @@ class PowerTraceFn(torch.autograd.Function):
         return dA, None, None
 
 
+class DagLossFn(torch.autograd.Function):
+    """DAGConditioner.loss (DAGConditioner.py:268-271): dag_const*(lambd*t + c/2*t^2) + l1_weight*mean|A| in one launch
+    per direction (a dozen scalar torch kernels otherwise).  lambd / c / dag_const / l1_weight are the module's device
+    buffers; they receive no gradient (the reference's are buffers too)."""
+
+    @staticmethod
+    def forward(ctx, A, t, lambd, c, dag_const, l1_weight):
+        require(A, "A"), require(t, "t")
+        duals = [require(_contig(v.detach()), "dual variable") for v in (lambd, c, dag_const, l1_weight)]
+        out = torch.empty((), device=A.device, dtype=A.dtype)
+        _call("gnf_dag_loss_fwd", ptr(A), A.shape[0], ptr(t), *[ptr(v) for v in duals], ptr(out), stream_ptr())
+        _count()
+        ctx.save_for_backward(A, t, *duals)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        A, t, lambd, c, dag_const, l1_weight = ctx.saved_tensors
+        g = _contig(g)
+        dA = torch.empty_like(A)
+        dt = torch.empty_like(t)
+        _call("gnf_dag_loss_bwd", ptr(A), A.shape[0], ptr(t), ptr(lambd), ptr(c), ptr(dag_const), ptr(l1_weight), ptr(g), ptr(dA),
+              ptr(dt), stream_ptr())
+        _count()
+        return dA, dt, None, None, None, None
+
+
 # ----------------------------------------------------------------------------------------------
 # Conditioner MLP engine
 # ----------------------------------------------------------------------------------------------

@@ -242,6 +242,16 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
                     const float* saved, float* dx, float* dh, const gnf_mlp_grad_t* grads, int passes, int R, int d,
                     void* work, size_t work_bytes, gnf_stream_t stream);
 
+/* DAGConditioner.loss (DAGConditioner.py:268-271) fused:  out = dag_const*(lambd*t + c/2*t^2) + l1_weight*mean|A|, with the
+ * dual variables read from their device buffers (lambd, c, dag_const, l1_weight: one float each, as registered by the
+ * reference's constructor :86-91) and t = the power trace (gnf_power_trace_fwd).  fp32, reference evaluation order (t^2
+ * overflows to inf where the reference's does).  Backward: dA = g*l1_weight*sign(A)/d^2 (the l1 term only; the trace's own
+ * dependence on A flows through gnf_power_trace_bwd), dt = g*dag_const*(lambd + c*t). */
+int gnf_dag_loss_fwd(const float* A, int d, const float* t, const float* lambd, const float* c, const float* dag_const,
+                     const float* l1_weight, float* out, gnf_stream_t stream);
+int gnf_dag_loss_bwd(const float* A, int d, const float* t, const float* lambd, const float* c, const float* dag_const,
+                     const float* l1_weight, const float* gout, float* dA, float* dt, gnf_stream_t stream);
+
 /* Measurement switch: 0 routes the layer-wise engine's hidden GEMMs to the generic tensor-core engine (gnf_linear_*_tc)
  * instead of the resident-weight kernel below.  Default 1. */
 int gnf_umnn_lw_set_rw(int enable);

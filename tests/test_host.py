@@ -119,6 +119,14 @@ def _dp_worker(rank, world, port, emu_path, ret):
     z, jac = model(x_full)
     model.loss(z, jac).backward()
     err = float((flat_dp - bucket.flat).norm() / bucket.flat.norm())
+    # the accumulation-free step protocol (what bench.py / GraphedTrainStep use) must give the same averaged gradients
+    bucket.begin_step()
+    z, jac = model(x)
+    model.loss(z, jac).backward()
+    assert not bucket.check_aliasing()            # autograd adopted the backward kernels' tensors
+    bucket.finish_step()
+    assert bucket.check_aliasing()                # p.grad points at the all-reduced slices again
+    err = max(err, float((flat_dp - bucket.flat).norm() / flat_dp.norm()))
     sd = torch.cat([p.detach().flatten() for p in model.parameters()])
     gathered = [torch.zeros_like(sd) for _ in range(world)]
     dist.all_gather(gathered, sd)
