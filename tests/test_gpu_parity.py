@@ -305,3 +305,24 @@ def test_umnn_backward_saved_activations_equals_recompute():
     for k in grads[0]:
         err = float((grads[0][k] - grads[1][k]).norm() / grads[1][k].norm().clamp_min(1e-20))
         assert err < 1e-5, (k, err)
+
+
+def test_dag_loss_fused_matches_reference_formula():
+    """DAGConditioner.loss (DAGConditioner.py:268-271): fused kernel pair vs the reference's torch expression, values and
+    gradients, including a dual-variable state in the middle of training."""
+    torch.manual_seed(3)
+    d = 17
+    A = (torch.randn(d, d, device="cuda") * .7).requires_grad_(True)
+    t = torch.tensor(3.25, device="cuda", requires_grad=True)
+    for lambd, c, dag_const, l1 in ((0., 1e-3, 1., .1), (2.5, 10., 1., 0.), (1., 1., 0., .3)):
+        duals = [torch.tensor(v, device="cuda") for v in (lambd, c, dag_const, l1)]
+        out = G.ops.DagLossFn.apply(A, t, *duals)
+        gA, gt = torch.autograd.grad(out * 1.7, (A, t))
+        ref = duals[2] * (duals[0] * t + duals[1] / 2 * t ** 2) + duals[3] * A.abs().mean()
+        rA, rt = torch.autograd.grad(ref * 1.7, (A, t))
+        assert abs(float(out) - float(ref)) <= 1e-6 * max(1., abs(float(ref)))
+        assert float((gA - rA).abs().max()) <= 1e-7 and abs(float(gt - rt)) <= 1e-6 * max(1., abs(float(rt)))
+    # fp32 overflow of t^2 must survive (SURVEY Q16)
+    big = torch.tensor(3e20, device="cuda")
+    out = G.ops.DagLossFn.apply(A.detach(), big, *[torch.tensor(v, device="cuda") for v in (0., 1e-3, 1., 0.)])
+    assert torch.isinf(out)
