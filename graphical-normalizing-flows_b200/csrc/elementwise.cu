@@ -238,7 +238,8 @@ int gnf_counter_add(uint64_t* counter, uint64_t inc, gnf_stream_t stream) {
 int gnf_dag_loss_fwd(const float* A, int d, const float* t, const float* lambd, const float* c, const float* dag_const,
                      const float* l1_weight, float* out, gnf_stream_t stream) {
   if (!A || !t || !lambd || !c || !dag_const || !l1_weight || !out || d <= 0) return fail(GNF_ERR_INVALID, "gnf_dag_loss_fwd: bad arguments");
-  GNF_LAUNCH(dag_loss_fwd_kernel, 1, 256, 256 * sizeof(float), (cudaStream_t)stream, A, d * d, t, lambd, c, dag_const, l1_weight, out);
+  const int threads = d * d >= 16384 ? 1024 : 256;       // one block: the reduction is over d^2 <= 6e5 elements
+  GNF_LAUNCH(dag_loss_fwd_kernel, 1, threads, threads * sizeof(float), (cudaStream_t)stream, A, d * d, t, lambd, c, dag_const, l1_weight, out);
   return check_launch("gnf_dag_loss_fwd");
 }
 

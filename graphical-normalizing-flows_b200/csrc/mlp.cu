@@ -37,11 +37,41 @@ __device__ __forceinline__ void gate_noise(const GateCtx& g, size_t idx, float& 
   }
 }
 
-// NOT inlined: the tile GEMM calls this once per element of its fully unrolled register tiles (32-64 call sites per
-// kernel); inlined, Philox + six transcendentals per site made the layer-1 kernels 0.2-0.4 MB of code and ncu showed
-// 23-53 % of their warp samples stalled on instruction fetch (stall_no_inst).
-template <bool kGrad>
-__device__ GNF_NOINLINE float gate_e(const GateCtx& g, int b, int i, int j, float* de_dx, float* de_dP) {
+// The heavy part of the stochastic gate is NOT inlined: the tile GEMM evaluates the gate once per element of its fully
+// unrolled register tiles (32-64 call sites per kernel); inlined, Philox + six transcendentals per site made the layer-1
+// kernels 0.2-0.4 MB of code and ncu showed 23-53 % of their warp samples stalled on instruction fetch (stall_no_inst).
+// Everything goes in and out by value (registers): an out-of-line gate_e taking the context by reference and returning
+// through pointers cost 20 % at d = 784, where the gate math is the whole kernel.
+//   returns (G, dG/dp) of the relaxed Bernoulli gate, DAGConditioner.stochastic_gate (DAGConditioner.py:94-103)
+__device__ __forceinline__ float2 gumbel_gate_math_inl(float p, float na, float nb, float T) {
+  const float eps = 1e-6f;
+  const float g1 = -logf(-logf(na)), g2 = -logf(-logf(nb));
+  const float z1 = expf((logf(p + eps) + g1) / T);
+  const float z2 = expf((logf(1.f - p + eps) + g2) / T);
+  const float G = z1 / (z1 + z2);
+  return make_float2(G, (G * (1.f - G) / T) * (1.f / (p + eps) + 1.f / (1.f - p + eps)));
+}
+// same with the uniforms drawn in place (training path: no replayed noise)
+__device__ __forceinline__ float2 gumbel_gate_philox_inl(float p, float T, uint64_t seed, uint64_t idx, uint64_t offset) {
+  const uint4 r = Philox::gen(seed, idx, offset);
+  return gumbel_gate_math_inl(p, Philox::u01(r.x), Philox::u01(r.y), T);
+}
+__device__ GNF_NOINLINE float2 gumbel_gate_math(float p, float na, float nb, float T) { return gumbel_gate_math_inl(p, na, nb, T); }
+__device__ GNF_NOINLINE float2 gumbel_gate_philox(float p, float T, uint64_t seed, uint64_t idx, uint64_t offset) {
+  return gumbel_gate_philox_inl(p, T, seed, idx, offset);
+}
+
+// standard normal by Box-Muller (DAGConditioner.noiser_gate, DAGConditioner.py:114-116), out of line for the same reason
+__device__ GNF_NOINLINE float normal_philox(uint64_t seed, uint64_t idx, uint64_t offset) {
+  const uint4 r = Philox::gen(seed, idx, offset);
+  const float u = Philox::u01(r.x), v = Philox::u01(r.y);
+  return sqrtf(-2.f * logf(u)) * cosf(6.283185307179586f * v);
+}
+
+// kInl: inline the Gumbel math after all -- for wide flows (d >= 256: d^2 gate evaluations per sample) the gate math IS the
+// kernel and the call overhead costs 10-15 % (cfg5, d = 784), while the short-K kernels of narrow flows are fetch-bound.
+template <bool kGrad, bool kInl>
+__device__ __forceinline__ float gate_e(const GateCtx& g, int b, int i, int j, float* de_dx, float* de_dP) {
   const float p = __ldg(g.P + (size_t)i * g.d + j);
   const float xv = __ldg(g.x + (size_t)b * g.d + j);
   if (g.mode == GNF_GATE_TABLE) {
@@ -49,21 +79,19 @@ __device__ GNF_NOINLINE float gate_e(const GateCtx& g, int b, int i, int j, floa
     return xv * p;
   }
   const size_t idx = ((size_t)b * g.d + i) * g.d + j;
-  float na, nb;
-  gate_noise(g, idx, na, nb);
   if (g.mode == GNF_GATE_GUMBEL) {
-    const float eps = 1e-6f;
-    const float g1 = -logf(-logf(na)), g2 = -logf(-logf(nb));
-    const float z1 = expf((logf(p + eps) + g1) / g.T);
-    const float z2 = expf((logf(1.f - p + eps) + g2) / g.T);
-    const float G = z1 / (z1 + z2);
+    float2 G;
+    const uint64_t off = g.offset + (g.offset_dev ? *g.offset_dev : 0ull);
+    if (g.n1) G = kInl ? gumbel_gate_math_inl(p, __ldg(g.n1 + idx), __ldg(g.n2 + idx), g.T) : gumbel_gate_math(p, __ldg(g.n1 + idx), __ldg(g.n2 + idx), g.T);
+    else G = kInl ? gumbel_gate_philox_inl(p, g.T, g.seed, (uint64_t)idx, off) : gumbel_gate_philox(p, g.T, g.seed, (uint64_t)idx, off);
     if (kGrad) {
-      *de_dx = G;
-      *de_dP = xv * (G * (1.f - G) / g.T) * (1.f / (p + eps) + 1.f / (1.f - p + eps));
+      *de_dx = G.x;
+      *de_dP = xv * G.y;
     }
-    return xv * G;
+    return xv * G.x;
   }
   // noiser gate: e = P*(x + n*sqrt((1-P)^2))
+  const float na = g.n1 ? __ldg(g.n1 + idx) : normal_philox(g.seed, (uint64_t)idx, g.offset + (g.offset_dev ? *g.offset_dev : 0ull));
   const float a = fabsf(1.f - p);
   if (kGrad) {
     const float sgn = (1.f - p) > 0.f ? 1.f : ((1.f - p) < 0.f ? -1.f : 0.f);
@@ -73,16 +101,21 @@ __device__ GNF_NOINLINE float gate_e(const GateCtx& g, int b, int i, int j, floa
   return p * (xv + na * a);
 }
 
+constexpr int kGateInlineMinD = 256;
+
+template <bool kInl>
 struct LoadDagA {  // A(m,k) = e[b,i,j], m = b*d+i, k = j
   static constexpr bool kContigK = true;
   GateCtx g;
-  __device__ __forceinline__ float operator()(int m, int k) const { return gate_e<false>(g, m / g.d, m % g.d, k, nullptr, nullptr); }
+  __device__ __forceinline__ float operator()(int m, int k) const { return gate_e<false, kInl>(g, m / g.d, m % g.d, k, nullptr, nullptr); }
 };
+template <bool kInl>
 struct LoadDagB {  // B(k,n) = e[m=k, j=n]
   static constexpr bool kContigK = false;
   GateCtx g;
-  __device__ __forceinline__ float operator()(int k, int n) const { return gate_e<false>(g, k / g.d, k % g.d, n, nullptr, nullptr); }
+  __device__ __forceinline__ float operator()(int k, int n) const { return gate_e<false, kInl>(g, k / g.d, k % g.d, n, nullptr, nullptr); }
 };
+template <bool kInl>
 struct EpiDagDgrad {  // ebar[m,j] -> dx[b,j] += ebar*de/dx ; dP[i,j] += ebar*de/dP
   GateCtx g;
   float* dx;
@@ -91,7 +124,7 @@ struct EpiDagDgrad {  // ebar[m,j] -> dx[b,j] += ebar*de/dx ; dP[i,j] += ebar*de
     const int b = m / g.d, i = m % g.d;
     for (int jj = 0; jj < nv; ++jj) {
       float ddx, ddp;
-      gate_e<true>(g, b, i, n + jj, &ddx, &ddp);
+      gate_e<true, kInl>(g, b, i, n + jj, &ddx, &ddp);
       atomicAdd(dx + (size_t)b * g.d + n + jj, v[jj] * ddx);
       atomicAdd(dP + (size_t)i * g.d + n + jj, v[jj] * ddp);
     }
@@ -339,11 +372,11 @@ int gnf_dag_l1_fwd(const float* x, const float* P, const gnf_gate_t* gate, const
   if (int e = make_gate(&g, x, P, gate, d)) return e;
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  LoadDagA al{g};
   LoadWeightT bl{W1, ldw};
   EpiBiasAct epi{Y, ldy, T, N, bias_period < 1 ? 1 : bias_period, relu};
   const int M = B * d;
-  launch_gemm_auto(al, bl, epi, M, N, d, false, s);
+  if (d >= kGateInlineMinD) launch_gemm_auto(LoadDagA<true>{g}, bl, epi, M, N, d, false, s);
+  else launch_gemm_auto(LoadDagA<false>{g}, bl, epi, M, N, d, false, s);
   return check_launch("gnf_dag_l1_fwd");
 }
 
@@ -357,9 +390,9 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
   if (B == 0) return check_launch("gnf_dag_l1_wgrad");
   const int M = B * d;
   LoadColMajorA al{dY, lddy};   // A(n, m) = dY[m, n]
-  LoadDagB bl{g};               // B(m, j) = e[m, j]
   EpiAtomicAdd epi{dW1, ldw};
-  launch_gemm_auto(al, bl, epi, N, d, M, true, s);
+  if (d >= kGateInlineMinD) launch_gemm_auto(al, LoadDagB<true>{g}, epi, N, d, M, true, s);    // B(m, j) = e[m, j]
+  else launch_gemm_auto(al, LoadDagB<false>{g}, epi, N, d, M, true, s);
   return check_launch("gnf_dag_l1_wgrad");
 }
 
@@ -375,10 +408,10 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   const int M = B * d;
   LoadRowMajorA al{dY, lddy};   // A(m, n)
   LoadRowMajorB bl{W1, ldw};    // B(n, j) = W1[n, j]
-  EpiDagDgrad epi{g, dx, dP};
   // N = d <= 64 gives one column of tiles (50 CTAs at cfg4): split the reduction over the layer width.  The epilogue is
   // linear in the accumulator and already reduces with atomics, so partial sums need no second pass.
-  launch_gemm_auto(al, bl, epi, M, d, N, true, s);
+  if (d >= kGateInlineMinD) launch_gemm_auto(al, bl, EpiDagDgrad<true>{g, dx, dP}, M, d, N, true, s);
+  else launch_gemm_auto(al, bl, EpiDagDgrad<false>{g, dx, dP}, M, d, N, true, s);
   return check_launch("gnf_dag_l1_dgrad");
 }
 

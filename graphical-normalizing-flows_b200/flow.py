@@ -109,6 +109,9 @@ class FCNormalizingFlow(NormalizingFlow):
             self.steps.append(step)
 
     def forward(self, x, context=None):
+        if x.dim() == 2 and x.shape[0] == 0:
+            # empty batch: nothing to launch (the reference returns empty tensors too; keep the graph connected to x)
+            return x * 1., x.sum(1)
         jac_tot = 0.
         n = len(self.steps)
         z = None
@@ -122,6 +125,8 @@ class FCNormalizingFlow(NormalizingFlow):
     def compute_ll(self, x, context=None):
         """ll [B], z [B,d] — the closure of ToyExperiments.py:134-137 / UCIExperiments.py:159-160."""
         z, jac = self.forward(x, context)
+        if x.dim() == 2 and x.shape[0] == 0:
+            return jac, z
         if isinstance(self.z_log_density, NormalLogDensity):
             return ops.NormalLLFn.apply(z.contiguous(), jac.contiguous()), z
         return self.z_log_density(z) + jac, z

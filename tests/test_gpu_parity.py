@@ -326,3 +326,41 @@ def test_dag_loss_fused_matches_reference_formula():
     big = torch.tensor(3e20, device="cuda")
     out = G.ops.DagLossFn.apply(A.detach(), big, *[torch.tensor(v, device="cuda") for v in (0., 1e-3, 1., 0.)])
     assert torch.isinf(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Edge batches: single sample, ragged sizes around the 64 / 128-row tile boundaries, and the empty batch, through every
+# engine combination of the training path (fused FFMA, layer-wise with FFMA GEMMs, layer-wise with tensor-core GEMMs).
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def engines():
+    def set_(umnn, gemm):
+        G.ops.UMNN_ENGINE = umnn
+        G.ops.set_gemm_mode(gemm)
+    yield set_
+    G.ops.UMNN_ENGINE = "auto"
+    G.ops.set_gemm_mode("ffma")
+
+
+@pytest.mark.parametrize("umnn,gemm", [("fused", "ffma"), ("layerwise", "ffma"), ("layerwise", "tf32x3"), ("auto", "auto")])
+@pytest.mark.parametrize("cfg,B", [("cfg2", 1), ("cfg2", 22), ("cfg4", 1), ("cfg4", 3), ("cfg3", 7)])
+def test_edge_batches_vs_oracle(engines, umnn, gemm, cfg, B):
+    M = _mvo()
+    engines(umnn, gemm)
+    _check(M.compare(M.CONFIGS[cfg], B, "cuda", train=True))
+
+
+@pytest.mark.parametrize("umnn,gemm", [("fused", "ffma"), ("layerwise", "tf32x3")])
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
+def test_empty_batch(engines, umnn, gemm, cfg):
+    M = _mvo()
+    engines(umnn, gemm)
+    spec = M.CONFIGS[cfg]
+    model = M.build(spec, "cuda")
+    x = torch.empty(0, spec["d"], device="cuda")
+    z, jac = model(x)
+    assert z.shape == (0, spec["d"]) and jac.shape == (0,)
+    with torch.no_grad():
+        ll, _ = model.compute_ll(x)
+    assert ll.shape == (0,)
+    torch.cuda.synchronize()
