@@ -83,6 +83,9 @@ _PROTOS = {
                          _P, _SZ, _P], C.c_int),
     "gnf_umnn_lw_set_rw": ([_I], C.c_int),
     "gnf_linear_rw_workspace_bytes": ([_I, _I], _SZ),
+    "gnf_linear_wgrad_rw_workspace_bytes": ([_I, _I], _SZ),
+    "gnf_linear_wgrad_rw": ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
+    "gnf_linear_wgrad_rw_set_trace": ([_P], C.c_int),
     "gnf_linear_rw_set_trace": ([_P], C.c_int),
     "gnf_linear_rw_set_debug": ([_I], C.c_int),
     "gnf_linear_fwd_rw": ([_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),

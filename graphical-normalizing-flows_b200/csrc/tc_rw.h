@@ -29,5 +29,12 @@ void rw_pack_image(const float* W, long long ldw, int N, int K, int transpose, c
                    cudaStream_t s);
 int launch_rw_gemm(const RwGemmParams& p, cudaStream_t s);
 
+// tc_rw_wgrad.cu: dW[N x K] = dY^T X over Q rows (N, K <= 160; X a dense [Q][pad32(K)] plane), partial tiles in `partial`
+// (rw_wgrad_partial_floats(K) floats), summed by a second kernel.
+bool rw_wgrad_supported(int N, int K);
+size_t rw_wgrad_partial_floats(int K);
+int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long ldx, float* dW, long long lddw, int Q, int N, int K, int passes,
+                    float* partial, cudaStream_t s);
+
 }  // namespace gnf
 #endif

@@ -302,13 +302,14 @@ __global__ void lw_finish_dh_kernel(float* __restrict__ dh, int E, const float* 
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) dh[(size_t)r * E] += lw_gz_total(gz, gzrev, r, d);
 }
 
+static int g_lw_use_rw_wgrad = 1;   // measurement switch (gnf_umnn_lw_set_rw bit 1): 0 = wgrad on the generic tensor-core engine
 static int g_lw_use_rw = 1;   // measurement switch (gnf_umnn_lw_set_rw): 0 = hidden GEMMs on the generic tensor-core engine
 
 struct LwPlan {
   int L, NP, E, nodes;
   int rw;          // hidden layers fit the resident-weight tensor-core kernel (tc_rw.cu)
   long long Q;
-  size_t off_P, off_Wp[GNF_MAX_LAYERS], off_dA, off_dB, off_D, total;  // workspace offsets in floats
+  size_t off_P, off_Wp[GNF_MAX_LAYERS], off_dA, off_dB, off_D, off_part, total;  // workspace offsets in floats
 };
 
 static int lw_plan(const gnf_mlp_t* net, int R, int S, int train, int backward, LwPlan* pl) {
@@ -340,9 +341,13 @@ static int lw_plan(const gnf_mlp_t* net, int R, int S, int train, int backward, 
   // per hidden layer: the zero-padded weight copy (generic engines) or the hi/lo TF32 images + bias (resident-weight kernel)
   for (int l = 1; l < L; ++l) { pl->off_Wp[l] = off; off += (size_t)2 * pl->NP * pl->NP + pl->NP; }
   pl->off_dA = pl->off_dB = 0;
+  pl->off_part = 0;
   if (backward) {
     pl->off_dA = off; off += plane;
     pl->off_dB = off; off += plane;
+#ifndef GNF_EMU
+    if (pl->rw) { pl->off_part = off; off += rw_wgrad_partial_floats(pl->NP); }   // per-CTA partial tiles of the wgrad kernel
+#endif
   }
   pl->total = off;
   return 0;
@@ -405,8 +410,14 @@ static int lw_dgrad_gemm(const float* dY, int lddy, const float* W, int ldw, con
 #endif
 }
 static int lw_wgrad_gemm(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K, int passes,
-                         cudaStream_t s) {
+                         float* rw_partial, cudaStream_t s) {
   if (passes == 0) return gnf_linear_wgrad(dY, lddy, X, ldx, dW, lddw, M, N, K, (gnf_stream_t)s);
+#ifndef GNF_EMU
+  if (rw_partial) {                                      // lane = output row: dY^T goes to TMEM untransposed (tc_rw_wgrad.cu)
+    if (int e = launch_rw_wgrad(dY, lddy, X, ldx, dW, lddw, M, N, K, passes, rw_partial, s)) return e;
+    return check_launch("gnf_umnn_bwd_lw (resident wgrad)");
+  }
+#endif
   return gnf_linear_wgrad_tc(dY, lddy, X, ldx, dW, lddw, M, N, K, passes, (gnf_stream_t)s);
 }
 
@@ -433,7 +444,8 @@ using namespace gnf;
 extern "C" {
 
 int gnf_umnn_lw_set_rw(int enable) {
-  g_lw_use_rw = enable != 0;
+  g_lw_use_rw = (enable & 1) != 0;
+  g_lw_use_rw_wgrad = (enable & 1) != 0 && (enable & 2) == 0;      // 1: everything resident; 3: forward/dgrad only; 0: generic engine
   return 0;
 }
 
@@ -527,7 +539,8 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   // hidden layers, top down: dW_l = delta_{l+1}^T a_l;  delta_l = (delta_{l+1} W_l) o relu'(a_l);  db_{l-1} = colsum delta_l
   for (int l = L - 1; l >= 1; --l) {
     const float* a_l = saved + (size_t)(l - 1) * plane;
-    if (int e = lw_wgrad_gemm(dcur, NP, a_l, NP, grads->dW[l], net->dims[l], (int)pl.Q, net->dims[l + 1], net->dims[l], passes, s)) return e;
+    if (int e = lw_wgrad_gemm(dcur, NP, a_l, NP, grads->dW[l], net->dims[l], (int)pl.Q, net->dims[l + 1], net->dims[l], passes,
+                              (use_rw && g_lw_use_rw_wgrad) ? ws + pl.off_part : nullptr, s)) return e;
     const uint32_t* mb = passes != 0 ? reinterpret_cast<const uint32_t*>(saved + (size_t)L * plane + pl.Q) + (size_t)(l - 1) * pl.Q * (NP / 32) : nullptr;
     if (int e = lw_dgrad_gemm(dcur, NP, ws + pl.off_Wp[l], NP, a_l, NP, mb, NP / 32, dnxt, NP, (int)pl.Q, net->dims[l + 1], net->dims[l], passes, use_rw ? NP : 0, s)) return e;
     if (l > 1) {

@@ -812,6 +812,23 @@ def linear_dgrad_rw(dY, W, act=None, mask_bits=None, passes=3):
     return dX
 
 
+def linear_wgrad_rw(dY, X, N, K, passes=3):
+    """dW [N, K] = dY[:, :N]^T @ X[:, :K] on the resident wgrad kernel (tc_rw_wgrad.cu).  X: dense [M, pad32(K)]."""
+    require(dY, "dY"), require(X, "X")
+    M = dY.shape[0]
+    if X.shape[1] != _pad32(K) or X.shape[0] != M:
+        raise ValueError(f"X must be [M, pad32(K) = {_pad32(K)}]")
+    nbytes = lib().gnf_linear_wgrad_rw_workspace_bytes(N, K)
+    if nbytes == 0:
+        raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
+    ws = torch.empty(nbytes // 4, device=dY.device, dtype=torch.float32)
+    dW = torch.empty(N, K, device=dY.device, dtype=torch.float32)
+    _call("gnf_linear_wgrad_rw", ptr(dY), dY.stride(0), ptr(X), X.stride(0), ptr(dW), K, M, N, K, int(passes), ptr(ws), nbytes,
+          stream_ptr())
+    _count(2)
+    return dW
+
+
 def counter_add(counter, inc=1):
     """*counter += inc on the device (int64 tensor with one element)."""
     _call("gnf_counter_add", ptr(counter), int(inc), stream_ptr())

@@ -253,7 +253,7 @@ int gnf_dag_loss_bwd(const float* A, int d, const float* t, const float* lambd, 
                      const float* l1_weight, const float* gout, float* dA, float* dt, gnf_stream_t stream);
 
 /* Measurement switch: 0 routes the layer-wise engine's hidden GEMMs to the generic tensor-core engine (gnf_linear_*_tc)
- * instead of the resident-weight kernel below.  Default 1. */
+ * instead of the resident-weight kernels below; 3 keeps forward/dgrad resident but runs wgrad on the generic engine.  Default 1. */
 int gnf_umnn_lw_set_rw(int enable);
 
 /* Resident-weight tensor-core layer GEMM (tc_rw.cu) -- the hidden x hidden layers of IntegrandNet
@@ -275,6 +275,17 @@ int gnf_linear_fwd_rw(const float* X, int ldx, const float* W, int ldw, const fl
 int gnf_linear_dgrad_rw(const float* dY, int lddy, const float* W, int ldw, const float* act, int ldact,
                         const uint32_t* mask_bits, float* dX, int lddx, int M, int N, int K, int passes, void* work,
                         size_t work_bytes, gnf_stream_t stream);
+
+/* Weight gradient of a narrow layer over all node-rows (tc_rw_wgrad.cu): dW[N,K] = dY^T X, N, K <= 160, M rows.  TMEM lane =
+ * output row, so dY^T is gathered straight from the row-major dY (a warp reads dY[q, n0..n0+31]); X must be a dense
+ * [M][round_up(K,32)] plane (ldx = round_up(K,32), 16-byte aligned) and is streamed once by bulk async copies; per-CTA partial
+ * tiles in `work` (gnf_linear_wgrad_rw_workspace_bytes(N, K)) are summed by a second kernel (deterministic). */
+size_t gnf_linear_wgrad_rw_workspace_bytes(int N, int K);
+/* Measurement: later gnf_linear_wgrad_rw launches write SM-clock stamps of CTA 0 into buf (3 x 256 int64, device; rows: MMA
+ * issuer, first stager thread, first loader thread).  NULL disables. */
+int gnf_linear_wgrad_rw_set_trace(long long* buf);
+int gnf_linear_wgrad_rw(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
+                        int passes, void* work, size_t work_bytes, gnf_stream_t stream);
 
 /* Measurement tool (not on the product path): TMEM-read bandwidth / MMA issue rate / overlap probe on one CTA.
  * mode bit0: stream tcgen05.ld; bit1: issue TF32 MMAs; out[0], out[1]: elapsed SM clocks of the two roles. */

@@ -41,3 +41,15 @@ for (M, N, K) in [(138600, 150, 150), (258300, 150, 150), (1419264, 150, 150), (
         c = t(lambda: G.ops.linear_dgrad_rw(dY, W, act=X, passes=passes))
         row += f"  passes={passes}: fwd {a*1e3:.0f}us {fl/a/1e9:.0f}TF {M*(NP+KP)*4/a/1e6:.0f}GB/s  dgrad(act mask) {c*1e3:.0f}us {fl/c/1e9:.0f}TF |"
     print(row)
+
+print("resident wgrad kernel (tc_rw_wgrad.cu)")
+for (M, N, K) in [(138600, 150, 150), (1419264, 150, 150), (150000, 100, 100)]:
+    NPn, KP = (N + 31) // 32 * 32, (K + 31) // 32 * 32
+    X = torch.zeros(M, KP, device="cuda"); X[:, :K] = torch.randn(M, K, device="cuda")
+    dY = torch.zeros(M, NPn, device="cuda"); dY[:, :N] = torch.randn(M, N, device="cuda")
+    fl = 2. * M * N * K
+    row = f"M={M} N={N} K={K}:"
+    for passes in (1, 3):
+        a = t(lambda: G.ops.linear_wgrad_rw(dY, X, N, K, passes=passes))
+        row += f"  passes={passes}: wgrad {a*1e3:.0f}us {fl/a/1e9:.0f}TF {M*(NPn+KP)*4/a/1e6:.0f}GB/s |"
+    print(row)
