@@ -56,6 +56,9 @@ _PROTOS = {
     "gnf_linear_fwd_tc": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_dgrad_tc": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_wgrad_tc": ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "gnf_split_tf32": ([_P, _I, _P, _P, _I, _I, _I, _P], C.c_int),
+    "gnf_linear_fwd_tc_ps": ([_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "gnf_linear_dgrad_tc_ps": ([_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_colsum": ([_P, _I, _P, _I, _I, _I, _P], C.c_int),
     "gnf_relu_mask": ([_P, _I, _P, _I, _I, _I, _P], C.c_int),
     "gnf_pack_rows": ([_P, _P, _P, _P, _I, _I, _P], C.c_int),

@@ -173,11 +173,12 @@ __device__ __forceinline__ void trace_stamp(long long* trace, int role, long lon
 }
 
 __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, int vecA, int vecB, const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB) {
+                                                               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo) {
   using namespace tc;
   GNF_SMEM(char, smem);
   const int BN = p.BN;
   const bool split = p.passes == 3;
+  const bool presplit = split && p.B_lo != nullptr;      // B arrives as separate hi / lo tiles (only with TMA)
   const uint32_t a_bytes = kGemmBM * 128u, b_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = (a_bytes + b_bytes) * (split ? 2u : 1u);
   // stage layout: [A_hi][B_hi]([A_lo][B_lo]); then the epilogue transpose blocks; then the barriers
@@ -223,9 +224,14 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
             else for (int sl = 0; sl < kGemmBM / 32; ++sl) tma_load_2d(st + sl * 4096, &tmA, tm * kGemmBM + 32 * sl, k0, &landed[s]);
             trace_stamp(p.trace, 0, it);
           } else {
-            mbar_expect_tx(&landed[s], b_bytes);
+            mbar_expect_tx(&landed[s], presplit ? 2u * b_bytes : b_bytes);
             if (p.b_src == TCG_SRC_K) tma_load_2d(st + a_bytes, &tmB, k0, tn * BN, &landed[s]);
             else for (int sl = 0; sl < BN / 32; ++sl) tma_load_2d(st + a_bytes + sl * 4096, &tmB, tn * BN + 32 * sl, k0, &landed[s]);
+            if (presplit) {                                // the lo tile goes straight to its slot: [A_hi][B_hi][A_lo][B_lo]
+              char* lo = st + 2 * a_bytes + b_bytes;
+              if (p.b_src == TCG_SRC_K) tma_load_2d(lo, &tmBlo, k0, tn * BN, &landed[s]);
+              else for (int sl = 0; sl < BN / 32; ++sl) tma_load_2d(lo + sl * 4096, &tmBlo, tn * BN + 32 * sl, k0, &landed[s]);
+            }
           }
         }
       }
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
       char* st = smem + (size_t)s * stage_bytes;
       if (split) {
         fill_dispatch<true>(vecA, st, st + a_bytes + b_bytes, nullptr, 0, p.a_src, 0, 0, 0, 0, kGemmBM, ptid);
-        fill_dispatch<true>(vecB, st + a_bytes, st + 2 * a_bytes + b_bytes, nullptr, 0, p.b_src, 0, 0, 0, 0, BN, ptid);
+        if (!presplit) fill_dispatch<true>(vecB, st + a_bytes, st + 2 * a_bytes + b_bytes, nullptr, 0, p.b_src, 0, 0, 0, 0, BN, ptid);
       }
       fence_async_smem();
       __syncwarp();
@@ -592,6 +598,18 @@ static long long* g_tc_gemm_trace = nullptr;
 static int g_tc_gemm_fold = 2;      // k-chunks accumulated inside the tensor core before a round-to-nearest fold (3xTF32)
 static bool g_tc_gemm_tma = true;   // measurement switch (gnf_tc_gemm_set_tma): 0 forces the cp.async staging path
 
+// hi = rn_tf32(W), lo = rn_tf32(W - hi), both [N][ld] with zero padding columns (ld >= K)
+__global__ void split_tf32_kernel(const float* __restrict__ W, long long ldw, float* __restrict__ hi, float* __restrict__ lo, int ld, int N, int K) {
+  const long long total = (long long)N * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ld), k = (int)(i - (long long)n * ld);
+    const float v = k < K ? W[n * ldw + k] : 0.f;
+    const float h = rn_tf32(v);
+    hi[i] = h;
+    lo[i] = rn_tf32(v - h);
+  }
+}
+
 int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return 0;
   if (p.passes != 1 && p.passes != 3) return fail(GNF_ERR_INVALID, "tensor-core GEMM: passes must be 1 or 3");
@@ -622,18 +640,22 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   p.c_vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc % 4) == 0) ? 1 : 0;
   p.act_vec = (p.act && (reinterpret_cast<uintptr_t>(p.act) & 15) == 0 && (p.ldact % 4) == 0) ? 1 : 0;
   p.bias_vec = (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (p.bias_ld % 4) == 0) ? 1 : 0;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBlo;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
+  memset(&tmBlo, 0, sizeof(tmBlo));
   p.use_tma = (g_tc_gemm_tma && make_operand_map(&tmA, p.A, p.lda, p.a_src, p.M, p.K, kGemmBM) &&
                make_operand_map(&tmB, p.B, p.ldb, p.b_src, p.N, p.K, p.BN)) ? 1 : 0;
+  if (p.passes != 3) p.B_lo = nullptr;
+  if (p.B_lo && !(p.use_tma && make_operand_map(&tmBlo, p.B_lo, p.ldb, p.b_src, p.N, p.K, p.BN)))
+    return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM: pre-split weights need TMA-loadable operands (16-byte aligned rows)");
   p.trace = g_tc_gemm_trace;
   const long long total = (long long)tiles * p.splits;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget); attr = true; }
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB);
+  GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB, tmBlo);
   return 0;
 }
 
@@ -672,6 +694,50 @@ int gnf_linear_dgrad_tc(const float* dY, int lddy, const float* W, int ldw, cons
   p.epi = TCG_EPI_MASK; p.C = dX; p.ldc = lddx; p.act = act; p.ldact = ldact;
   if (int e = launch_tc_gemm(p, (cudaStream_t)stream)) return e;
   return check_launch("gnf_linear_dgrad_tc");
+#endif
+}
+
+int gnf_split_tf32(const float* W, int ldw, float* hi, float* lo, int ld, int N, int K, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!W || !hi || !lo || N <= 0 || K <= 0 || ldw < K || ld < K) return fail(GNF_ERR_INVALID, "gnf_split_tf32: bad arguments");
+  long long blocks = ((long long)N * ld + 255) / 256;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  GNF_LAUNCH(split_tf32_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, W, (long long)ldw, hi, lo, ld, N, K);
+  return check_launch("gnf_split_tf32");
+#endif
+}
+
+int gnf_linear_fwd_tc_ps(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw, const float* bias, int bias_period, float* Y,
+                         int ldy, int M, int N, int K, int relu, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!X || !W_hi || !W_lo || !Y || M < 0 || N <= 0 || K <= 0 || ldx < K || ldw < K || ldy < N) return fail(GNF_ERR_INVALID, "gnf_linear_fwd_tc_ps: bad arguments");
+  TcGemmParams p = {};
+  p.A = X; p.lda = ldx; p.a_src = TCG_SRC_K;
+  p.B = W_hi; p.B_lo = W_lo; p.ldb = ldw; p.b_src = TCG_SRC_K;
+  p.M = M; p.N = N; p.K = K; p.passes = 3;
+  p.epi = TCG_EPI_BIAS_ACT; p.C = Y; p.ldc = ldy; p.bias = bias; p.bias_ld = N; p.bias_period = bias_period < 1 ? 1 : bias_period; p.relu = relu;
+  if (int e = launch_tc_gemm(p, (cudaStream_t)stream)) return e;
+  return check_launch("gnf_linear_fwd_tc_ps");
+#endif
+}
+
+int gnf_linear_dgrad_tc_ps(const float* dY, int lddy, const float* W_hi, const float* W_lo, int ldw, const float* act, int ldact, float* dX,
+                           int lddx, int M, int N, int K, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!dY || !W_hi || !W_lo || !dX || M < 0 || N <= 0 || K <= 0 || lddy < N || ldw < K || lddx < K) return fail(GNF_ERR_INVALID, "gnf_linear_dgrad_tc_ps: bad arguments");
+  TcGemmParams p = {};
+  p.A = dY; p.lda = lddy; p.a_src = TCG_SRC_K;
+  p.B = W_hi; p.B_lo = W_lo; p.ldb = ldw; p.b_src = TCG_SRC_MN;
+  p.M = M; p.N = K; p.K = N; p.passes = 3;
+  p.epi = TCG_EPI_MASK; p.C = dX; p.ldc = lddx; p.act = act; p.ldact = ldact;
+  if (int e = launch_tc_gemm(p, (cudaStream_t)stream)) return e;
+  return check_launch("gnf_linear_dgrad_tc_ps");
 #endif
 }
 

@@ -12,6 +12,8 @@ struct TcGemmParams {
   // C[m, n] = sum_k A(m, k) * B(n, k);  A: Mrows x Kred,  B: Ncols x Kred
   const float* A; long long lda; int a_src;    // TCG_SRC_K: A(m,k) = A[m*lda + k];  TCG_SRC_MN: A(m,k) = A[k*lda + m]
   const float* B; long long ldb; int b_src;    // same convention with n in place of m
+  const float* B_lo;                           // 3xTF32 only, nullable: B is already rn_tf32(b) and B_lo = rn_tf32(b - B) (same layout):
+                                               // both are TMA-loaded and the stagers skip the B split (weights: split once per call)
   int M, N, K;
   int BN, stages, passes, splits, k_per_split;
   int fold, acc_stride;                        // k-chunks per in-core accumulation group; TMEM columns between accumulator regions

@@ -54,6 +54,9 @@ def _note_flops(name, flops):
         _FLOPS.setdefault(name, []).append(float(flops))
 
 
+_TIMES_ALIAS = {}    # entry point -> the name its timings are filed under (flavours of one kernel)
+
+
 def _call(name, *args):
     fn = getattr(lib(), name)
     if _TIMING and not L._SIMULATOR:
@@ -61,7 +64,7 @@ def _call(name, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        _TIMES.setdefault(name, []).append((e0, e1))
+        _TIMES.setdefault(_TIMES_ALIAS.get(name, name), []).append((e0, e1))
     else:
         rc = fn(*args)
     check(rc)
@@ -294,6 +297,23 @@ def _tma_weight(W):
     return Wp
 
 
+PRESPLIT_WEIGHTS = True      # 3xTF32: split the weights once per call (gnf_split_tf32) instead of per tile in shared memory
+
+
+def _split_weight(W):
+    """(W_hi, W_lo) with rows padded to 4 floats, for the *_tc_ps entry points."""
+    N, K = W.shape
+    hi = torch.empty(N, _pad4(K), device=W.device, dtype=W.dtype)
+    lo = torch.empty_like(hi)
+    _call("gnf_split_tf32", ptr(W), W.stride(0), ptr(hi), ptr(lo), hi.stride(0), N, K, stream_ptr())
+    _count()
+    return hi, lo
+
+
+def _tma_ok(t, ld):
+    return t.data_ptr() % 16 == 0 and ld % 4 == 0
+
+
 def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=None):
     """Y = act(X[:, :K] @ W^T + bias).  X may be a row-strided view described by (ldx, K)."""
     M = X.shape[0]
@@ -304,7 +324,13 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
         out = _rows(M, N, X)
         ldy = out.stride(0)
     passes = _gemm_passes(M, N, K)
-    if passes:
+    if passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(X, ldx) and K == W.shape[1]:
+        hi, lo = _split_weight(W)
+        _note_flops("gnf_linear_fwd_tc", 2. * M * N * K)
+        _TIMES_ALIAS["gnf_linear_fwd_tc_ps"] = "gnf_linear_fwd_tc"
+        _call("gnf_linear_fwd_tc_ps", ptr(X), ldx, ptr(hi), ptr(lo), hi.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K,
+              int(relu), stream_ptr())
+    elif passes:
         W = _tma_weight(W)
         _note_flops("gnf_linear_fwd_tc", 2. * M * N * K)
         _call("gnf_linear_fwd_tc", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
@@ -322,7 +348,13 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
         out = _rows(M, K, dY)
         lddx = out.stride(0)
     passes = _gemm_passes(M, N, K)
-    if passes:
+    if passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(dY, lddy):
+        hi, lo = _split_weight(W)
+        _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K)
+        _TIMES_ALIAS["gnf_linear_dgrad_tc_ps"] = "gnf_linear_dgrad_tc"
+        _call("gnf_linear_dgrad_tc_ps", ptr(dY), lddy, ptr(hi), ptr(lo), hi.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
+              ptr(out), lddx, M, N, K, stream_ptr())
+    elif passes:
         W = _tma_weight(W)
         _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K)
         _call("gnf_linear_dgrad_tc", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),

@@ -109,6 +109,15 @@ int gnf_linear_dgrad_tc(const float* dY, int lddy, const float* W, int ldw, cons
                         int lddx, int M, int N, int K, int passes, gnf_stream_t stream);
 int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
                         int passes, gnf_stream_t stream);
+/* 3xTF32 with the weights split ONCE per call instead of per tile in shared memory: gnf_split_tf32 writes W_hi = rn_tf32(W) and
+ * W_lo = rn_tf32(W - W_hi) as [N][ld] (ld a multiple of 4 floats, 16-byte aligned: both are TMA-loaded); the _ps flavours of
+ * forward / dgrad take the pair.  The in-kernel split is bound by shared-memory bandwidth: dropping the weight
+ * half of it shortens the k-chunk cadence. */
+int gnf_split_tf32(const float* W, int ldw, float* W_hi, float* W_lo, int ld, int N, int K, gnf_stream_t stream);
+int gnf_linear_fwd_tc_ps(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw, const float* bias, int bias_period,
+                         float* Y, int ldy, int M, int N, int K, int relu, gnf_stream_t stream);
+int gnf_linear_dgrad_tc_ps(const float* dY, int lddy, const float* W_hi, const float* W_lo, int ldw, const float* act, int ldact,
+                           float* dX, int lddx, int M, int N, int K, gnf_stream_t stream);
 /* Measurement switch: 0 makes the tensor-core GEMM stage every operand with cp.async (the path taken anyway by operands
  * whose base / leading dimension are not 16-byte aligned) instead of TMA tensor maps.  Default 1. */
 int gnf_tc_gemm_set_tma(int enable);
