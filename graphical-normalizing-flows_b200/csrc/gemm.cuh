@@ -28,6 +28,8 @@ struct TileCfg {
 using TileBig = TileCfg<128, 128, 16, 8, 8>;   // 256 threads, 8x8 per thread
 using TileMid = TileCfg<128, 64, 16, 8, 4>;    // 256 threads, 8x4 per thread (32 < N <= 64)
 using TileSkinny = TileCfg<128, 32, 16, 4, 4>; // 256 threads, 4x4 per thread (N <= 32)
+using TileTiny = TileCfg<32, 32, 64, 4, 4>;    // 64 threads, 64-deep k tiles (the loop is one global round trip per k tile): N <= 32 and too few 128-row tiles to fill the GPU (the 630 -> 30 output layer)
+using TileShort = TileCfg<32, 128, 16, 4, 8>;  // 128 threads: M <= 32 with a wide output (the output layer's wgrad: 30 x 630)
 
 template <class Cfg, class ALoad, class BLoad, class Epi>
 __global__ void __launch_bounds__(Cfg::THREADS) gemm_kernel(ALoad al, BLoad bl, Epi epi, int M, int N, int K, int k_per_split) {
@@ -224,7 +226,9 @@ static inline void launch_gemm_auto(const ALoad& al, const BLoad& bl, const Epi&
     if (want > maxs) want = maxs;
     return want < 1 ? 1 : want;
   };
-  if (N <= 32) launch_gemm<TileSkinny>(al, bl, epi, M, N, K, splits(128, 32), stream);
+  if (N <= 32 && !split_k && ceil_div(M, 128) < kNumSMs) launch_gemm<TileTiny>(al, bl, epi, M, N, K, 1, stream);
+  else if (N <= 32) launch_gemm<TileSkinny>(al, bl, epi, M, N, K, splits(128, 32), stream);
+  else if (M <= 32 && N > 64) launch_gemm<TileShort>(al, bl, epi, M, N, K, splits(32, 128), stream);
   else if (N <= 64) launch_gemm<TileMid>(al, bl, epi, M, N, K, splits(128, 64), stream);
   else launch_gemm<TileBig>(al, bl, epi, M, N, K, splits(128, 128), stream);
 }

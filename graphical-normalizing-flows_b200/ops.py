@@ -7,6 +7,7 @@ allocations handed to the library as raw device pointers on torch's current stre
 """
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -300,13 +301,25 @@ def _tma_weight(W):
 PRESPLIT_WEIGHTS = True      # 3xTF32: split the weights once per call (gnf_split_tf32) instead of per tile in shared memory
 
 
+_SPLIT_CACHE = {}
+
+
 def _split_weight(W):
-    """(W_hi, W_lo) with rows padded to 4 floats, for the *_tc_ps entry points."""
+    """(W_hi, W_lo) with rows padded to 4 floats, for the *_tc_ps entry points.  The forward's split is reused by the same
+    step's dgrad: keyed by storage and version (optimizers update in place, which bumps the version), and by the stream
+    capture state so that a captured step never refers to tensors made outside its graph."""
+    key = (W.data_ptr(), W._version, tuple(W.shape), torch.cuda.is_current_stream_capturing() if W.is_cuda else False)
+    hit = _SPLIT_CACHE.get(key)
+    if hit is not None and hit[2]() is W:
+        return hit[0], hit[1]
     N, K = W.shape
     hi = torch.empty(N, _pad4(K), device=W.device, dtype=W.dtype)
     lo = torch.empty_like(hi)
     _call("gnf_split_tf32", ptr(W), W.stride(0), ptr(hi), ptr(lo), hi.stride(0), N, K, stream_ptr())
     _count()
+    if len(_SPLIT_CACHE) >= 16:
+        _SPLIT_CACHE.clear()
+    _SPLIT_CACHE[key] = (hi, lo, weakref.ref(W))
     return hi, lo
 
 
@@ -423,6 +436,7 @@ class MlpFn(torch.autograd.Function):
         weights = [require(_contig(p), "weight") for p in params[0::2]]
         biases = [require(_contig(p), "bias") for p in params[1::2]]
         n = len(weights)
+        _SPLIT_CACHE.clear()     # weight splits live from a forward to its own backward only
         if weights[0].shape[1] != K0 or x.shape[1] < K0:
             raise ValueError(f"MLP: first layer expects {weights[0].shape[1]} inputs, got {K0} (x has {x.shape[1]} columns)")
         acts = []
@@ -557,6 +571,7 @@ class DagMlpFn(torch.autograd.Function):
         biases = [require(_contig(p), "bias") for p in params[1::2]]
         B, d = x.shape
         n = len(weights)
+        _SPLIT_CACHE.clear()     # weight splits live from a forward to its own backward only
         if weights[0].shape[1] != (2 * d if hot else d):
             raise ValueError(f"DAGConditioner: first layer expects {weights[0].shape[1]} inputs, d={d}, hot_encoding={hot}")
         for t in (gate.noise or ()):
