@@ -180,12 +180,24 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
     // the thread's share (coalesced view) of one 32-column chunk: 8 x 16 bytes, rows 4i + sub.  Exactly one load group
     // is outstanding per thread (its next chunk); memory parallelism comes from the eight loader warps.
     float4 buf[8];
-    auto issue = [&](long long tl, int c) {                  // (tl, c) past the end: zeros
-      const long long row0 = ((long long)blockIdx.x + tl * gridDim.x) * kRwRows + quarter * 32 + sub;
-      const float* src = p.A + row0 * p.lda + c * 32 + 4 * piece;
+    // Unconditional loads from clamped coordinates: a conditional around an inline-asm load is a branch per load (measured in
+    // the wgrad loader: 100 clocks per load to issue).  Rows past M and prefetches past the end read valid memory whose
+    // values are never used: rows >= M are never stored by the epilogue.
+    auto issue = [&](long long tl, int c) {
+      if (p.debug & 2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        buf[i] = (tl < n_local && c < NCH && row0 + 4 * i < p.M && !(p.debug & 2)) ? rw_ldg16(src + (long long)(4 * i) * p.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+      }
+      const long long tlc = tl < n_local ? tl : n_local - 1;
+      const int cc = c < NCH ? c : NCH - 1;
+      const long long row0 = ((long long)blockIdx.x + tlc * gridDim.x) * kRwRows + quarter * 32 + sub;
+      const float* src = p.A + cc * 32 + 4 * piece;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long r = (row0 + 4 * i < p.M) ? row0 + 4 * i : (long long)p.M - 1;
+        buf[i] = rw_ldg16(src + r * p.lda);
+      }
     };
     issue(0, half);
     for (long long tl = 0; tl < n_local; ++tl)
