@@ -86,15 +86,43 @@ def umnn_kernel_flops(spec, S, rows, backward):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region: NVML in-process every 5 ms (nvidia-smi, one
+    process spawn per sample, gets a single sample into a 50 ms region), nvidia-smi as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _reasons_nvml(self):
+        n = self.nvml
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        return [("Active" if mask & bits[k] else "Not Active") for k in self.NAMES]
 
     def _run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    sm = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    self.samples.append([str(sm), str(self.max_sm)] + self._reasons_nvml())
+                    time.sleep(0.005)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -112,19 +140,18 @@ class ClockSampler:
         if self.thread:
             self.thread.join(timeout=6)
         sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             try:
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[2:6]):
+                for n, v in zip(self.NAMES, s[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -414,7 +441,8 @@ def main():
                                               -c["ms_per_step"])):
             ach = c["flops_per_launch"] / (c["avg_launch_ms"] / 1e3) / 1e12
             obj = {"bound": "tensor", "kernel": c["kernel"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                   "traffic": traffic_table.get(f"{c['kernel']}@{cfg}"), "avg_launch_ms": c["avg_launch_ms"],
+                   "traffic": traffic_table.get(f"{c['kernel']}.{mode}@{cfg}", traffic_table.get(f"{c['kernel']}@{cfg}")),
+                   "avg_launch_ms": c["avg_launch_ms"],
                    "flops_per_launch": c["flops_per_launch"], "launches_per_step": c["launches_per_step"], "peak_source": peak_src,
                    "note": c["note"], "share_of_step": c["ms_per_step"] / step_ms, "timed_entry_points": c["entries"]}
             if roofline is None:
