@@ -57,6 +57,7 @@ _PROTOS = {
     "gnf_linear_dgrad_tc": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_wgrad_tc": ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_split_tf32": ([_P, _I, _P, _P, _I, _I, _I, _P], C.c_int),
+    "gnf_linear_tc_ps2": ([_I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_fwd_tc_ps": ([_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_dgrad_tc_ps": ([_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_colsum": ([_P, _I, _P, _I, _I, _I, _P], C.c_int),

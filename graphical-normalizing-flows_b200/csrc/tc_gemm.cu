@@ -173,12 +173,14 @@ __device__ __forceinline__ void trace_stamp(long long* trace, int role, long lon
 }
 
 __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, int vecA, int vecB, const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo) {
+                                                               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                                                               const __grid_constant__ CUtensorMap tmAlo) {
   using namespace tc;
   GNF_SMEM(char, smem);
   const int BN = p.BN;
   const bool split = p.passes == 3;
   const bool presplit = split && p.B_lo != nullptr;      // B arrives as separate hi / lo tiles (only with TMA)
+  const bool presplitA = presplit && p.A_lo != nullptr;  // so does A: nothing left to split, the MMA warp consumes the landed tiles
   const uint32_t a_bytes = kGemmBM * 128u, b_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = (a_bytes + b_bytes) * (split ? 2u : 1u);
   // stage layout: [A_hi][B_hi]([A_lo][B_lo]); then the epilogue transpose blocks; then the barriers
@@ -219,9 +221,14 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
           mbar_wait(&empty[s], (uint32_t)(((it / p.stages) & 1) ^ 1));
           char* st = smem + (size_t)s * stage_bytes;
           if (isA) {
-            mbar_expect_tx(&landed[s], a_bytes);
+            mbar_expect_tx(&landed[s], presplitA ? 2u * a_bytes : a_bytes);
             if (p.a_src == TCG_SRC_K) tma_load_2d(st, &tmA, k0, tm * kGemmBM, &landed[s]);
             else for (int sl = 0; sl < kGemmBM / 32; ++sl) tma_load_2d(st + sl * 4096, &tmA, tm * kGemmBM + 32 * sl, k0, &landed[s]);
+            if (presplitA) {
+              char* lo = st + a_bytes + b_bytes;
+              if (p.a_src == TCG_SRC_K) tma_load_2d(lo, &tmAlo, k0, tm * kGemmBM, &landed[s]);
+              else for (int sl = 0; sl < kGemmBM / 32; ++sl) tma_load_2d(lo + sl * 4096, &tmAlo, tm * kGemmBM + 32 * sl, k0, &landed[s]);
+            }
             trace_stamp(p.trace, 0, it);
           } else {
             mbar_expect_tx(&landed[s], presplit ? 2u * b_bytes : b_bytes);
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
       if (lane == 0) mbar_arrive(&full[s]);
     };
     if (p.use_tma) {
-      if (split) {                                       // single-pass TF32: the MMA warp consumes the landed tiles directly
+      if (split && !presplitA) {                         // single-pass TF32 / fully pre-split: the MMA warp consumes the landed tiles directly
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
           const int sp = (int)(w / ((long long)tiles_m * tiles_n));
           const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
       // per k-step (8 k) descriptor advance: K-major: 32 bytes inside the swizzle atom; MN-major: 8 tile rows = 1024 bytes
       const uint32_t a_step = (p.a_src == TCG_SRC_K) ? 2u : 64u, b_step = (p.b_src == TCG_SRC_K) ? 2u : 64u;
       const bool a_mn = p.a_src == TCG_SRC_MN, b_mn = p.b_src == TCG_SRC_MN;
-      uint64_t* ready = (p.use_tma && !split) ? landed : full;
+      uint64_t* ready = (p.use_tma && (!split || presplitA)) ? landed : full;
       long long it = 0;
       int gcount = 0;                                    // accumulator groups issued so far (buffer = gcount & 1)
       for (long long w = blockIdx.x; w < total; w += gridDim.x) {
@@ -640,22 +647,26 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   p.c_vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc % 4) == 0) ? 1 : 0;
   p.act_vec = (p.act && (reinterpret_cast<uintptr_t>(p.act) & 15) == 0 && (p.ldact % 4) == 0) ? 1 : 0;
   p.bias_vec = (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (p.bias_ld % 4) == 0) ? 1 : 0;
-  CUtensorMap tmA, tmB, tmBlo;
+  CUtensorMap tmA, tmB, tmBlo, tmAlo;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
   memset(&tmBlo, 0, sizeof(tmBlo));
+  memset(&tmAlo, 0, sizeof(tmAlo));
   p.use_tma = (g_tc_gemm_tma && make_operand_map(&tmA, p.A, p.lda, p.a_src, p.M, p.K, kGemmBM) &&
                make_operand_map(&tmB, p.B, p.ldb, p.b_src, p.N, p.K, p.BN)) ? 1 : 0;
   if (p.passes != 3) p.B_lo = nullptr;
   if (p.B_lo && !(p.use_tma && make_operand_map(&tmBlo, p.B_lo, p.ldb, p.b_src, p.N, p.K, p.BN)))
     return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM: pre-split weights need TMA-loadable operands (16-byte aligned rows)");
+  if (!p.B_lo) p.A_lo = nullptr;
+  if (p.A_lo && !make_operand_map(&tmAlo, p.A_lo, p.lda, p.a_src, p.M, p.K, kGemmBM))
+    return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM: pre-split activations need TMA-loadable operands (16-byte aligned rows)");
   p.trace = g_tc_gemm_trace;
   const long long total = (long long)tiles * p.splits;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget); attr = true; }
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB, tmBlo);
+  GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB, tmBlo, tmAlo);
   return 0;
 }
 
@@ -738,6 +749,39 @@ int gnf_linear_dgrad_tc_ps(const float* dY, int lddy, const float* W_hi, const f
   p.epi = TCG_EPI_MASK; p.C = dX; p.ldc = lddx; p.act = act; p.ldact = ldact;
   if (int e = launch_tc_gemm(p, (cudaStream_t)stream)) return e;
   return check_launch("gnf_linear_dgrad_tc_ps");
+#endif
+}
+
+int gnf_linear_tc_ps2(int op, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, const float* bias,
+                      int bias_period, const float* act, int ldact, float* C, int ldc, int M, int N, int K, int relu, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!A_hi || !A_lo || !B_hi || !B_lo || !C || M < 0 || N <= 0 || K <= 0 || op < 0 || op > 2) return fail(GNF_ERR_INVALID, "gnf_linear_tc_ps2: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  TcGemmParams p = {};
+  p.passes = 3;
+  if (op == 0) {            // forward: Y[M,N] = act(X[M,K] W[N,K]^T + b);  A = X, B = W
+    p.A = A_hi; p.A_lo = A_lo; p.lda = lda; p.a_src = TCG_SRC_K;
+    p.B = B_hi; p.B_lo = B_lo; p.ldb = ldb; p.b_src = TCG_SRC_K;
+    p.M = M; p.N = N; p.K = K;
+    p.epi = TCG_EPI_BIAS_ACT; p.C = C; p.ldc = ldc; p.bias = bias; p.bias_ld = N; p.bias_period = bias_period < 1 ? 1 : bias_period; p.relu = relu;
+  } else if (op == 1) {     // dgrad: dX[M,K] = (dY[M,N] W[N,K]) o relu'(act);  A = dY, B = W (MN-major)
+    p.A = A_hi; p.A_lo = A_lo; p.lda = lda; p.a_src = TCG_SRC_K;
+    p.B = B_hi; p.B_lo = B_lo; p.ldb = ldb; p.b_src = TCG_SRC_MN;
+    p.M = M; p.N = K; p.K = N;
+    p.epi = TCG_EPI_MASK; p.C = C; p.ldc = ldc; p.act = act; p.ldact = ldact;
+  } else {                  // wgrad: dW[N,K] = dY[M,N]^T X[M,K];  A = dY (MN-major), B = X (MN-major), split-K atomics into zeroed dW
+    if (ldc == K) cudaMemsetAsync(C, 0, (size_t)N * K * sizeof(float), s);
+    else for (int n = 0; n < N; ++n) cudaMemsetAsync(C + (size_t)n * ldc, 0, (size_t)K * sizeof(float), s);
+    if (M == 0) return check_launch("gnf_linear_tc_ps2");
+    p.A = A_hi; p.A_lo = A_lo; p.lda = lda; p.a_src = TCG_SRC_MN;
+    p.B = B_hi; p.B_lo = B_lo; p.ldb = ldb; p.b_src = TCG_SRC_MN;
+    p.M = N; p.N = K; p.K = M;
+    p.epi = TCG_EPI_ATOMIC; p.C = C; p.ldc = ldc;
+  }
+  if (int e = launch_tc_gemm(p, s)) return e;
+  return check_launch("gnf_linear_tc_ps2");
 #endif
 }
 

@@ -327,8 +327,34 @@ def _tma_ok(t, ld):
     return t.data_ptr() % 16 == 0 and ld % 4 == 0
 
 
-def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=None):
-    """Y = act(X[:, :K] @ W^T + bias).  X may be a row-strided view described by (ldx, K)."""
+# ... and optionally the activation operands too (one elementwise pass each, shared by the GEMMs that read them).  Measured on
+# cfg4 (profiles/r01zq): with nothing left to split in shared memory the k-chunk cadence does not move (72 us forward either way) --
+# four TMA tiles per chunk (72 KB) put the kernel on the L2 -> SM bandwidth instead (29 B/clk/SM = 8.4 TB/s over the chip) -- and
+# only wgrad gains (98 -> 77 us), which the two extra passes eat.  Off by default; kept (and tested) for multicast clusters.
+PRESPLIT_ACTS = False
+PRESPLIT_ACTS_MIN_K = 256    # short reductions do not amortise the extra pass
+
+
+def _split_mat(X, M, K, ldx):
+    """TF32 (hi, lo) copies of the [M, K] matrix at X (row stride ldx), rows padded to 4 floats."""
+    hi = torch.empty(M, _pad4(K), device=X.device, dtype=X.dtype)
+    lo = torch.empty_like(hi)
+    _call("gnf_split_tf32", ptr(X), ldx, ptr(hi), ptr(lo), hi.stride(0), M, K, stream_ptr())
+    _count()
+    return hi, lo
+
+
+def _ps2(op, A, B, ldab, bias, bias_period, act, C, ldc, M, N, K, relu, name):
+    """gnf_linear_tc_ps2 with both operands pre-split; A, B = (hi, lo) pairs."""
+    _note_flops(name, 2. * M * N * K)
+    _TIMES_ALIAS["gnf_linear_tc_ps2"] = name
+    _call("gnf_linear_tc_ps2", op, ptr(A[0]), ptr(A[1]), ldab[0], ptr(B[0]), ptr(B[1]), ldab[1], ptr(bias), bias_period,
+          ptr(act), (act.stride(0) if act is not None else 0), ptr(C), ldc, M, N, K, int(relu), stream_ptr())
+
+
+def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=None, x_split=None, want_split=False):
+    """Y = act(X[:, :K] @ W^T + bias).  X may be a row-strided view described by (ldx, K).
+    x_split: (hi, lo) of X if the caller has them; want_split: also return the pair this call used (or None)."""
     M = X.shape[0]
     N = W.shape[0]
     K = W.shape[1] if K is None else K
@@ -337,7 +363,12 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
         out = _rows(M, N, X)
         ldy = out.stride(0)
     passes = _gemm_passes(M, N, K)
-    if passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(X, ldx) and K == W.shape[1]:
+    used = None
+    if passes == 3 and PRESPLIT_WEIGHTS and PRESPLIT_ACTS and K == W.shape[1] and K >= PRESPLIT_ACTS_MIN_K and M > 0:
+        used = x_split if x_split is not None else _split_mat(X, M, K, ldx)
+        wh, wl = _split_weight(W)
+        _ps2(0, used, (wh, wl), (used[0].stride(0), wh.stride(0)), bias, bias_period, None, out, ldy, M, N, K, relu, "gnf_linear_fwd_tc")
+    elif passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(X, ldx) and K == W.shape[1]:
         hi, lo = _split_weight(W)
         _note_flops("gnf_linear_fwd_tc", 2. * M * N * K)
         _TIMES_ALIAS["gnf_linear_fwd_tc_ps"] = "gnf_linear_fwd_tc"
@@ -352,16 +383,19 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
         _call("gnf_linear_fwd", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
               stream_ptr())
     _count()
-    return out
+    return (out, used) if want_split else out
 
 
-def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
+def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None, dy_split=None):
     N, K = W.shape
     if out is None:
         out = _rows(M, K, dY)
         lddx = out.stride(0)
     passes = _gemm_passes(M, N, K)
-    if passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(dY, lddy):
+    if passes == 3 and PRESPLIT_WEIGHTS and PRESPLIT_ACTS and dy_split is not None:
+        wh, wl = _split_weight(W)
+        _ps2(1, dy_split, (wh, wl), (dy_split[0].stride(0), wh.stride(0)), None, 1, act, out, lddx, M, N, K, 0, "gnf_linear_dgrad_tc")
+    elif passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(dY, lddy):
         hi, lo = _split_weight(W)
         _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K)
         _TIMES_ALIAS["gnf_linear_dgrad_tc_ps"] = "gnf_linear_dgrad_tc"
@@ -379,10 +413,12 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None):
     return out
 
 
-def linear_wgrad(dY, lddy, X, ldx, M, N, K):
+def linear_wgrad(dY, lddy, X, ldx, M, N, K, dy_split=None, x_split=None):
     dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
     passes = _gemm_passes(M, N, K, "wgrad")
-    if passes:
+    if passes == 3 and PRESPLIT_ACTS and dy_split is not None and x_split is not None:
+        _ps2(2, dy_split, x_split, (dy_split[0].stride(0), x_split[0].stride(0)), None, 1, None, dW, K, M, N, K, 0, "gnf_linear_wgrad_tc")
+    elif passes:
         _note_flops("gnf_linear_wgrad_tc", 2. * M * N * K)
         _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, passes, stream_ptr())
     else:
@@ -398,7 +434,7 @@ def colsum(Y, ldy, M, N, period=1):
     return out
 
 
-def _mlp_backward(gout, ldg, acts, x_in, ldx, K0, weights, need_dx, first_layer_done=False):
+def _mlp_backward(gout, ldg, acts, x_in, ldx, K0, weights, need_dx, first_layer_done=False, act_splits=None):
     """Shared backward of a Linear/ReLU stack.
 
     gout: cotangent of the last layer's (un-activated) output [M, N_last] with row stride ldg.
@@ -416,8 +452,16 @@ def _mlp_backward(gout, ldg, acts, x_in, ldx, K0, weights, need_dx, first_layer_
         dbs[l] = colsum(delta, ldd, M, N).view(N)
         if l > 0:
             a_prev = acts[l - 1]
-            dWs[l] = linear_wgrad(delta, ldd, a_prev, a_prev.stride(0), M, N, K)
-            delta = linear_dgrad(delta, ldd, W, a_prev, M)
+            # the cotangent is read by this layer's wgrad and dgrad: split it once for both (when they run pre-split at all)
+            xs = act_splits[l] if act_splits is not None else None
+            ds = None
+            if (PRESPLIT_ACTS and PRESPLIT_WEIGHTS and M > 0 and min(N, K) >= PRESPLIT_ACTS_MIN_K and _gemm_passes(M, N, K) == 3
+                    and _gemm_passes(M, N, K, "wgrad") == 3):
+                ds = _split_mat(delta, M, N, ldd)
+                if xs is None:
+                    xs = _split_mat(a_prev, M, K, a_prev.stride(0))
+            dWs[l] = linear_wgrad(delta, ldd, a_prev, a_prev.stride(0), M, N, K, dy_split=ds, x_split=xs if ds is not None else None)
+            delta = linear_dgrad(delta, ldd, W, a_prev, M, dy_split=ds)
             ldd = delta.stride(0)
         else:
             dWs[0] = linear_wgrad(delta, ldd, x_in, ldx, M, N, K0)
@@ -591,13 +635,15 @@ class DagMlpFn(torch.autograd.Function):
                                    ptr(y), y.stride(0), B, d, N1, int(n > 1), st)
         _count(3)
         acts = []
+        splits = [None] * n       # splits[l] = TF32 (hi, lo) of layer l's input, when its forward GEMM ran pre-split: reused by its wgrad
         cur = y
         for l in range(1, n):
             acts.append(cur)
             out = None
             if l == n - 1:   # final layer writes straight into the [B, d, H] result (no view of an internal tensor)
                 out = torch.empty(B, d, weights[l].shape[0], device=x.device, dtype=x.dtype)
-            cur = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), out=out, ldy=weights[l].shape[0])
+            cur, splits[l] = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), out=out, ldy=weights[l].shape[0], want_split=True)
+        ctx.act_splits = splits if any(ctx.needs_input_grad) else None
         ctx.save_for_backward(x, A, P, dPdA, *weights, *acts)
         ctx.gate, ctx.hot, ctx.n = gate, hot, n
         if n == 1:
@@ -615,7 +661,9 @@ class DagMlpFn(torch.autograd.Function):
         M = B * d
         gh = _contig(gh).view(M, -1)
         st = stream_ptr()
-        dWs, dbs, _, delta = _mlp_backward(gh, gh.stride(0), acts, None, 0, 0, weights, False, first_layer_done=True)
+        dWs, dbs, _, delta = _mlp_backward(gh, gh.stride(0), acts, None, 0, 0, weights, False, first_layer_done=True,
+                                           act_splits=ctx.act_splits)
+        ctx.act_splits = None
         W1 = weights[0]
         N1 = W1.shape[0]
         g = gate.c_struct()

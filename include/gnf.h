@@ -118,6 +118,13 @@ int gnf_linear_fwd_tc_ps(const float* X, int ldx, const float* W_hi, const float
                          float* Y, int ldy, int M, int N, int K, int relu, gnf_stream_t stream);
 int gnf_linear_dgrad_tc_ps(const float* dY, int lddy, const float* W_hi, const float* W_lo, int ldw, const float* act, int ldact,
                            float* dX, int lddx, int M, int N, int K, gnf_stream_t stream);
+/* Both operands pre-split (gnf_split_tf32 on the activations as well: one 10-us elementwise pass per 16 MB operand, reused by the
+ * GEMMs that consume it): nothing is split in shared memory, the MMA warp consumes the TMA tiles as they land.
+ * op 0 = forward (A = X [M,K], B = W [N,K], bias / relu), 1 = dgrad (A = dY [M,N], B = W [N,K], act = ReLU mask source, C = dX),
+ * 2 = wgrad (A = dY [M,N], B = X [M,K], C = dW [N,K]).  lda / ldb are the row strides of the hi AND lo arrays. */
+int gnf_linear_tc_ps2(int op, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
+                      const float* bias, int bias_period, const float* act, int ldact, float* C, int ldc, int M, int N, int K,
+                      int relu, gnf_stream_t stream);
 /* Measurement switch: 0 makes the tensor-core GEMM stage every operand with cp.async (the path taken anyway by operands
  * whose base / leading dimension are not 16-byte aligned) instead of TMA tensor maps.  Default 1. */
 int gnf_tc_gemm_set_tma(int enable);
