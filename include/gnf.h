@@ -109,7 +109,8 @@ int gnf_linear_dgrad_tc(const float* dY, int lddy, const float* W, int ldw, cons
                         int lddx, int M, int N, int K, int passes, gnf_stream_t stream);
 int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
                         int passes, gnf_stream_t stream);
-/* 3xTF32 with the weights split ONCE per call instead of per tile in shared memory: gnf_split_tf32 writes W_hi = rn_tf32(W) and
+/* DAGMLP / MADE / CouplingMLP hidden layers (DAGConditioner.py:7-20, AutoregressiveConditioner.py:24-25, CouplingConditioner.py:6-18)
+ * in 3xTF32 with the weights split ONCE per call instead of per tile in shared memory: gnf_split_tf32 writes W_hi = rn_tf32(W) and
  * W_lo = rn_tf32(W - W_hi) as [N][ld] (ld a multiple of 4 floats, 16-byte aligned: both are TMA-loaded); the _ps flavours of
  * forward / dgrad take the pair.  The in-kernel split is bound by shared-memory bandwidth: dropping the weight
  * half of it shortens the k-chunk cadence. */
@@ -292,7 +293,9 @@ int gnf_linear_dgrad_rw(const float* dY, int lddy, const float* W, int ldw, cons
                         const uint32_t* mask_bits, float* dX, int lddx, int M, int N, int K, int passes, void* work,
                         size_t work_bytes, gnf_stream_t stream);
 
-/* Weight gradient of a narrow layer over all node-rows (tc_rw_wgrad.cu): dW[N,K] = dY^T X, N, K <= 160, M rows.  TMEM lane =
+/* Weight gradient of an IntegrandNet hidden layer (MonotonicNormalizer.py:12-38) over all quadrature node-rows -- the parameter
+ * gradient UMNN's NeuralIntegral.backward accumulates node by node -- (tc_rw_wgrad.cu): dW[N,K] = dY^T X,
+ * N, K <= 160, M rows.  TMEM lane =
  * output row, so dY^T is gathered straight from the row-major dY (a warp reads dY[q, n0..n0+31]); X must be a dense
  * [M][round_up(K,32)] plane (ldx = round_up(K,32), 16-byte aligned) and is streamed once by bulk async copies; per-CTA partial
  * tiles in `work` (gnf_linear_wgrad_rw_workspace_bytes(N, K)) are summed by a second kernel (deterministic). */
