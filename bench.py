@@ -351,8 +351,11 @@ def main():
             eager_kflops = G.ops.collect_call_flops()
             G.ops.enable_kernel_timing(False)
             eager_launches = (G.ops.launch_count() - l0) // n_eager
-            graphed = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=True, warmup=3)
-            step = graphed
+            if mode == "train":
+                step = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=True, warmup=3)
+            else:
+                graphed_eval = G.GraphedEvalStep(model, pool[0], warmup=3)
+                step = lambda x: graphed_eval(x)[0].mean()
             for i in range(3):
                 step(pool[i % n_pool])
             barrier()
@@ -461,10 +464,11 @@ def main():
 
     config["gemm_engine"] = args.gemm
     config["umnn_engine"] = args.umnn_engine
-    use_graph = args.mode == "train" and args.cuda_graph in ("on", "auto")
+    use_graph_any = args.cuda_graph in ("on", "auto")
+    use_graph = use_graph_any
     config["cuda_graph"] = use_graph
     opt_kwargs = dict(lr=lr, weight_decay=wd, fused=True, capturable=True) if use_graph else None
-    if use_graph:
+    if use_graph and args.mode == "train":
         opt = torch.optim.Adam(model.parameters(), **opt_kwargs)
     main_res = measure(args.mode, args.precision, args.gemm, S, args.steps, args.warmup, True, use_graph)
     extra = None
@@ -472,12 +476,12 @@ def main():
         # the metric's second half: log-likelihood evaluation (UCIExperiments.py:152-162: S = nb_steps + 20), in the
         # fast mode (tensor-core UMNN forward + TF32 conditioner GEMMs, ll tolerance 2e-3)
         try:
-            extra = measure("eval", "tf32", "auto-fast", S + 20, args.steps, 3, False)
+            extra = measure("eval", "tf32", "auto-fast", S + 20, args.steps, 3, False, use_graph_any)
         except RuntimeError as err:      # e.g. integrand weights too large to stay resident in shared memory
             if "umnn tc" not in str(err):
                 raise
             G.ops.enable_kernel_timing(False)
-            extra = measure("eval", "strict", "auto-fast", S + 20, args.steps, 3, False)
+            extra = measure("eval", "strict", "auto-fast", S + 20, args.steps, 3, False, use_graph_any)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -499,7 +503,7 @@ def main():
                                            "strict fp32 UMNN forward (integrand too wide for the resident-weight tensor-core kernel) + "
                                            "single-pass TF32 conditioner GEMMs"),
                         **{k: extra[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "roofline", "achieved_tflops_step",
-                                                 "algorithmic_gflop_per_step", "nb_steps", "kernel_ms")}}
+                                                 "algorithmic_gflop_per_step", "nb_steps", "kernel_ms", "cuda_graph")}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

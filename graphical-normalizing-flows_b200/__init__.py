@@ -12,12 +12,12 @@ from .flow import (FCNormalizingFlow, MNIST_A_prior, NormalLogDensity, Normalizi
                    buildFCNormalizingFlow)
 from .normalizers import AffineNormalizer, ELUPlus, IntegrandNet, MonotonicNormalizer, Normalizer
 from . import dist
-from .graphs import GraphedTrainStep
+from .graphs import GraphedEvalStep, GraphedTrainStep
 from .configs import CONFIGS, build_from_spec
 
 __all__ = [
     "AutoregressiveConditioner", "Conditioner", "ConditionnalMADE", "CouplingConditioner", "CouplingMLP", "DAGConditioner",
     "DAGMLP", "MADE", "MaskedLinear", "FCNormalizingFlow", "MNIST_A_prior", "NormalLogDensity", "NormalizingFlow",
     "NormalizingFlowStep", "buildFCNormalizingFlow", "AffineNormalizer", "ELUPlus", "IntegrandNet", "MonotonicNormalizer",
-    "Normalizer", "ops", "dist", "CONFIGS", "build_from_spec", "GraphedTrainStep",
+    "Normalizer", "ops", "dist", "CONFIGS", "build_from_spec", "GraphedTrainStep", "GraphedEvalStep",
 ]

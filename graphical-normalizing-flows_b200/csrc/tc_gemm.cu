@@ -556,19 +556,49 @@ static inline int vec_width(const float* p, long long ld) {
   return 1;
 }
 
-static int pick_bn(int N, int max_bn) {
-  int best = 64;
-  long long best_cost = -1;
+static int g_tc_gemm_force_bn = 0;      // measurement overrides (gnf_tc_gemm_set_tile); 0 = planned
+static int g_tc_gemm_force_splits = 0;
+
+// Tile width and split-K factor for the persistent engine, chosen per problem shape.  The kernel hands work items
+// (tile x k-split) to `kNumSMs` CTAs round-robin, so its duration is  rounds x (k-chunks per item) x (chunk cadence)  plus one
+// exposed epilogue: what matters is how full the LAST round is, not only the padding of N.  (The first version took the
+// widest tile that fits -- 6300 x 632: 50 x 4 = 200 items = 2 rounds of which the second is 35 % full -- and ceil(SMs / tiles)
+// splits for the wgrad: 20 tiles x 8 = 160 items = 2 rounds for 12 stragglers.)
+// Cost unit: one k-chunk of a 128 x 160 tile.  The chunk cadence is bound by operand movement (TMA / split), which scales
+// with BM + BN; the epilogue of a tile is worth ~10 such chunks at BN = 160 (profiles/r01zb_tc_gemm_trace_tma_path.txt).
+static void plan_tiles(int M, int N, int K, int max_bn, bool atomic, int* bn_out, int* splits_out) {
   const int cands[7] = {64, 96, 128, 160, 192, 224, 256};
+  const int tiles_m = (M + kGemmBM - 1) / kGemmBM;
+  const int kchunks = (K + kGemmKC - 1) / kGemmKC;
+  const int max_splits = atomic ? (K + 8 * kGemmKC - 1) / (8 * kGemmKC) : 1;
+  double best_cost = -1.;
+  int best_bn = 64, best_sp = 1;
   for (int i = 0; i < 7; ++i) {
     const int bn = cands[i];
     if (bn > max_bn) break;
-    const long long padded = (long long)((N + bn - 1) / bn) * bn;
-    // padded width is wasted tensor work; small tiles pay more A re-reads and more per-tile overhead
-    const long long cost = padded * 8 + (long long)((N + bn - 1) / bn) * 160;
-    if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = bn; }
+    if (g_tc_gemm_force_bn && bn != g_tc_gemm_force_bn) continue;
+    const long long tiles = (long long)tiles_m * ((N + bn - 1) / bn);
+    const double chunk = (128. + bn) / 288., epi = 10. * bn / 160.;
+    for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); ++sp) {
+      if (g_tc_gemm_force_splits && sp != (g_tc_gemm_force_splits < max_splits ? g_tc_gemm_force_splits : (max_splits < 1 ? 1 : max_splits))) continue;
+      const int per = (kchunks + sp - 1) / sp;
+      const int eff = (kchunks + per - 1) / per;         // splits that actually get work
+      if (eff != sp) continue;
+      const long long items = tiles * eff;
+      const long long rounds = (items + kNumSMs - 1) / kNumSMs;
+      const double cost = (double)rounds * (per * chunk + 1.) + epi;
+      if (best_cost < 0. || cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && bn > best_bn)) { best_cost = cost; best_bn = bn; best_sp = eff; }
+    }
   }
-  return best;
+  if (best_cost < 0. && (g_tc_gemm_force_bn || g_tc_gemm_force_splits)) {   // the forced combination does not exist for this shape
+    const int fb = g_tc_gemm_force_bn, fs = g_tc_gemm_force_splits;
+    g_tc_gemm_force_bn = g_tc_gemm_force_splits = 0;
+    plan_tiles(M, N, K, max_bn, atomic, bn_out, splits_out);
+    g_tc_gemm_force_bn = fb; g_tc_gemm_force_splits = fs;
+    return;
+  }
+  *bn_out = best_bn;
+  *splits_out = best_sp;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda).
@@ -622,7 +652,8 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (p.passes != 1 && p.passes != 3) return fail(GNF_ERR_INVALID, "tensor-core GEMM: passes must be 1 or 3");
   // 3xTF32: two partial accumulators + the round-to-nearest running sum must fit the 512 TMEM columns (3 x 160);
   // single-pass TF32: two accumulators of up to 256 columns, no folding
-  p.BN = pick_bn(p.N, p.passes == 3 ? 160 : 256);
+  int plan_splits = 1;
+  plan_tiles(p.M, p.N, p.K, p.passes == 3 ? 160 : 256, p.epi == TCG_EPI_ATOMIC, &p.BN, &plan_splits);
   p.acc_stride = p.passes == 3 ? 160 : 256;
   p.fold = p.passes == 3 ? g_tc_gemm_fold : (1 << 20);
   // every candidate is a multiple of 32: K-major fills advance 8/16/32 rows per pass, MN-major tiles are 32-row slabs
@@ -633,13 +664,7 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (stages < 2) return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM: tile does not fit shared memory");
   p.stages = stages;
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + p.BN - 1) / p.BN);
-  int splits = 1;
-  if (p.epi == TCG_EPI_ATOMIC) {
-    splits = (kNumSMs + tiles - 1) / tiles;
-    const int max_splits = (p.K + 8 * kGemmKC - 1) / (8 * kGemmKC);
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-  }
+  const int splits = plan_splits;
   const int kchunks = (p.K + kGemmKC - 1) / kGemmKC;
   p.k_per_split = ((kchunks + splits - 1) / splits) * kGemmKC;
   p.splits = (p.K + p.k_per_split - 1) / p.k_per_split;
@@ -802,6 +827,19 @@ int gnf_tc_gemm_set_fold(int chunks) {
 #else
   if (chunks < 1) return fail(GNF_ERR_INVALID, "gnf_tc_gemm_set_fold: need >= 1 k-chunk per fold");
   g_tc_gemm_fold = chunks > (1 << 20) ? (1 << 20) : chunks;
+  return 0;
+#endif
+}
+
+int gnf_tc_gemm_set_tile(int bn, int splits) {
+#ifdef GNF_EMU
+  (void)bn; (void)splits;
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (bn != 0 && (bn < 64 || bn > 256 || bn % 32 != 0)) return fail(GNF_ERR_INVALID, "gnf_tc_gemm_set_tile: tile width must be 0 (planned) or 64, 96, ... 256");
+  if (splits < 0) return fail(GNF_ERR_INVALID, "gnf_tc_gemm_set_tile: splits must be >= 0 (0 = planned)");
+  g_tc_gemm_force_bn = bn;
+  g_tc_gemm_force_splits = splits;
   return 0;
 #endif
 }

@@ -224,74 +224,79 @@ __global__ void lw_out_bwd_kernel(const float* __restrict__ aL, const float* __r
 //   D[r][c]     = sum_k delta_1[(r,k)][c]                   (-> dh = D W0[:,1:], dW0[:,1:] = D^T h, db0 = colsum D)
 //   dW0[c][0]  += sum_q delta_1[q][c] * t_q
 //   dx[r]       = delta_1[(r,S+1)] . W0[:,0]  +  jac[r] * gz[r]         (chain rule of the jac output + Leibniz rule)
+// Block = (NP/4) column quads x kLwRL row lanes; a row lane owns WHOLE rows r (all nodes of the row, four 16-byte loads in
+// flight per thread), so D[r] leaves from registers and the only block-wide exchange per batch of kLwRL rows is the dx dot
+// product (one __syncthreads per batch, double-buffered partials).  (The first version split the nodes of ONE row over the row
+// lanes: <= 3 loads per thread between two block barriers per row -- latency-bound at 1.3 TB/s, 67 us for an 89 MB plane.)
 __global__ void lw_layer1_bwd_kernel(const float* __restrict__ d1, const float* __restrict__ x, const float* __restrict__ ccn,
                                      const float* __restrict__ W0, int ldw0, int N1, const float* __restrict__ jac,
                                      const float* __restrict__ gz, const float* __restrict__ gzrev, float* __restrict__ D,
                                      float* __restrict__ dW0, float* __restrict__ db0, float* __restrict__ dx, LwGeom g) {
-  GNF_SMEM(float, red);                       // [kLwRL][NP] + [1]
-  float* dts = red + kLwRL * g.NP;
+  GNF_SMEM(float, red);                       // [kLwRL][NP]; the loop uses its first 2*kLwRL*(NP/4) floats for the dx partials
   const int C4 = g.NP / 4;
   const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, c = 4 * c4;
   float w[4], sT[4] = {0.f, 0.f, 0.f, 0.f}, sD[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int e = 0; e < 4; ++e) w[e] = (c + e < N1) ? __ldg(W0 + (size_t)(c + e) * ldw0) : 0.f;
-  if (threadIdx.x == 0) *dts = 0.f;
-  __syncthreads();
-  const int per = (g.R + gridDim.x - 1) / gridDim.x;
+  const bool m0 = c + 0 < N1, m1 = c + 1 < N1, m2 = c + 2 < N1, m3 = c + 3 < N1;
+  const int per = ((g.R + gridDim.x - 1) / gridDim.x + kLwRL - 1) / kLwRL * kLwRL;    // whole batches of kLwRL rows per block
   const int r0 = blockIdx.x * per, r1 = (r0 + per < g.R) ? r0 + per : g.R;
-  for (int r = r0; r < r1; ++r) {
-    const float xv = __ldg(x + r);
-    float Dp[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int kn0 = rl; kn0 < g.nodes; kn0 += 4 * kLwRL) {   // this row lane's node-rows, four loads in flight
-      float4 dv[4];
+  int it = 0;
+  for (int rb = r0; rb < r1; rb += kLwRL, ++it) {          // uniform trip count per block
+    const int r = rb + rl;
+    const bool valid = r < r1;
+    float dot = 0.f;
+    if (valid) {
+      const float xv = __ldg(x + r);
+      const float* row = d1 + (size_t)r * g.nodes * g.NP + c;
+      float Dp[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int kn0 = 0; kn0 < g.nodes; kn0 += 4) {
+        float4 dv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int kn = kn0 + u * kLwRL;
-        dv[u] = (kn < g.nodes) ? __ldg(reinterpret_cast<const float4*>(d1 + ((size_t)r * g.nodes + kn) * g.NP + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int u = 0; u < 4; ++u) {                      // unconditional loads from clamped addresses, masked at use
+          const int kn = (kn0 + u < g.nodes) ? kn0 + u : g.nodes - 1;
+          dv[u] = __ldg(reinterpret_cast<const float4*>(row + (size_t)kn * g.NP));
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int kn = kn0 + u * kLwRL;
-        if (kn < g.nodes) {
-          const float t = lw_node_abscissa(xv, ccn, kn, g.S);
-          const float v[4] = {c + 0 < N1 ? dv[u].x : 0.f, c + 1 < N1 ? dv[u].y : 0.f, c + 2 < N1 ? dv[u].z : 0.f, c + 3 < N1 ? dv[u].w : 0.f};
+        for (int u = 0; u < 4; ++u) {
+          const int kn = kn0 + u;
+          if (kn < g.nodes) {
+            const float t = lw_node_abscissa(xv, ccn, kn, g.S);
+            const float v[4] = {m0 ? dv[u].x : 0.f, m1 ? dv[u].y : 0.f, m2 ? dv[u].z : 0.f, m3 ? dv[u].w : 0.f};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { Dp[e] += v[e]; sT[e] = fmaf(v[e], t, sT[e]); }
-          if (kn == g.S + 1) atomicAdd(dts, (v[0] * w[0] + v[1] * w[1]) + (v[2] * w[2] + v[3] * w[3]));
+            for (int e = 0; e < 4; ++e) { Dp[e] += v[e]; sT[e] = fmaf(v[e], t, sT[e]); }
+            if (kn == g.S + 1) dot = (v[0] * w[0] + v[1] * w[1]) + (v[2] * w[2] + v[3] * w[3]);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) red[rl * g.NP + c + e] = Dp[e];
+      for (int e = 0; e < 4; ++e) sD[e] += Dp[e];
+      *reinterpret_cast<float4*>(D + (size_t)r * g.NP + c) = make_float4(Dp[0], Dp[1], Dp[2], Dp[3]);
+    }
+    float* part = red + (it & 1) * (kLwRL * C4);
+    part[rl * C4 + c4] = dot;
+    __syncthreads();
+    if (valid && c4 == 0) {
+      float s = 0.f;
+      for (int k = 0; k < C4; ++k) s += part[rl * C4 + k];
+      dx[r] = s + __ldg(jac + r) * lw_gz_total(gz, gzrev, r, g.d);
+    }
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+    const float* src = pass == 0 ? sT : sD;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[rl * g.NP + c + e] = src[e];
     __syncthreads();
     if (rl == 0) {
-      float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float s = 0.f;
-        for (int k = 0; k < kLwRL; ++k) s += red[k * g.NP + c + e];
-        o[e] = s;
-        sD[e] += s;
-      }
-      *reinterpret_cast<float4*>(D + (size_t)r * g.NP + c) = make_float4(o[0], o[1], o[2], o[3]);
-      if (c4 == 0) {
-        dx[r] = *dts + __ldg(jac + r) * lw_gz_total(gz, gzrev, r, g.d);
-        *dts = 0.f;
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) red[rl * g.NP + c + e] = sT[e];
-  __syncthreads();
-  if (rl == 0) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (c + e < N1) {
-        float s = 0.f;
-        for (int k = 0; k < kLwRL; ++k) s += red[k * g.NP + c + e];
-        atomicAdd(dW0 + (size_t)(c + e) * ldw0, s);
-        atomicAdd(db0 + c + e, sD[e]);
+        if (c + e < N1) {
+          float s = 0.f;
+          for (int k = 0; k < kLwRL; ++k) s += red[k * g.NP + c + e];
+          if (pass == 0) atomicAdd(dW0 + (size_t)(c + e) * ldw0, s);
+          else atomicAdd(db0 + c + e, s);
+        }
       }
     }
   }
@@ -552,7 +557,7 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   float* D = ws + pl.off_D;
   // db0 = colsum(D) comes out of the reduction kernel below (for L == 1 the output pass has already put colsum(delta_1) there)
   cudaMemsetAsync(grads->db[0], 0, (size_t)net->dims[1] * sizeof(float), s);
-  GNF_LAUNCH(lw_layer1_bwd_kernel, lw_blocks(R, 4, 5), red_threads, red_smem, s, dcur, x, ccn, net->W[0], 1 + E, net->dims[1], jac, gz,
+  GNF_LAUNCH(lw_layer1_bwd_kernel, lw_blocks(R, kLwRL, 6), red_threads, red_smem, s, dcur, x, ccn, net->W[0], 1 + E, net->dims[1], jac, gz,
              gzrev, D, grads->dW[0], grads->db[0], dx, g);
   if (int e = gnf_linear_wgrad(D, NP, h, E, grads->dW[0] + 1, 1 + E, R, net->dims[1], E, stream)) return e;
   if (int e = gnf_linear_dgrad(D, NP, net->W[0] + 1, 1 + E, nullptr, 0, dh, E, R, net->dims[1], E, stream)) return e;

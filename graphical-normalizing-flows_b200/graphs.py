@@ -1,4 +1,5 @@
-"""CUDA-graph capture of a whole training step (zero_grad -> forward -> loss -> backward -> [all-reduce] -> optimizer).
+"""CUDA-graph capture of a whole training step (zero_grad -> forward -> loss -> backward -> [all-reduce] -> optimizer)
+and of the log-likelihood evaluation step.
 
 The step of the small configs is launch-bound (tens of kernels of a few microseconds each): replaying one captured
 graph removes the per-launch gaps.  Everything inside the step is already asynchronous on the current stream and
@@ -10,18 +11,61 @@ import torch
 from . import ops
 
 
+def _device_noise_counters(model, dev):
+    """Move every DAG conditioner's Philox offset to a device counter (created once; later graphs share it)."""
+    counters = []
+    for c in model.getConditioners():
+        if hasattr(c, "_noise_counter"):
+            if c._noise_seed is None:
+                c._noise_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            if c._noise_counter is None:
+                c._noise_counter = torch.full((1,), c._noise_calls + 1, dtype=torch.int64, device=dev)
+            counters.append(c._noise_counter)
+    return counters
+
+
+def _capture(body, warmup):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(warmup):
+            body()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = body()
+    return graph, out
+
+
+class GraphedEvalStep:
+    """compute_ll (NormalizingFlow.py:48-50 / UCIExperiments.py:152-162) of a fixed batch shape as one captured graph: the
+    evaluation step of the small configs is nine launches of 7-80 us, i.e. launch-bound when issued one by one.
+    Returns (ll [B], z [B,d]) -- static tensors overwritten by the next call."""
+
+    def __init__(self, model, example_x, warmup=3):
+        self.static_x = example_x.clone()
+        self.counters = _device_noise_counters(model, example_x.device)
+
+        def body():
+            for cnt in self.counters:
+                ops.counter_add(cnt, 1)
+            with torch.no_grad():
+                return model.compute_ll(self.static_x)
+
+        self.graph, self.static_out = _capture(body, warmup)
+
+    def __call__(self, x):
+        self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 class GraphedTrainStep:
     def __init__(self, model, optimizer, bucket, example_x, allreduce=True, warmup=3):
         self.model, self.opt, self.bucket = model, optimizer, bucket
         self.static_x = example_x.clone()
-        dev = example_x.device
-        self.counters = []
-        for c in model.getConditioners():
-            if hasattr(c, "_noise_counter"):
-                if c._noise_seed is None:
-                    c._noise_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-                c._noise_counter = torch.full((1,), c._noise_calls + 1, dtype=torch.int64, device=dev)
-                self.counters.append(c._noise_counter)
+        self.counters = _device_noise_counters(model, example_x.device)
         self.allreduce = allreduce
 
         def body():
@@ -36,16 +80,7 @@ class GraphedTrainStep:
             optimizer.step()
             return loss.detach()
 
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                body()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = body()
+        self.graph, self.static_loss = _capture(body, warmup)
 
     def __call__(self, x):
         self.static_x.copy_(x, non_blocking=True)

@@ -129,6 +129,9 @@ int gnf_linear_tc_ps2(int op, const float* A_hi, const float* A_lo, int lda, con
 /* Measurement switch: 0 makes the tensor-core GEMM stage every operand with cp.async (the path taken anyway by operands
  * whose base / leading dimension are not 16-byte aligned) instead of TMA tensor maps.  Default 1. */
 int gnf_tc_gemm_set_tma(int enable);
+/* Measurement switch: force the tensor-core GEMM's tile width (64, 96, ... 256 columns; 3xTF32 is capped at 160) and / or the
+ * split-K factor of the wgrad orientation; 0 = planned per shape (fill of the last round of work items over the SMs). */
+int gnf_tc_gemm_set_tile(int bn, int splits);
 /* 3xTF32 accuracy knob: k-chunks (of 32) accumulated inside the tensor core (round-toward-zero accumulation) before the
  * partial sum is folded into a round-to-nearest running sum.  Default 2; a huge value disables folding. */
 int gnf_tc_gemm_set_fold(int chunks);

@@ -284,6 +284,30 @@ def test_cuda_graph_replays_draw_fresh_gate_noise():
     assert l1 != l2, "two replays on the same batch with lr=0 must differ through the stochastic gate noise"
 
 
+@pytest.mark.parametrize("cfg,B", [("cfg4", 100), ("cfg2", 300), ("cfg1", 100)])
+def test_cuda_graph_eval_step_matches_eager_and_follows_weight_updates(cfg, B):
+    """GraphedEvalStep replays compute_ll: same per-sample ll as the eager call on new batches, and -- the padded / split
+    weight copies are made inside the graph -- also after the parameters were updated in place."""
+    M = _mvo()
+    spec = M.CONFIGS[cfg]
+    model = M.build(spec, "cuda", seed=5)
+    parity.set_modes(model, dict(stoch_gate=False))
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xs = [torch.randn(B, spec["d"], device="cuda", generator=g) for _ in range(3)]
+    step = G.GraphedEvalStep(model, xs[0])
+    for it, x in enumerate(xs):
+        if it == 2:
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.mul_(1.01)
+        ll_g, z_g = step(x)
+        ll_g, z_g = ll_g.clone(), z_g.clone()
+        with torch.no_grad():
+            ll_e, z_e = model.compute_ll(x)
+        assert float(((ll_g - ll_e).abs() / ll_e.abs().clamp_min(1e-6)).max()) < 1e-5, it
+        assert float((z_g - z_e).abs().max()) < 1e-4, it
+
+
 def test_umnn_backward_saved_activations_equals_recompute():
     """The backward that reloads the forward's hidden activations and the one that recomputes them (UMNN's way) give the
     same gradients (bit-identical activations; only the atomics' order differs)."""
