@@ -131,6 +131,289 @@ struct EpiDagDgrad {  // ebar[m,j] -> dx[b,j] += ebar*de/dx ; dP[i,j] += ebar*de
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Layer 1 of narrow DAG flows (d <= 64): gate tile resident in shared memory
+// ------------------------------------------------------------------------------------------------
+// The functor loaders above evaluate the gate wherever the tile GEMM asks for an operand element: once per (row block, N tile) in
+// the forward (630 outputs = 5 N tiles), once per (N tile, row block) in the wgrad and once per split-K slice in the dgrad's
+// epilogue -- 5-6 evaluations of ~300 instructions (Philox4x32-10 + six logf/expf + divisions) per gate.  ncu on cfg4
+// (profiles/r01zt_ncu_dag_l1.txt): 36-40 M warp instructions per kernel against 7.8 M FFMA, issue slots 59-63 % busy: the gate
+// math, not the contraction, was the kernel.  With K = d <= 64 the whole e tile of a row block ([rows, d]) fits in shared memory:
+// these kernels evaluate every gate exactly ONCE per direction and loop over the layer width around the resident tile.
+constexpr int kDagMaxD = 64;
+constexpr int kDagKP = 64;                       // padded K / j extent of the resident tile
+
+// All three prefetch the next operand tile into registers (batched, unconditional loads from clamped addresses) while the
+// current one is being consumed: the first version loaded tile by tile between two barriers and was slower than the redundant
+// kernels (latency-bound at ~1.3 CTAs per SM: 81 / 76 / 91 us vs 73 / 62 / 75 us).
+
+// Forward: Y[m, :] = act(e[m, :] W1[:, :d]^T + T[m % period, :]).  CTA = 32 rows, 256 threads; both operands k-contiguous in
+// shared memory (Es[m][k], Ws[n][k], row stride 68 floats): a thread owns 4 rows (its warp's) x 4 columns {lane + 32 c} and
+// reads float4 along k -- every 16-byte shared-memory access (quarter-warp phases) and every store is conflict-free, and the
+// global stores of a warp are 128 contiguous bytes per row.  Loops over the N tiles of 128.  grid = ceil(M / 32).
+constexpr int kDagFwdBM = 32, kDagFwdBN = 128, kDagFwdThreads = 256;
+constexpr int kDagLDK = kDagKP + 4;
+constexpr int kDagFwdWPer = kDagFwdBN * kDagKP / kDagFwdThreads;       // 32 prefetch registers
+constexpr size_t kDagFwdSmem = (size_t)(kDagFwdBM + kDagFwdBN) * kDagLDK * sizeof(float);
+
+__global__ void __launch_bounds__(kDagFwdThreads, 2) dag_l1_fwd_kernel(GateCtx g, const float* __restrict__ W1, int ldw, const float* __restrict__ T,
+                                                                    int bias_ld, int period, int relu, float* __restrict__ Y, int ldy, int M, int N) {
+  GNF_SMEM(float, smem);
+  float* Es = smem;                              // [BM][LDK]   Es[m][j]
+  float* Ws = smem + kDagFwdBM * kDagLDK;        // [BN][LDK]   Ws[n][k]
+  const int t = threadIdx.x, m0 = blockIdx.x * kDagFwdBM, d = g.d;
+  float rw[kDagFwdWPer];
+  auto prefetch = [&](int n0) {
+#pragma unroll
+    for (int e = 0; e < kDagFwdWPer; ++e) {
+      const int idx = t + e * kDagFwdThreads, k = idx % kDagKP, nn = idx / kDagKP;
+      const bool ok = k < d && n0 + nn < N;
+      const float v = __ldg(W1 + (size_t)(ok ? n0 + nn : 0) * ldw + (ok ? k : 0));
+      rw[e] = ok ? v : 0.f;
+    }
+  };
+  prefetch(0);
+  // a gate is a ~1.5 k-clock dependent chain (Philox rounds, logf(-logf), divisions, expf) and the SM holds ~10 warps here:
+  // inlined and unrolled by four so that four independent chains are in flight per thread (this loop is rolled, unlike the
+  // register-tile loaders above: the code stays small)
+#pragma unroll 4
+  for (int idx = t; idx < kDagFwdBM * kDagKP; idx += kDagFwdThreads) {
+    const int j = idx % kDagKP, mm = idx / kDagKP, m = m0 + mm;
+    float v = 0.f;
+    if (m < M && j < d) v = gate_e<false, true>(g, m / d, m % d, j, nullptr, nullptr);
+    Es[mm * kDagLDK + j] = v;
+  }
+  const int tx = t % 32, ty = t / 32;            // lane = column residue, warp = group of 4 rows
+  const float* brow[4];                          // bias-table row of each of the thread's rows (clamped for rows >= M)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = (m0 + ty * 4 + i < M) ? m0 + ty * 4 + i : M - 1;
+    brow[i] = T + (size_t)(period > 1 ? (m % period) : 0) * bias_ld;
+  }
+  for (int n0 = 0; n0 < N; n0 += kDagFwdBN) {
+#pragma unroll
+    for (int e = 0; e < kDagFwdWPer; ++e) {
+      const int idx = t + e * kDagFwdThreads;
+      Ws[(idx / kDagKP) * kDagLDK + idx % kDagKP] = rw[e];
+    }
+    __syncthreads();
+    if (n0 + kDagFwdBN < N) prefetch(n0 + kDagFwdBN);
+    // the accumulators start from the bias table: these 16 loads are in flight during the k loop (added in the epilogue, each
+    // was a full L2 round trip in front of its store: half of the kernel's warp samples, profiles/r01zx_ncu_dag_l1_fwd.txt)
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int n = n0 + tx + 32 * c;
+        acc[i][c] = T ? __ldg(brow[i] + (n < N ? n : N - 1)) : 0.f;
+      }
+#pragma unroll 2
+    for (int k = 0; k < kDagKP; k += 4) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&Es[(ty * 4 + i) * kDagLDK + k]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(&Ws[(tx + 32 * c) * kDagLDK + k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[i][c] = fmaf(a[i].x, b[c].x, acc[i][c]);
+          acc[i][c] = fmaf(a[i].y, b[c].y, acc[i][c]);
+          acc[i][c] = fmaf(a[i].z, b[c].z, acc[i][c]);
+          acc[i][c] = fmaf(a[i].w, b[c].w, acc[i][c]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int n = n0 + tx + 32 * c;
+        if (n < N) Y[(size_t)m * ldy + n] = relu ? fmaxf(acc[i][c], 0.f) : acc[i][c];
+      }
+    }
+    __syncthreads();                             // Ws is overwritten by the next N tile
+  }
+}
+
+// Weight gradient: dW1[n, j] += sum_{m in the CTA's 64 rows} dY[m, n] e[m, j].  CTA = 64 rows of the reduction, 256 threads
+// (thread tile 8 n x 4 j, outer-product form: both operands are stored as they arrive, [m][n] and [m][j]), loops over the N tiles
+// of 128 and adds its partial tiles with atomics.  grid = ceil(M / 64).
+constexpr int kDagWgBK = 64, kDagWgBN = 128, kDagWgThreads = 256;
+constexpr int kDagWgLDN = kDagWgBN + 4;
+constexpr int kDagWgPer = kDagWgBK * kDagWgBN / kDagWgThreads;         // 32 prefetch registers
+constexpr size_t kDagWgSmem = (size_t)kDagWgBK * (kDagLDK + kDagWgLDN) * sizeof(float);
+
+__global__ void __launch_bounds__(kDagWgThreads, 2) dag_l1_wgrad_kernel(GateCtx g, const float* __restrict__ dY, int lddy, EpiAtomicAdd epi, int M, int N) {
+  GNF_SMEM(float, smem);
+  float* Em = smem;                              // [BK][LDK]   Em[m][j]
+  float* Ds = smem + kDagWgBK * kDagLDK;         // [BK][LDN]   Ds[m][n]
+  const int t = threadIdx.x, m0 = blockIdx.x * kDagWgBK, d = g.d;
+  const int rows = (M - m0 < kDagWgBK) ? M - m0 : kDagWgBK;
+  float rd[kDagWgPer];
+  auto prefetch = [&](int n0) {
+#pragma unroll
+    for (int e = 0; e < kDagWgPer; ++e) {
+      const int idx = t + e * kDagWgThreads, nn = idx % kDagWgBN, mm = idx / kDagWgBN;
+      const bool ok = mm < rows && n0 + nn < N;
+      const float v = __ldg(dY + (size_t)(m0 + (ok ? mm : 0)) * lddy + (ok ? n0 + nn : 0));
+      rd[e] = ok ? v : 0.f;
+    }
+  };
+  // every CTA adds into the same dW1 tiles: start at a different N tile per CTA so that the atomics of concurrently running
+  // CTAs do not pile up on the same addresses
+  const int ntiles = (N + kDagWgBN - 1) / kDagWgBN, first = blockIdx.x % ntiles;
+  prefetch(first * kDagWgBN);
+#pragma unroll 4
+  for (int idx = t; idx < kDagWgBK * kDagKP; idx += kDagWgThreads) {   // four independent gate chains in flight (see the forward)
+    const int j = idx % kDagKP, mm = idx / kDagKP, m = m0 + mm;
+    float v = 0.f;
+    if (m < M && j < d) v = gate_e<false, true>(g, m / d, m % d, j, nullptr, nullptr);
+    Em[mm * kDagLDK + j] = v;
+  }
+  const int tx = t % 16, ty = t / 16;            // 16 j quads x 16 groups of 8 output rows n
+  for (int it = 0; it < ntiles; ++it) {
+    const int n0 = ((first + it) % ntiles) * kDagWgBN;
+#pragma unroll
+    for (int e = 0; e < kDagWgPer; ++e) {
+      const int idx = t + e * kDagWgThreads;
+      Ds[(idx / kDagWgBN) * kDagWgLDN + idx % kDagWgBN] = rd[e];
+    }
+    __syncthreads();
+    if (it + 1 < ntiles) prefetch(((first + it + 1) % ntiles) * kDagWgBN);
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll 4
+    for (int mm = 0; mm < kDagWgBK; ++mm) {       // rows >= `rows` of both tiles are zero
+      const float4 a0 = *reinterpret_cast<const float4*>(&Ds[mm * kDagWgLDN + ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Ds[mm * kDagWgLDN + ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Em[mm * kDagLDK + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(a[i], b[c], acc[i][c]);
+    }
+    const int j = tx * 4;
+    if (j < d) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = n0 + ty * 8 + i;
+        if (n < N) epi(n, j, acc[i], (d - j < 4) ? d - j : 4);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Input gradient: ebar[m, j] = sum_n dY[m, n] W1[n, j] over the WHOLE layer width in one CTA (no split-K: the gate derivatives of
+// the epilogue are evaluated once), then dx[b, j] += ebar de/dx, dP[i, j] += ebar de/dP.  CTA = 32 rows, 128 threads (thread tile
+// 4 rows x 4 j), k-chunks of 32 (As[m][k] as it arrives, Bs[k][j] as it arrives; four k per step).  grid = ceil(M / 32).
+constexpr int kDagDgBM = 32, kDagDgBK = 32, kDagDgThreads = 128;
+constexpr int kDagDgLDA = kDagDgBK + 4;
+constexpr int kDagDgAPer = kDagDgBM * kDagDgBK / kDagDgThreads, kDagDgBPer = kDagDgBK * kDagKP / kDagDgThreads;   // 8 + 16
+constexpr size_t kDagDgSmem = (size_t)(kDagDgBM * kDagDgLDA + kDagDgBK * kDagLDK) * sizeof(float);
+
+__global__ void __launch_bounds__(kDagDgThreads, 4) dag_l1_dgrad_kernel(GateCtx g, const float* __restrict__ dY, int lddy, const float* __restrict__ W1, int ldw,
+                                                                     float* __restrict__ dx, float* __restrict__ dP, int M, int N) {
+  GNF_SMEM(float, smem);
+  float* As = smem;                              // [BM][LDA]   As[m][k] = dY[m0 + m, n0 + k]
+  float* Bs = smem + kDagDgBM * kDagDgLDA;       // [BK][LDK]   Bs[k][j] = W1[n0 + k, j]
+  const int t = threadIdx.x, m0 = blockIdx.x * kDagDgBM, d = g.d;
+  const int tx = t % 16, ty = t / 16;            // 16 j quads x 8 groups of 4 rows
+  float ra[kDagDgAPer], rb[kDagDgBPer];
+  auto prefetch = [&](int n0) {
+#pragma unroll
+    for (int e = 0; e < kDagDgAPer; ++e) {
+      const int idx = t + e * kDagDgThreads, kk = idx % kDagDgBK, mm = idx / kDagDgBK;
+      const bool ok = m0 + mm < M && n0 + kk < N;
+      const float v = __ldg(dY + (size_t)(ok ? m0 + mm : 0) * lddy + (ok ? n0 + kk : 0));
+      ra[e] = ok ? v : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < kDagDgBPer; ++e) {
+      const int idx = t + e * kDagDgThreads, j = idx % kDagKP, kk = idx / kDagKP;
+      const bool ok = j < d && n0 + kk < N;
+      const float v = __ldg(W1 + (size_t)(ok ? n0 + kk : 0) * ldw + (ok ? j : 0));
+      rb[e] = ok ? v : 0.f;
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+  prefetch(0);
+  for (int n0 = 0; n0 < N; n0 += kDagDgBK) {
+#pragma unroll
+    for (int e = 0; e < kDagDgAPer; ++e) {
+      const int idx = t + e * kDagDgThreads;
+      As[(idx / kDagDgBK) * kDagDgLDA + idx % kDagDgBK] = ra[e];
+    }
+#pragma unroll
+    for (int e = 0; e < kDagDgBPer; ++e) {
+      const int idx = t + e * kDagDgThreads;
+      Bs[(idx / kDagKP) * kDagLDK + idx % kDagKP] = rb[e];
+    }
+    __syncthreads();
+    if (n0 + kDagDgBK < N) prefetch(n0 + kDagDgBK);
+#pragma unroll 2
+    for (int kk = 0; kk < kDagDgBK; kk += 4) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty * 4 + i) * kDagDgLDA + kk]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) b[u] = *reinterpret_cast<const float4*>(&Bs[(kk + u) * kDagLDK + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(a[i].x, b[0].x, acc[i][0]); acc[i][1] = fmaf(a[i].x, b[0].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].x, b[0].z, acc[i][2]); acc[i][3] = fmaf(a[i].x, b[0].w, acc[i][3]);
+        acc[i][0] = fmaf(a[i].y, b[1].x, acc[i][0]); acc[i][1] = fmaf(a[i].y, b[1].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].y, b[1].z, acc[i][2]); acc[i][3] = fmaf(a[i].y, b[1].w, acc[i][3]);
+        acc[i][0] = fmaf(a[i].z, b[2].x, acc[i][0]); acc[i][1] = fmaf(a[i].z, b[2].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].z, b[2].z, acc[i][2]); acc[i][3] = fmaf(a[i].z, b[2].w, acc[i][3]);
+        acc[i][0] = fmaf(a[i].w, b[3].x, acc[i][0]); acc[i][1] = fmaf(a[i].w, b[3].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].w, b[3].z, acc[i][2]); acc[i][3] = fmaf(a[i].w, b[3].w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+  // epilogue: the four gates of a row are evaluated together (inlined: independent chains in flight), then their atomics
+  const int j = tx * 4;
+  if (j < d) {
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {                // rolled: four inlined gates per trip, not sixteen (instruction fetch)
+      const int m = m0 + ty * 4 + i;
+      if (m >= M) continue;
+      const int b = m / d, iv = m % d;
+      float av[4], ddx[4], ddp[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) av[jj] = i == 0 ? acc[0][jj] : (i == 1 ? acc[1][jj] : (i == 2 ? acc[2][jj] : acc[3][jj]));
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        ddx[jj] = ddp[jj] = 0.f;
+        if (j + jj < d) gate_e<true, true>(g, b, iv, j + jj, &ddx[jj], &ddp[jj]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        if (j + jj < d) {
+          atomicAdd(dx + (size_t)b * d + j + jj, av[jj] * ddx[jj]);
+          atomicAdd(dP + (size_t)iv * d + j + jj, av[jj] * ddp[jj]);
+        }
+      }
+    }
+  }
+}
+
+static int g_dag_l1_resident = 1;   // measurement switch (gnf_dag_l1_set_resident): 0 = functor-loader tile GEMM for every d
+
 static int make_gate(GateCtx* out, const float* x, const float* P, const gnf_gate_t* gate, int d) {
   if (!gate) return fail(GNF_ERR_INVALID, "gate descriptor is NULL");
   if (gate->mode < GNF_GATE_TABLE || gate->mode > GNF_GATE_NOISER) return fail(GNF_ERR_UNSUPPORTED, "unknown gate mode %d", gate->mode);
@@ -375,6 +658,10 @@ int gnf_dag_l1_fwd(const float* x, const float* P, const gnf_gate_t* gate, const
   LoadWeightT bl{W1, ldw};
   EpiBiasAct epi{Y, ldy, T, N, bias_period < 1 ? 1 : bias_period, relu};
   const int M = B * d;
+  if (d <= kDagMaxD && g_dag_l1_resident) {
+    GNF_LAUNCH(dag_l1_fwd_kernel, ceil_div(M, kDagFwdBM), kDagFwdThreads, kDagFwdSmem, s, g, W1, ldw, T, N, bias_period < 1 ? 1 : bias_period, relu, Y, ldy, M, N);
+    return check_launch("gnf_dag_l1_fwd");
+  }
   if (d >= kGateInlineMinD) launch_gemm_auto(LoadDagA<true>{g}, bl, epi, M, N, d, false, s);
   else launch_gemm_auto(LoadDagA<false>{g}, bl, epi, M, N, d, false, s);
   return check_launch("gnf_dag_l1_fwd");
@@ -391,6 +678,14 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
   const int M = B * d;
   LoadColMajorA al{dY, lddy};   // A(n, m) = dY[m, n]
   EpiAtomicAdd epi{dW1, ldw};
+  if (d <= kDagMaxD && g_dag_l1_resident) {
+#ifndef GNF_EMU
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(dag_l1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDagWgSmem); attr = true; }
+#endif
+    GNF_LAUNCH(dag_l1_wgrad_kernel, ceil_div(M, kDagWgBK), kDagWgThreads, kDagWgSmem, s, g, dY, lddy, epi, M, N);
+    return check_launch("gnf_dag_l1_wgrad");
+  }
   if (d >= kGateInlineMinD) launch_gemm_auto(al, LoadDagB<true>{g}, epi, N, d, M, true, s);    // B(m, j) = e[m, j]
   else launch_gemm_auto(al, LoadDagB<false>{g}, epi, N, d, M, true, s);
   return check_launch("gnf_dag_l1_wgrad");
@@ -408,11 +703,20 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   const int M = B * d;
   LoadRowMajorA al{dY, lddy};   // A(m, n)
   LoadRowMajorB bl{W1, ldw};    // B(n, j) = W1[n, j]
-  // N = d <= 64 gives one column of tiles (50 CTAs at cfg4): split the reduction over the layer width.  The epilogue is
+  if (d <= kDagMaxD && g_dag_l1_resident) {
+    GNF_LAUNCH(dag_l1_dgrad_kernel, ceil_div(M, kDagDgBM), kDagDgThreads, kDagDgSmem, s, g, dY, lddy, W1, ldw, dx, dP, M, N);
+    return check_launch("gnf_dag_l1_dgrad");
+  }
+  // wide flows: N = d gives few tile columns: split the reduction over the layer width.  The epilogue is
   // linear in the accumulator and already reduces with atomics, so partial sums need no second pass.
   if (d >= kGateInlineMinD) launch_gemm_auto(al, bl, EpiDagDgrad<true>{g, dx, dP}, M, d, N, true, s);
   else launch_gemm_auto(al, bl, EpiDagDgrad<false>{g, dx, dP}, M, d, N, true, s);
   return check_launch("gnf_dag_l1_dgrad");
+}
+
+int gnf_dag_l1_set_resident(int enable) {
+  g_dag_l1_resident = enable != 0;
+  return 0;
 }
 
 int gnf_dag_finish_dA(const float* dP, const float* dPdA, float* dA, int d, int accumulate, gnf_stream_t stream) {

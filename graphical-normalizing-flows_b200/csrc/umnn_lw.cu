@@ -167,31 +167,54 @@ __global__ void lw_out_bwd_kernel(const float* __restrict__ aL, const float* __r
   float w[4], sW[4] = {0.f, 0.f, 0.f, 0.f}, sB[4] = {0.f, 0.f, 0.f, 0.f}, sy = 0.f;
 #pragma unroll
   for (int e = 0; e < 4; ++e) w[e] = (c + e < NL) ? __ldg(wl + c + e) : 0.f;
-  const long long per = (g.Q + gridDim.x - 1) / gridDim.x;
-  const long long q0 = (long long)blockIdx.x * per;
-  const long long q1 = (q0 + per < g.Q) ? q0 + per : g.Q;
-  for (long long q = q0 + rl; q < q1; q += kLwRL) {
-    const int r = (int)(q / g.nodes), kn = (int)(q % g.nodes);
-    float gq;
-    if (kn <= g.S) {
-      gq = (lw_gz_total(gz, gzrev, r, g.d) * __ldg(x + r) / 2.f) * __ldg(ccw + kn);
-    } else {
-      gq = gjac ? __ldg(gjac + r) : 0.f;
-      if (glogdet) gq += __ldg(glogdet + r / g.d) / __ldg(jac + r);
-    }
-    const float y = __ldg(ysave + q);
-    gq *= (y > 0.f) ? 1.f : expf(y);
-    const float4 av = __ldg(reinterpret_cast<const float4*>(aL + (size_t)q * g.NP + c));
-    const float a[4] = {c + 0 < NL ? av.x : 0.f, c + 1 < NL ? av.y : 0.f, c + 2 < NL ? av.z : 0.f, c + 3 < NL ? av.w : 0.f};
-    float o[4];
+  // Q < 2^31 (lw_plan): 32-bit indices; (r, kn) of a thread's node-row advance incrementally -- a 64-bit q / nodes per row
+  // is a function call (CALL.REL) -- and two node-rows are in flight per thread
+  const int Q = (int)g.Q;
+  const int per = (Q + gridDim.x - 1) / gridDim.x;
+  const int q0 = blockIdx.x * per;
+  const int q1 = (q0 + per < Q) ? q0 + per : Q;
+  int q = q0 + rl;
+  int r = q / g.nodes, kn = q - r * g.nodes;
+  const int dr = kLwRL / g.nodes, dk = kLwRL - dr * g.nodes;     // q += kLwRL  ==  (r, kn) += (dr, dk) with one carry
+  for (; q < q1; q += 2 * kLwRL) {
+    int rr[2], kk[2];
+    float4 av[2];
+    float ys[2];
+    bool ok[2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      sW[e] = fmaf(gq, a[e], sW[e]);
-      o[e] = a[e] > 0.f ? gq * w[e] : 0.f;
-      sB[e] += o[e];
+    for (int u = 0; u < 2; ++u) {
+      rr[u] = r; kk[u] = kn;
+      ok[u] = q + u * kLwRL < q1;
+      const int qq = ok[u] ? q + u * kLwRL : q;             // clamped address, masked at use
+      av[u] = __ldg(reinterpret_cast<const float4*>(aL + (size_t)qq * g.NP + c));
+      ys[u] = __ldg(ysave + qq);
+      r += dr; kn += dk;
+      if (kn >= g.nodes) { kn -= g.nodes; ++r; }
     }
-    *reinterpret_cast<float4*>(dL + (size_t)q * g.NP + c) = make_float4(o[0], o[1], o[2], o[3]);
-    if (c4 == 0) sy += gq;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const int ru = rr[u];
+      float gq;
+      if (kk[u] <= g.S) {
+        gq = (lw_gz_total(gz, gzrev, ru, g.d) * __ldg(x + ru) / 2.f) * __ldg(ccw + kk[u]);
+      } else {
+        gq = gjac ? __ldg(gjac + ru) : 0.f;
+        if (glogdet) gq += __ldg(glogdet + ru / g.d) / __ldg(jac + ru);
+      }
+      const float y = ys[u];
+      gq *= (y > 0.f) ? 1.f : expf(y);
+      const float a[4] = {c + 0 < NL ? av[u].x : 0.f, c + 1 < NL ? av[u].y : 0.f, c + 2 < NL ? av[u].z : 0.f, c + 3 < NL ? av[u].w : 0.f};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sW[e] = fmaf(gq, a[e], sW[e]);
+        o[e] = a[e] > 0.f ? gq * w[e] : 0.f;
+        sB[e] += o[e];
+      }
+      *reinterpret_cast<float4*>(dL + (size_t)(q + u * kLwRL) * g.NP + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (c4 == 0) sy += gq;
+    }
   }
   float* ry = red + kLwRL * g.NP;
   for (int pass = 0; pass < 2; ++pass) {

@@ -195,6 +195,9 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
  * dx [B,d] and dP [d,d] are zero-filled by the call. */
 int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const float* x, const float* P,
                      const gnf_gate_t* gate, float* dx, float* dP, int B, int d, int N, gnf_stream_t stream);
+/* Measurement switch: 1 (default) = narrow flows (d <= 64) run layer 1 on the kernels that keep the gate tile of a row block
+ * resident in shared memory (every gate evaluated once per direction); 0 = functor-loader tile GEMM for every d. */
+int gnf_dag_l1_set_resident(int enable);
 /* dA[i,j] (+)= dP[i,j]*dPdA[i,j]. */
 int gnf_dag_finish_dA(const float* dP, const float* dPdA, float* dA, int d, int accumulate, gnf_stream_t stream);
 /* Debug / parity hook: materialise the in-kernel Philox draws for (seed, offset) as [B,d,d] tensors. */
