@@ -98,6 +98,7 @@ _PROTOS = {
     "gnf_tc_gemm_set_fold": ([_I], C.c_int),
     "gnf_tc_gemm_set_tile": ([_I, _I], C.c_int),
     "gnf_dag_l1_set_resident": ([_I], C.c_int),
+    "gnf_tc_gemm_plan": ([_I, _I, _I, _I, _I, _P, _P], C.c_int),
     "gnf_tc_gemm_set_trace": ([_P], C.c_int),
     "gnf_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
     "gnf_tc_probe": ([_I, _I, _P, _P], C.c_int),

@@ -844,6 +844,17 @@ int gnf_tc_gemm_set_tile(int bn, int splits) {
 #endif
 }
 
+int gnf_tc_gemm_plan(int M, int N, int K, int passes, int wgrad, int* bn, int* splits) {
+#ifdef GNF_EMU
+  (void)M; (void)N; (void)K; (void)passes; (void)wgrad; (void)bn; (void)splits;
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (M <= 0 || N <= 0 || K <= 0 || !bn || !splits || (passes != 1 && passes != 3)) return fail(GNF_ERR_INVALID, "gnf_tc_gemm_plan: bad arguments");
+  plan_tiles(M, N, K, passes == 3 ? 160 : 256, wgrad != 0, bn, splits);
+  return 0;
+#endif
+}
+
 int gnf_tc_gemm_set_tma(int enable) {
 #ifdef GNF_EMU
   (void)enable;

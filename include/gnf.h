@@ -132,6 +132,9 @@ int gnf_tc_gemm_set_tma(int enable);
 /* Measurement switch: force the tensor-core GEMM's tile width (64, 96, ... 256 columns; 3xTF32 is capped at 160) and / or the
  * split-K factor of the wgrad orientation; 0 = planned per shape (fill of the last round of work items over the SMs). */
 int gnf_tc_gemm_set_tile(int bn, int splits);
+/* Host-only query of that plan for a GEMM of M x N outputs reduced over K (wgrad != 0: the split-K orientation, where M x N is
+ * the weight shape and K the number of rows): writes the tile width and the split-K factor the engine would use. */
+int gnf_tc_gemm_plan(int M, int N, int K, int passes, int wgrad, int* bn, int* splits);
 /* 3xTF32 accuracy knob: k-chunks (of 32) accumulated inside the tensor core (round-toward-zero accumulation) before the
  * partial sum is folded into a round-to-nearest running sum.  Default 2; a huge value disables folding. */
 int gnf_tc_gemm_set_fold(int chunks);

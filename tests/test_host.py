@@ -153,3 +153,33 @@ def test_shard_batch_covers_the_batch():
     x = torch.arange(10).view(10, 1)
     parts = [G.dist.shard_batch(x, r, 4) for r in range(4)]
     assert torch.equal(torch.cat(parts), x)
+
+
+def test_tensor_core_gemm_plan_fills_the_last_round_of_work_items():
+    """The persistent tcgen05 GEMM hands (tile x k-split) items round-robin to 148 CTAs: the planner must not leave a nearly
+    empty last round (the first version ran cfg4's wgrad as 160 items = 2 rounds for 12 stragglers).  Host-only query."""
+    import ctypes as C
+    import __graft_entry__
+    __graft_entry__.build()
+    lib = G._lib.load_library()          # dlopen + bind; the query is host code, no GPU needed
+    bn, sp = C.c_int(0), C.c_int(0)
+
+    def plan(M, N, K, passes, wgrad):
+        assert lib.gnf_tc_gemm_plan(M, N, K, passes, wgrad, C.byref(bn), C.byref(sp)) == 0
+        tiles = -(-M // 128) * -(-N // bn.value)
+        return bn.value, sp.value, tiles * sp.value
+
+    # cfg4 conditioner hidden layer, 100 samples: forward / dgrad (no split), wgrad (split-K over the 6300 rows)
+    b, s, items = plan(6300, 632, 632, 3, 0)
+    assert s == 1 and b in (64, 96, 128, 160) and items <= 2 * 148 and items / (-(-items // 148) * 148) > 0.8, (b, s, items)
+    b, s, items = plan(632, 632, 6300, 3, 1)
+    assert b <= 160 and s >= 1 and items <= 148 and items >= 120, (b, s, items)
+    # big batch: many rounds, the widest 3xTF32 tile wins; single pass may use up to 256 columns
+    assert plan(64512, 632, 632, 3, 0)[0] == 160
+    assert plan(78400, 1024, 1024, 1, 0)[0] == 256
+    # every plan is a legal tile
+    for (M, N, K, p, w) in [(100, 30, 630, 3, 0), (15000, 60, 60, 1, 0), (210, 210, 10000, 3, 1), (1, 1, 1, 1, 1)]:
+        b, s, _ = plan(M, N, K, p, w)
+        assert b % 32 == 0 and 64 <= b <= (160 if p == 3 else 256) and s >= 1
+    assert lib.gnf_tc_gemm_plan(0, 1, 1, 3, 0, C.byref(bn), C.byref(sp)) != 0
+    assert lib.gnf_tc_gemm_set_tile(100, 0) != 0 and lib.gnf_tc_gemm_set_tile(0, 0) == 0
