@@ -50,6 +50,8 @@ _PROTOS = {
     "gnf_power_trace_workspace_bytes": ([_I], _SZ),
     "gnf_power_trace_fwd": ([_P, _I, _F, _I, _P, _P, _SZ, _P], C.c_int),
     "gnf_power_trace_bwd": ([_P, _I, _F, _I, _P, _P, _P, _SZ, _P], C.c_int),
+    "gnf_power_trace_fwd_save": ([_P, _I, _F, _I, _P, _P, _P], C.c_int),
+    "gnf_power_trace_bwd_saved": ([_P, _P, _I, _F, _I, _P, _P, _P], C.c_int),
     "gnf_linear_fwd": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_dgrad": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_wgrad": ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _P], C.c_int),

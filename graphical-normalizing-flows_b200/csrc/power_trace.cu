@@ -125,6 +125,40 @@ __global__ void __launch_bounds__(kPTThreads) power_trace_small_bwd(const float*
   }
 }
 
+// Training flavour of the small-d forward: one launch leaves everything the backward needs.  G = B^(p-1) by the same binary
+// chain, t = tr(G B) - d = sum_ik G[i][k] B[k][i] - d (a dot product instead of the last matrix product), and G goes to global
+// memory so that the backward is one elementwise pass (trace_bwd_kernel) instead of a second single-CTA chain of p-1 products
+// (21 us at d = 63, p = 13, on the critical path of every training step).  The last product's rounding order differs from
+// torch.matrix_power's (B^12 B instead of B^5 B^8): ~1e-6 relative on t; the no-grad path keeps torch's order.
+__global__ void __launch_bounds__(kPTThreads) power_trace_small_fwd_save(const float* __restrict__ A, int d, float alpha, int p, float* __restrict__ t_out,
+                                                                         float* __restrict__ Gout) {
+  GNF_SMEM(float, smem);
+  if (p <= 0) {                                  // tr(I) - d = 0, no dependence on A
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) Gout[e] = 0.f;
+    if (threadIdx.x == 0) *t_out = 0.f;
+    return;
+  }
+  sm_build_B(smem, A, d, alpha);
+  const float* G = sm_matrix_power(smem, d, p - 1);
+  const float* Bm = smem;
+  float s = 0.f;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, k = e % d;
+    const float gv = G[i * kLD + k];
+    Gout[e] = gv;
+    s = fmaf(gv, Bm[k * kLD + i], s);
+  }
+  __syncthreads();                               // every read of the chain's buffers is done: reuse one as the reduction scratch
+  float* red = smem + kMatFloats;
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (int)blockDim.x; ++i) tot += red[i];
+    *t_out = tot - (float)d;
+  }
+}
+
 // ------------------------------- large-d helpers -------------------------------
 __global__ void build_B_kernel(const float* __restrict__ A, float* __restrict__ Bm, int d, float alpha) {
   const size_t n = (size_t)d * d;
@@ -222,6 +256,23 @@ int gnf_power_trace_fwd(const float* A, int d, float alpha, int p, float* t_out,
   const float* M = big_matrix_power(w, d, p, s);
   GNF_LAUNCH(trace_kernel, 1, 256, 256 * sizeof(float), s, M, d, t_out);
   return check_launch("gnf_power_trace_fwd");
+}
+
+int gnf_power_trace_fwd_save(const float* A, int d, float alpha, int p, float* t_out, float* G_out, gnf_stream_t stream) {
+  if (!A || !t_out || !G_out || d <= 0 || p < 0) return fail(GNF_ERR_INVALID, "gnf_power_trace_fwd_save: bad arguments");
+  if (d > kSmallD) return fail(GNF_ERR_UNSUPPORTED, "gnf_power_trace_fwd_save: d <= %d only (larger d: gnf_power_trace_fwd / _bwd)", kSmallD);
+  const size_t smem = (size_t)5 * kMatFloats * sizeof(float);
+#ifndef GNF_EMU
+  cudaFuncSetAttribute(power_trace_small_fwd_save, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  GNF_LAUNCH(power_trace_small_fwd_save, 1, kPTThreads, smem, (cudaStream_t)stream, A, d, alpha, p, t_out, G_out);
+  return check_launch("gnf_power_trace_fwd_save");
+}
+
+int gnf_power_trace_bwd_saved(const float* A, const float* G, int d, float alpha, int p, const float* gt, float* dA, gnf_stream_t stream) {
+  if (!A || !G || !gt || !dA || d <= 0 || p < 0) return fail(GNF_ERR_INVALID, "gnf_power_trace_bwd_saved: bad arguments");
+  GNF_LAUNCH(trace_bwd_kernel, pt_blocks(d), 256, 0, (cudaStream_t)stream, A, G, d, alpha, p, gt, dA);
+  return check_launch("gnf_power_trace_bwd_saved");
 }
 
 int gnf_power_trace_bwd(const float* A, int d, float alpha, int p, const float* gt, float* dA, void* work,

@@ -181,6 +181,9 @@ def _pt_workspace(d, device):
     return torch.empty((n + 3) // 4, device=device, dtype=torch.float32), n
 
 
+POWER_TRACE_SAVE_MAX_D = 64   # d <= 64 and A needs a gradient: the forward leaves (I + alpha A∘A)^(p-1) for the backward
+
+
 class PowerTraceFn(torch.autograd.Function):
     """tr((I + alpha A∘A)^p) - d  (DAGConditioner.get_power_trace, DAGConditioner.py:176-194)."""
 
@@ -189,19 +192,31 @@ class PowerTraceFn(torch.autograd.Function):
         require(A, "A")
         d = A.shape[0]
         t = torch.empty((), device=A.device, dtype=A.dtype)
+        ctx.alpha, ctx.p = float(alpha), int(p)
+        if d <= POWER_TRACE_SAVE_MAX_D and ctx.needs_input_grad[0]:
+            G = torch.empty(d, d, device=A.device, dtype=A.dtype)
+            _TIMES_ALIAS["gnf_power_trace_fwd_save"] = "gnf_power_trace_fwd"
+            _call("gnf_power_trace_fwd_save", ptr(A), d, float(alpha), int(p), ptr(t), ptr(G), stream_ptr())
+            _count()
+            ctx.save_for_backward(A, G)
+            return t
         ws, n = _pt_workspace(d, A.device)
         _call("gnf_power_trace_fwd", ptr(A), d, float(alpha), int(p), ptr(t), ptr(ws), n, stream_ptr())
         _count()
         ctx.save_for_backward(A)
-        ctx.alpha, ctx.p = float(alpha), int(p)
         return t
 
     @staticmethod
     def backward(ctx, gt):
-        (A,) = ctx.saved_tensors
+        A = ctx.saved_tensors[0]
         d = A.shape[0]
         gt = _contig(gt)
         dA = torch.empty_like(A)
+        if len(ctx.saved_tensors) == 2:
+            _TIMES_ALIAS["gnf_power_trace_bwd_saved"] = "gnf_power_trace_bwd"
+            _call("gnf_power_trace_bwd_saved", ptr(A), ptr(ctx.saved_tensors[1]), d, ctx.alpha, ctx.p, ptr(gt), ptr(dA), stream_ptr())
+            _count()
+            return dA, None, None
         ws, n = _pt_workspace(d, A.device)
         _call("gnf_power_trace_bwd", ptr(A), d, ctx.alpha, ctx.p, ptr(gt), ptr(dA), ptr(ws), n, stream_ptr())
         _count()

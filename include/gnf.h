@@ -79,6 +79,13 @@ int gnf_power_trace_fwd(const float* A, int d, float alpha, int p, float* t_out,
 int gnf_power_trace_bwd(const float* A, int d, float alpha, int p, const float* gt, float* dA, void* work,
                         size_t work_bytes, gnf_stream_t stream);
 
+/* Training flavour for d <= 64: the forward also leaves G = (I+alpha A∘A)^(p-1) [d,d] in G_out (t = tr(G B) - d as a dot product:
+ * the last product's rounding order differs from torch.matrix_power's by ~1e-6 relative), and the backward is one elementwise
+ * pass over it instead of a second single-CTA chain of matrix products. */
+int gnf_power_trace_fwd_save(const float* A, int d, float alpha, int p, float* t_out, float* G_out, gnf_stream_t stream);
+int gnf_power_trace_bwd_saved(const float* A, const float* G, int d, float alpha, int p, const float* gt, float* dA,
+                              gnf_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------
  * Conditioner MLP engine (K1 layers 2..L, K5, K6): nn.Linear / ReLU stacks
  * (DAGConditioner.py:7-20, AutoregressiveConditioner.py:24-25, CouplingConditioner.py:6-18)

@@ -39,3 +39,27 @@ def test_golden_monotonic_case_layerwise_engine_in_simulator(emu, name):
         parity.run_case(name, "cpu")
     finally:
         G.ops.UMNN_ENGINE = "auto"
+
+
+def test_power_trace_golden_in_simulator(emu):
+    """K2 against the reference's golden power traces, both flavours: the no-grad forward (torch.matrix_power's order) and
+    the training forward that leaves (I + alpha A∘A)^(p-1) for an elementwise backward (d <= 64)."""
+    import numpy as np
+    from helpers import GOLDEN, rel_l2
+    torch.set_num_threads(1)
+    f = np.load(os.path.join(GOLDEN, "power_trace.npz"))
+    for key in sorted({k.rsplit(".", 1)[0] for k in f.files}):
+        d, p, alpha = f[key + ".meta"]
+        if int(d) > 64:
+            continue                      # the host-driven GEMM chain is too slow for the simulator; covered on the GPU
+        want = float(f[key + ".t"])
+        tol = 2e-5 * abs(want) + 1e-5 * float(d)
+        A = torch.from_numpy(f[key + ".A"])
+        with torch.no_grad():
+            t0 = G.ops.PowerTraceFn.apply(A, float(alpha), int(p))
+        assert abs(float(t0) - want) <= tol, key
+        A = A.clone().requires_grad_(True)
+        t = G.ops.PowerTraceFn.apply(A, float(alpha), int(p))
+        t.backward()
+        assert abs(float(t.detach()) - want) <= tol, key
+        assert rel_l2(A.grad, torch.from_numpy(f[key + ".dA"])) < 1e-4, key
