@@ -449,9 +449,19 @@ __global__ void colsum_kernel(const float* __restrict__ Y, float* __restrict__ o
   const int q0 = blockIdx.y * q_per;
   const int q1 = (q0 + q_per < Q) ? q0 + q_per : Q;
   if (c < C && (c % ldy) < N) {
-    float s = 0.f;
-    for (int q = q0; q < q1; ++q) s += __ldg(Y + (size_t)q * rowstride + c);
-    atomicAdd(out + (size_t)(c / ldy) * N + (c % ldy), s);
+    // eight independent row loads in flight per thread (one per iteration left a few KB in flight per SM: 26 us for an 89 MB plane)
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = Y + c;
+    int q = q0;
+    for (; q + 7 < q1; q += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(q + u) * rowstride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += v[u];
+    }
+    for (; q < q1; ++q) s[0] += __ldg(src + (size_t)q * rowstride);
+    atomicAdd(out + (size_t)(c / ldy) * N + (c % ldy), ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
   }
 }
 
@@ -597,7 +607,7 @@ int gnf_colsum(const float* Y, int ldy, float* out, int M, int N, int period, gn
   if (M == 0) return check_launch("gnf_colsum");
   const int Q = M / period, C = period * ldy;
   const int cblocks = ceil_div(C, 256);
-  int qsplit = ceil_div(4 * kNumSMs, cblocks);
+  int qsplit = ceil_div(8 * kNumSMs, cblocks);
   if (qsplit > ceil_div(Q, 8)) qsplit = ceil_div(Q, 8);
   if (qsplit < 1) qsplit = 1;
   const int q_per = ceil_div(Q, qsplit);

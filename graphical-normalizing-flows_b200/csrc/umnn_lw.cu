@@ -20,6 +20,7 @@
 namespace gnf {
 
 constexpr int kLwRL = 8;  // row lanes per block in the reduction kernels: blockDim = (NP/4) * kLwRL
+constexpr int kOutBwdU = 3;  // node-rows in flight per thread in lw_out_bwd_kernel: 59 registers -> 3 blocks of 320 threads per SM, ~46 KB in flight
 
 struct LwGeom {
   int R, d, E, S, nodes, NP, L;
@@ -168,7 +169,7 @@ __global__ void lw_out_bwd_kernel(const float* __restrict__ aL, const float* __r
 #pragma unroll
   for (int e = 0; e < 4; ++e) w[e] = (c + e < NL) ? __ldg(wl + c + e) : 0.f;
   // Q < 2^31 (lw_plan): 32-bit indices; (r, kn) of a thread's node-row advance incrementally -- a 64-bit q / nodes per row
-  // is a function call (CALL.REL) -- and two node-rows are in flight per thread
+  // is a function call (CALL.REL) -- and kOutBwdU node-rows are in flight per thread
   const int Q = (int)g.Q;
   const int per = (Q + gridDim.x - 1) / gridDim.x;
   const int q0 = blockIdx.x * per;
@@ -176,13 +177,13 @@ __global__ void lw_out_bwd_kernel(const float* __restrict__ aL, const float* __r
   int q = q0 + rl;
   int r = q / g.nodes, kn = q - r * g.nodes;
   const int dr = kLwRL / g.nodes, dk = kLwRL - dr * g.nodes;     // q += kLwRL  ==  (r, kn) += (dr, dk) with one carry
-  for (; q < q1; q += 2 * kLwRL) {
-    int rr[2], kk[2];
-    float4 av[2];
-    float ys[2];
-    bool ok[2];
+  for (; q < q1; q += kOutBwdU * kLwRL) {
+    int rr[kOutBwdU], kk[kOutBwdU];
+    float4 av[kOutBwdU];
+    float ys[kOutBwdU];
+    bool ok[kOutBwdU];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kOutBwdU; ++u) {
       rr[u] = r; kk[u] = kn;
       ok[u] = q + u * kLwRL < q1;
       const int qq = ok[u] ? q + u * kLwRL : q;             // clamped address, masked at use
@@ -192,7 +193,7 @@ __global__ void lw_out_bwd_kernel(const float* __restrict__ aL, const float* __r
       if (kn >= g.nodes) { kn -= g.nodes; ++r; }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kOutBwdU; ++u) {
       if (!ok[u]) continue;
       const int ru = rr[u];
       float gq;
@@ -562,7 +563,10 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   const size_t red_smem = ((size_t)kLwRL * NP + kLwRL + 4) * sizeof(float);
   const float* ysave = saved + (size_t)L * plane;
   // output layer: delta_L, dW_L, db_L, db_{L-1}
-  GNF_LAUNCH(lw_out_bwd_kernel, lw_blocks(pl.Q, 64, 4), red_threads, red_smem, s, saved + (size_t)(L - 1) * plane, ysave, net->W[L],
+  // one resident wave: at 64 registers per thread an SM holds 65536 / (64 * threads) blocks (3 at NP = 160; the grid of 4 per
+  // SM ran as 1.33 waves)
+  const int out_bwd_per_sm = 65536 / (64 * red_threads) < 1 ? 1 : (65536 / (64 * red_threads) > 4 ? 4 : 65536 / (64 * red_threads));
+  GNF_LAUNCH(lw_out_bwd_kernel, lw_blocks(pl.Q, 64, out_bwd_per_sm), red_threads, red_smem, s, saved + (size_t)(L - 1) * plane, ysave, net->W[L],
              net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dcur, grads->dW[L], grads->db[L], grads->db[L - 1], g);
   // hidden layers, top down: dW_l = delta_{l+1}^T a_l;  delta_l = (delta_{l+1} W_l) o relu'(a_l);  db_{l-1} = colsum delta_l
   for (int l = L - 1; l >= 1; --l) {
