@@ -20,7 +20,23 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, dev=False):
+    """Product library, or (dev=True) libgnf_sm100_dev.so = the same sources with -DGNF_DEVTOOLS: clock-stamp traces,
+    ablation switches and tiling overrides for scripts/ -- never loaded by the package."""
+    global OUT, OBJ
+    if dev:
+        saved = (OUT, OBJ, list(NVCC_FLAGS))
+        OUT, OBJ = os.path.join(HERE, "libgnf_sm100_dev.so"), os.path.join(HERE, "build_dev")
+        NVCC_FLAGS.append("-DGNF_DEVTOOLS")
+        try:
+            return _build(force, verbose)
+        finally:
+            OUT, OBJ = saved[0], saved[1]
+            NVCC_FLAGS[:] = saved[2]
+    return _build(force, verbose)
+
+
+def _build(force=False, verbose=False):
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         [os.path.join(os.path.dirname(HERE), "include", "gnf.h")]
@@ -49,4 +65,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
-    print(build(force=True, verbose="-v" in sys.argv))
+    print(build(force=True, verbose="-v" in sys.argv, dev="--dev" in sys.argv))

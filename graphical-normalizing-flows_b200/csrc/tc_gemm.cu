@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // the whole warp runs the loop converged; one elected lane issues (tc_common.cuh: mma_*_w)
       const uint32_t idesc = make_idesc_tf32(kGemmBM, BN) | (p.a_src == TCG_SRC_MN ? (1u << 15) : 0u) | (p.b_src == TCG_SRC_MN ? (1u << 16) : 0u);
       // per k-step (8 k) descriptor advance: K-major: 32 bytes inside the swizzle atom; MN-major: 8 tile rows = 1024 bytes
       const uint32_t a_step = (p.a_src == TCG_SRC_K) ? 2u : 64u, b_step = (p.b_src == TCG_SRC_K) ? 2u : 64u;
@@ -320,24 +320,24 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
             const int s = (int)(it % p.stages);
             mbar_wait(&ready[s], (uint32_t)((it / p.stages) & 1));
             fence_after_sync();
-            trace_stamp(p.trace, 3, it);
+            if (lane == 0) trace_stamp(p.trace, 3, it);
             const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
             const uint64_t da_hi = make_sw128_desc(st, a_mn), db_hi = make_sw128_desc(st + a_bytes, b_mn);
             const uint64_t da_lo = make_sw128_desc(st + a_bytes + b_bytes, a_mn), db_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes, b_mn);
 #pragma unroll
             for (int ks = 0; ks < kGemmKC / 8; ++ks) {
               const uint64_t oa = (uint64_t)(a_step * ks), ob = (uint64_t)(b_step * ks);
-              mma_tf32_ss(d_tmem, da_hi + oa, db_hi + ob, idesc, first ? 0u : 1u);
+              mma_tf32_ss_w(d_tmem, da_hi + oa, db_hi + ob, idesc, first ? 0u : 1u);
               first = false;
               if (split) {
-                mma_tf32_ss(d_tmem, da_lo + oa, db_hi + ob, idesc, 1u);
-                mma_tf32_ss(d_tmem, da_hi + oa, db_lo + ob, idesc, 1u);
+                mma_tf32_ss_w(d_tmem, da_lo + oa, db_hi + ob, idesc, 1u);
+                mma_tf32_ss_w(d_tmem, da_hi + oa, db_lo + ob, idesc, 1u);
               }
             }
-            mma_commit(&empty[s]);
+            mma_commit_w(&empty[s]);
           }
-          mma_commit(&tfull[acc]);
-          trace_stamp(p.trace, 4, gcount);
+          mma_commit_w(&tfull[acc]);
+          if (lane == 0) trace_stamp(p.trace, 4, gcount);
         }
       }
     }

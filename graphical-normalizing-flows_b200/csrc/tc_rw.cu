@@ -136,13 +136,13 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
 
   if (warp >= kRwEpiWarps + kRwLoadWarps) {
     // ===================== MMA issuer (one thread) =====================
-    if (warp == kRwEpiWarps + kRwLoadWarps && lane == 0) {
+    if (warp == kRwEpiWarps + kRwLoadWarps) {   // the whole warp runs the loop converged; one elected lane issues
       const uint32_t idesc = make_idesc_tf32(kRwRows, NP);
       const uint32_t whi = smem_u32(smem), wlo = whi + (uint32_t)NP * (uint32_t)KP * 4u;
       const uint64_t dhi0 = make_smem_desc(whi, (uint32_t)NP * 16u, 128u), dlo0 = make_smem_desc(wlo, (uint32_t)NP * 16u, 128u);
       const uint64_t dstep = (uint64_t)((2u * (uint32_t)NP * 16u) >> 4);      // one k-step (8 k) = two 16-byte K chunks of the image
       const uint32_t tD = tmem_base + kRwColD, tAhi = tmem_base + kRwColAhi, tAlo = tmem_base + kRwColAlo;
-      RwTrace trm = {(p.trace && blockIdx.x == 0) ? p.trace : nullptr, 0};
+      RwTrace trm = {(p.trace && blockIdx.x == 0 && lane == 0) ? p.trace : nullptr, 0};
       mbar_wait(w_full, 0);
       for (long long tl = 0; tl < n_local; ++tl) {
         trm.stamp();                                         // per tile: start, D free, chunk c issued (x NCH), all issued
@@ -156,17 +156,17 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
           fence_after_sync();
           const int k0 = c * 4, k1 = (p.debug & 4) ? k0 + (c == 0 ? 1 : 0) : ((k0 + 4 < nksteps) ? k0 + 4 : nksteps);
           if (split) {
-            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAlo + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
-            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dlo0 + dstep * kk, idesc, 1u);
+            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts_w(tD, tAlo + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
+            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts_w(tD, tAhi + kk * 8, dlo0 + dstep * kk, idesc, 1u);
           } else {
-            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
+            for (int kk = k0; kk < k1; ++kk) mma_tf32_ts_w(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
           }
           trm.stamp();
         }
         if (split && !(p.debug & 4))
-          for (int kk = 0; kk < nksteps; ++kk) mma_tf32_ts(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, 1u);
-        mma_commit(a_empty);
-        mma_commit(d_full);
+          for (int kk = 0; kk < nksteps; ++kk) mma_tf32_ts_w(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, 1u);
+        mma_commit_w(a_empty);
+        mma_commit_w(d_full);
         trm.stamp();
       }
     }

@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
     }
   } else if (warp == 13) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // the whole warp runs the loop converged; one elected lane issues (tc_common.cuh: mma_*_w)
       const uint32_t idesc = make_idesc_tf32(128, NP);
       const uint64_t dstep = (uint64_t)((2u * NP * 16u) >> 4);             // one k-step (8 q) = two 16-byte q-quads of the image
       const uint32_t tD0 = tmem_base + kWgColD0, tD1 = tmem_base + kWgColD1;
-      WgTrace tr = {(p.trace && blockIdx.x == 0) ? p.trace : nullptr, 0};
+      WgTrace tr = {(p.trace && blockIdx.x == 0 && lane == 0) ? p.trace : nullptr, 0};
       for (int j = 0; j < nloc; ++j) {
         const int i = j % kWgImgStages, b = j & 1;
         tr.stamp();                                                        // per chunk: start, A full, image full, issued
@@ -125,24 +125,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
         for (int ks = 0; ks < kWgQC / 8; ++ks) {
           const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
           if (split) {
-            mma_tf32_ts(tD0, tA + 16 + ks * 8, bhi + dstep * ks, idesc, acc);
-            mma_tf32_ts(tD0, tA + 0 + ks * 8, blo + dstep * ks, idesc, 1u);
-            mma_tf32_ts(tD0, tA + 0 + ks * 8, bhi + dstep * ks, idesc, 1u);
+            mma_tf32_ts_w(tD0, tA + 16 + ks * 8, bhi + dstep * ks, idesc, acc);
+            mma_tf32_ts_w(tD0, tA + 0 + ks * 8, blo + dstep * ks, idesc, 1u);
+            mma_tf32_ts_w(tD0, tA + 0 + ks * 8, bhi + dstep * ks, idesc, 1u);
             if (two) {
-              mma_tf32_ts(tD1, tA + 48 + ks * 8, bhi + dstep * ks, idesc, acc);
-              mma_tf32_ts(tD1, tA + 32 + ks * 8, blo + dstep * ks, idesc, 1u);
-              mma_tf32_ts(tD1, tA + 32 + ks * 8, bhi + dstep * ks, idesc, 1u);
+              mma_tf32_ts_w(tD1, tA + 48 + ks * 8, bhi + dstep * ks, idesc, acc);
+              mma_tf32_ts_w(tD1, tA + 32 + ks * 8, blo + dstep * ks, idesc, 1u);
+              mma_tf32_ts_w(tD1, tA + 32 + ks * 8, bhi + dstep * ks, idesc, 1u);
             }
           } else {
-            mma_tf32_ts(tD0, tA + 0 + ks * 8, bhi + dstep * ks, idesc, acc);
-            if (two) mma_tf32_ts(tD1, tA + 32 + ks * 8, bhi + dstep * ks, idesc, acc);
+            mma_tf32_ts_w(tD0, tA + 0 + ks * 8, bhi + dstep * ks, idesc, acc);
+            if (two) mma_tf32_ts_w(tD1, tA + 32 + ks * 8, bhi + dstep * ks, idesc, acc);
           }
         }
-        mma_commit(&a_empty[b]);
-        mma_commit(&img_empty[i]);
+        mma_commit_w(&a_empty[b]);
+        mma_commit_w(&img_empty[i]);
         tr.stamp();
       }
-      mma_commit(d_full);
+      mma_commit_w(d_full);
     }
   } else if (warp >= 5) {
     // ===================== stagers: raw [16 q][NP] -> canonical K-major images [(q/4)][k][q%4] of hi and lo =====================

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(2 * kTcRows + 32) umnn_fwd_tc2_kernel(TcFwdPar
 
   if (is_issuer) {
     // ===================== MMA issuer warp =====================
-    if (lane == 0) {
+    {   // the whole warp runs the loop converged; one elected lane issues (tc_common.cuh: mma_*_w)
       for (long long i = 0; i < n_iter; ++i) {
         const int layer = (int)(i % L);
         const uint32_t wbase = img_addr + p.off[layer] * 4u;
@@ -362,14 +362,14 @@ __global__ void __launch_bounds__(2 * kTcRows + 32) umnn_fwd_tc2_kernel(TcFwdPar
           constexpr uint64_t kDescStep = (2u * NP * 16u) >> 4;   // one k-step = two 16-byte K chunks of the image
           uint32_t ta = tmem_base + rA;
           const uint32_t td = tmem_base + rD;
-          mma_tf32_ts(td, ta, bdesc, idesc, 0u);
+          mma_tf32_ts_w(td, ta, bdesc, idesc, 0u);
 #pragma unroll 4
           for (int ks = 1; ks < nk; ++ks) {
             bdesc += kDescStep;
             ta += 8;
-            mma_tf32_ts(td, ta, bdesc, idesc, 1u);
+            mma_tf32_ts_w(td, ta, bdesc, idesc, 1u);
           }
-          mma_commit(&bars[1 + gg]);
+          mma_commit_w(&bars[1 + gg]);
           stamp(i, gg, 2);
         }
       }

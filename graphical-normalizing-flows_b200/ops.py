@@ -719,6 +719,9 @@ SAVE_ACTIVATIONS_MAX_BYTES = 48 << 30
 # mode allows tensor cores, the integrand has a hidden x hidden layer worth a GEMM and the activations fit the budget.
 UMNN_ENGINE = "auto"
 UMNN_LAYERWISE_MIN_NODE_ROWS = 16384
+# The strict forward of the layer-wise engine runs as ONE fused tensor-core kernel (gnf_umnn_fwd_tc3) when the integrand fits it
+# (>= 3 linear layers, hidden widths <= 160); False = per-layer passes (gnf_umnn_fwd_lw).
+UMNN_FWD_FUSED_TC3 = True
 
 
 def _umnn_layerwise_passes(net, R, S, train):
@@ -806,6 +809,19 @@ class UmnnFn(torch.autograd.Function):
         if fast:
             _call("gnf_umnn_fwd_tc", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
                   ptr(logdet), R, d, ptr(ws), nbytes, stream_ptr())
+        elif lw_passes == 3 and UMNN_FWD_FUSED_TC3 and lib().gnf_umnn_tc3_workspace_bytes(C.byref(net), R) != 0:
+            # fused strict forward (tc_umnn3.cu): 3xTF32, the activation chain of a tile stays in TMEM from the first to the
+            # last hidden layer; training keeps the planes / masks the layer-wise backward consumes, evaluation keeps nothing.
+            # MMA order: training = all correction products of a layer first (order 1: 20 instead of 60 truncating additions at
+            # full accumulator magnitude; with order 0 the saved activations carry a one-sided 5e-7 error that the backward's
+            # cancelling sums amplify to 1e-3 .. 2e-3 on the integrand's bias gradients); evaluation = per-chunk order 0
+            if train:
+                saved = torch.empty(lib().gnf_umnn_lw_saved_floats(C.byref(net), R, int(S), 1), device=x.device, dtype=torch.float32)
+            nbytes = lib().gnf_umnn_tc3_workspace_bytes(C.byref(net), R)
+            ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+            _call("gnf_umnn_fwd_tc3", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
+                  ptr(logdet), ptr(saved), int(train), int(train), R, d, ptr(ws), nbytes, stream_ptr())
+            _count(6)
         elif lw_passes is not None:
             # layer-wise engine: hidden x hidden layers on the tensor-core GEMM engine, activations in HBM
             saved = torch.empty(lib().gnf_umnn_lw_saved_floats(C.byref(net), R, int(S), int(train)), device=x.device,

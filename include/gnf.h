@@ -275,6 +275,20 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
                     const float* saved, float* dx, float* dh, const gnf_mlp_grad_t* grads, int passes, int R, int d,
                     void* work, size_t work_bytes, gnf_stream_t stream);
 
+/* Fused strict forward of the same integral on the tensor cores (tc_umnn3.cu): 3xTF32 (fp32-equivalent, round-to-nearest
+ * hi/lo split), the activation chain of a 128-node-row tile resident in TMEM from the first to the last hidden layer, the
+ * hidden weights streamed through shared memory as pre-split hi/lo K-chunks.  Replaces the per-layer passes of
+ * gnf_umnn_fwd_lw (MonotonicNormalizer.py:51-66 / UMNN ParallelNeuralIntegral forward): same outputs, and -- when
+ * `saved` is given -- the same saved-activation buffer ([gnf_umnn_lw_saved_floats(net, R, S, train)] floats), so that
+ * gnf_umnn_bwd_lw consumes it unchanged.  saved == NULL (evaluation): no activation touches HBM.
+ * order: 0 = per K-chunk a_lo*b_hi, a_hi*b_lo, a_hi*b_hi; 1 = all correction products of a layer first (the hi images
+ * are streamed twice).  Hidden widths <= 160, >= 3 linear layers; otherwise GNF_ERR_UNSUPPORTED.
+ * work: gnf_umnn_tc3_workspace_bytes(net, R) bytes, 16-byte aligned. */
+size_t gnf_umnn_tc3_workspace_bytes(const gnf_mlp_t* net, int R);
+int gnf_umnn_fwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
+                     float* z, float* zrev, float* jac, float* logdet, float* saved, int train, int order, int R, int d,
+                     void* work, size_t work_bytes, gnf_stream_t stream);
+
 /* DAGConditioner.loss (DAGConditioner.py:268-271) fused:  out = dag_const*(lambd*t + c/2*t^2) + l1_weight*mean|A|, with the
  * dual variables read from their device buffers (lambd, c, dag_const, l1_weight: one float each, as registered by the
  * reference's constructor :86-91) and t = the power trace (gnf_power_trace_fwd).  fp32, reference evaluation order (t^2
