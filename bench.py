@@ -13,9 +13,10 @@ the configuration north_star's target is quoted on; 100 samples per GPU (its YAM
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM, timed per step with CUDA
 events (L2 flushed between timed steps), max over ranks.  `e2e` = the same metric through the public API with
 pinned HOST input batches copied H2D and the loss read back D2H inside the timed region.
-`--impl reference` times the reference algorithm's CPU port (oracle/, torch CPU, all host threads) on the same
-workload: /root/reference does not exist on the GPU box and its UMNN dependency is not installable, so the
-CPU arm is the oracle port ("kind": "port").
+`--impl reference` times the reference ITSELF on the host CPU (all threads) on the same workload: the verbatim copy of its
+`models/` package under the git-ignored baseline/_ref/ (made by baseline/install_ref.py in the build container, shipped
+with the snapshot), stock classes and code path, with oracle/UMNN.py standing in for the uninstallable UMNN==1.0
+("kind": "reference+restated-UMNN"); only if that copy is missing does it fall back to the oracle port ("kind": "port").
 """
 import argparse
 import json
@@ -155,9 +156,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (reference algorithm, torch CPU)
+# CPU arm: the reference itself (baseline/_ref/models, stock classes and code path, + the restated UMNN dependency) when the
+# copy made by baseline/install_ref.py travelled with the snapshot; else the oracle port (reference algorithm, torch CPU)
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_fn(cfg, B, mode, S):
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_arm
+    lr, wd = ADAM[cfg]
+    if ref_arm.available():
+        return ref_arm.step_fn(CONFIGS[cfg], B, mode, S, lr, wd), "reference+restated-UMNN"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gnf_oracle as O
     spec = {k: v for k, v in CONFIGS[cfg].items() if k != "A_prior"}
@@ -168,7 +175,6 @@ def cpu_reference_step_fn(cfg, B, mode, S):
     keys = O.trainable_keys(sd)
     for k in keys:
         sd[k] = sd[k].clone().requires_grad_(True)
-    lr, wd = ADAM[cfg]
     opt = torch.optim.Adam([sd[k] for k in keys], lr=lr, weight_decay=wd)
     g = torch.Generator().manual_seed(0)
     d = spec["d"]
@@ -185,7 +191,7 @@ def cpu_reference_step_fn(cfg, B, mode, S):
         loss = O.flow_loss(z, jac, sd, spec)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     def eval_step():
         x = torch.randn(B, d, generator=g)
@@ -193,31 +199,37 @@ def cpu_reference_step_fn(cfg, B, mode, S):
             ll, _ = O.compute_ll(x, sd, spec, None, noises(), S)
         return float(ll.mean())
 
-    return train_step if mode == "train" else eval_step
+    return (train_step if mode == "train" else eval_step), "port"
 
 
 def time_cpu(cfg, B, mode, S, steps, warmup, budget_s=25.):
-    """Bounded CPU timing: batch reduced (stated in `sample`) when a full step would blow the budget."""
+    """Bounded CPU timing: EXACTLY `steps` timed steps after `warmup` untimed ones; the batch is reduced (stated in `sample`)
+    when full-batch steps would blow the time budget."""
     torch.set_num_threads(os.cpu_count() or 1)
     Bc = B
     probe_B = min(B, 16)
-    fn = cpu_reference_step_fn(cfg, probe_B, mode, S)
-    t0 = time.perf_counter(); fn(); fn(); t1 = time.perf_counter()
-    per_sample = (t1 - t0) / 2 / probe_B
+    fn, kind = cpu_reference_step_fn(cfg, probe_B, mode, S)
+    fn()
+    t0 = time.perf_counter(); fn(); t1 = time.perf_counter()
+    per_sample = (t1 - t0) / probe_B
     total_steps = steps + warmup
     if per_sample * B * total_steps > budget_s:
         Bc = max(1, int(budget_s / (per_sample * total_steps)))
-    fn = cpu_reference_step_fn(cfg, Bc, mode, S)
+    fn, kind = cpu_reference_step_fn(cfg, Bc, mode, S)
     for _ in range(warmup):
         fn()
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    mean = sum(ts) / len(ts)
     ts.sort()
     med = ts[len(ts) // 2]
-    return {"value": Bc / med, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} {mode} steps of {WORKLOAD_NAME[cfg]} at batch {Bc} (of {B}) on the host CPU, "
-                      f"median step {med * 1e3:.1f} ms, after {warmup} warm-up"}, med
+    what = ("the reference's own classes (baseline/_ref/models: buildFCNormalizingFlow, forward, loss, backward, Adam) with "
+            "oracle/UMNN.py standing in for the absent UMNN==1.0" if kind != "port" else "the oracle port of the reference algorithm")
+    return {"value": Bc / mean, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "steps": steps, "warmup": warmup, "batch": Bc, "median_step_ms": med * 1e3, "mean_step_ms": mean * 1e3,
+            "sample": f"{steps} {mode} steps of {WORKLOAD_NAME[cfg]} at batch {Bc} (of {B}) on the host CPU after {warmup} warm-up "
+                      f"steps, {what}; value = batch / mean step time"}, mean
 
 
 # ------------------------------------------------------------------------------------------------
@@ -261,13 +273,17 @@ def main():
                                  if args.precision == "strict" else
                                  "tf32 tensor-core UMNN forward (tcgen05, ll tol 2e-3) + strict fp32 elsewhere"), "l2": "flushed between timed steps (256 MiB write)"}
 
+    config["gemm_engine"] = args.gemm
+    config["umnn_engine"] = args.umnn_engine
+    config["cuda_graph"] = args.cuda_graph in ("on", "auto")
+
     # ---------------- reference arm ----------------
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, med = time_cpu(cfg, B, args.mode, S, max(3, min(args.steps, 10)), 2, budget_s=120.)
+        cb, mean = time_cpu(cfg, B, args.mode, S, args.steps, args.warmup, budget_s=150.)
         line = {"metric": metric, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "impl": "reference",
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -465,11 +481,8 @@ def main():
                 "last_loss": last, "kernel_ms": {k: sum(v) / len(v) for k, v in ktimes.items() if v},
                 "nb_steps": S_, "precision": precision, "gemm_engine": gemm, "cuda_graph": bool(use_graph)}
 
-    config["gemm_engine"] = args.gemm
-    config["umnn_engine"] = args.umnn_engine
     use_graph_any = args.cuda_graph in ("on", "auto")
     use_graph = use_graph_any
-    config["cuda_graph"] = use_graph
     opt_kwargs = dict(lr=lr, weight_decay=wd, fused=True, capturable=True) if use_graph else None
     if use_graph and args.mode == "train":
         opt = torch.optim.Adam(model.parameters(), **opt_kwargs)

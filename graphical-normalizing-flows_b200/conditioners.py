@@ -157,9 +157,16 @@ class DAGConditioner(Conditioner):
         if self._noise_seed is None:
             self._noise_seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # follows torch.manual_seed
         if self._noise_counter is not None:
-            # graph-capturable: the Philox offset lives on the device and is bumped inside the captured step
+            # graph-capturable: the Philox offset lives on the device.  Inside a capture the captured step bumps it itself and
+            # its forward and backward replay together.  An EAGER call made after a graph was built draws fresh noise (bump)
+            # and freezes the offset it used in a private scalar, so that its backward regenerates the same noise even if a
+            # graph replay moves the shared counter in between.
+            cnt = self._noise_counter
+            if not torch.cuda.is_current_stream_capturing():
+                ops.counter_add(cnt, 1)
+                cnt = cnt.clone()
             return ops.GateSpec(mode, imp, self.h_thresh, self.gumble_T, seed=self._noise_seed,
-                                offset=(self._noise_rank << 40), offset_dev=self._noise_counter)
+                                offset=(self._noise_rank << 40), offset_dev=cnt)
         self._noise_calls += 1
         return ops.GateSpec(mode, imp, self.h_thresh, self.gumble_T, seed=self._noise_seed,
                             offset=(self._noise_rank << 40) + self._noise_calls)
@@ -244,7 +251,7 @@ class DAGConditioner(Conditioner):
             self.noise_gate = False
             self.s_thresh = False
             self.h_thresh = 0.
-            self.A.data = (soft > zero_threshold).float()
+            self.A.data.copy_((soft > zero_threshold).float())        # in place: A keeps its storage (captured graphs, optimizers)
             self.A *= 1. - torch.eye(self.in_size, device=self.A.device)
         self.A.requires_grad = False
         self.A.grad = None
@@ -255,44 +262,61 @@ class DAGConditioner(Conditioner):
             return self._longest_path(adj)
         return 0
 
+    def _set_scalar(self, name, value):
+        """In-place update of a one-element dual buffer: the device pointer stays valid for captured CUDA graphs and for the
+        fused loss kernel (the reference rebinds the attribute to a fresh tensor; the value semantics are the same)."""
+        buf = getattr(self, name)
+        value = torch.as_tensor(value, dtype=buf.dtype, device=buf.device).reshape(buf.shape)
+        buf.copy_(value)
+
+    def graph_state(self):
+        """Everything a captured step froze at capture time: host-side flags, the power-trace exponent, and the identity /
+        address of A and of the dual buffers.  Graphed*Step compares it on every call and recaptures on change."""
+        return (int(self.exponent), bool(self.s_thresh), float(self.h_thresh), bool(self.stoch_gate), bool(self.noise_gate),
+                float(self.gumble_T), bool(self.hot_encoding), float(self.alpha_factor), self._alpha_host(), id(self.A),
+                self.A.data_ptr(), bool(self.A.requires_grad), self.lambd.data_ptr(), self.c.data_ptr(),
+                self.dag_const.data_ptr(), self.l1_weight.data_ptr())
+
     def update_dual_param(self):
-        """Augmented-Lagrangian update (DAGConditioner.py:196-260)."""
+        """Augmented-Lagrangian update (DAGConditioner.py:196-260).  The dual buffers are updated in place (stable device
+        pointers); `self.A = nn.Parameter(A_before)` is kept as the reference has it -- a NEW Parameter object, which, exactly
+        as in the reference, is no longer known to an optimizer built earlier."""
         with torch.no_grad():
             lag_const = self.get_power_trace()
             while self.dag_const > 0. and lag_const < self.tol and self.exponent < self.in_size:
                 self.exponent += 50
                 lag_const = self.get_power_trace()
             if self.dag_const > 0. and lag_const > self.tol:
-                self.lambd = self.lambd + self.c * lag_const
+                self._set_scalar("lambd", self.lambd + self.c * lag_const)
                 if lag_const.abs() > self.gamma * self.prev_trace.abs():
                     self.c *= self.eta
-                self.prev_trace = lag_const
+                self._set_scalar("prev_trace", lag_const)
             elif self.dag_const > 0.:
                 A_before = self.A.clone()
                 self.post_process()
-                self.alpha = self.getAlpha().to(self.A.device)
+                self._set_scalar("alpha", self.getAlpha())
                 lag_const = self.get_power_trace()
                 if lag_const > 0.:
                     self.stoch_gate, self.noise_gate, self.s_thresh, self.h_thresh = True, False, True, 0.
                     self.A = nn.Parameter(A_before)
                     self.A.requires_grad = True
                     self.A.grad = self.A.clone()
-                    self.alpha = self.getAlpha().to(self.A.device)
-                    self.prev_trace = self.get_power_trace()
+                    self._set_scalar("alpha", self.getAlpha())
+                    self._set_scalar("prev_trace", self.get_power_trace())
                     self.c *= 1 / self.eta
-                    self.lambd = self.lambd + self.c * lag_const
-                    self.dag_const = torch.tensor(1., device=self.A.device)
+                    self._set_scalar("lambd", self.lambd + self.c * lag_const)
+                    self._set_scalar("dag_const", 1.)
                 else:
-                    self.dag_const = torch.tensor(0., device=self.A.device)
-                    self.l1_weight = torch.tensor(0., device=self.A.device)
+                    self._set_scalar("dag_const", 0.)
+                    self._set_scalar("l1_weight", 0.)
             else:
                 if not self._is_dag(self._adjacency(self.A.detach() ** 2)):
                     self.A.requires_grad = True
                     self.A.grad = self.A.clone()
                     self.stoch_gate, self.noise_gate, self.s_thresh, self.h_thresh = True, False, True, 0.
-                    self.alpha = self.getAlpha().to(self.A.device)
-                    self.prev_trace = self.get_power_trace()
-                    self.dag_const = torch.tensor(1., device=self.A.device)
+                    self._set_scalar("alpha", self.getAlpha())
+                    self._set_scalar("prev_trace", self.get_power_trace())
+                    self._set_scalar("dag_const", 1.)
                 else:
                     self.is_invertible = True
         return lag_const

@@ -243,12 +243,9 @@ static inline void launch_gemm(const ALoad& al, const BLoad& bl, const Epi& epi,
   splits = ceil_div(K > 0 ? K : 1, k_per_split);
   dim3 grid(ceil_div(M, Cfg::BM), ceil_div(N, Cfg::BN), splits);
 #ifndef GNF_EMU
-  static bool attr_set = false;
-  if (!attr_set && Cfg::SMEM_BYTES > 48 * 1024) {
+  if (Cfg::SMEM_BYTES > 48 * 1024)         // per launch: the attribute is per device (a process-wide flag breaks a second GPU)
     cudaFuncSetAttribute(gemm_kernel<Cfg, ALoad, BLoad, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)Cfg::SMEM_BYTES);
-    attr_set = true;
-  }
 #endif
   GNF_LAUNCH((gemm_kernel<Cfg, ALoad, BLoad, Epi>), grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, al, bl, epi, M, N,
              K, k_per_split);

@@ -690,8 +690,7 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
   EpiAtomicAdd epi{dW1, ldw};
   if (d <= kDagMaxD && g_dag_l1_resident) {
 #ifndef GNF_EMU
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(dag_l1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDagWgSmem); attr = true; }
+    cudaFuncSetAttribute(dag_l1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDagWgSmem);   // per device: set per launch
 #endif
     GNF_LAUNCH(dag_l1_wgrad_kernel, ceil_div(M, kDagWgBK), kDagWgThreads, kDagWgSmem, s, g, dY, lddy, epi, M, N);
     return check_launch("gnf_dag_l1_wgrad");

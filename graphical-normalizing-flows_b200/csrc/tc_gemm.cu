@@ -688,8 +688,8 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   p.trace = g_tc_gemm_trace;
   const long long total = (long long)tiles * p.splits;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget); attr = true; }
+  // per launch: the attribute is per DEVICE, a process-wide "done" flag breaks the second GPU of a process (and is racy)
+  cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
   GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB, tmBlo, tmAlo);
   return 0;

@@ -94,7 +94,11 @@ def shard_batch(x, rank=None, world=None):
         rank = dist.get_rank() if is_dist() else 0
     if world is None:
         world = dist.get_world_size() if is_dist() else 1
-    per = (x.shape[0] + world - 1) // world
+    if x.shape[0] % world != 0:
+        # unequal (or empty) shards would bias the AVG all-reduce of per-rank mean gradients and turn an empty shard's
+        # mean log-likelihood into NaN on every rank
+        raise ValueError(f"batch of {x.shape[0]} samples does not split evenly over {world} ranks: drop or pad the remainder")
+    per = x.shape[0] // world
     return x[rank * per:(rank + 1) * per]
 
 

@@ -24,6 +24,17 @@ def _device_noise_counters(model, dev):
     return counters
 
 
+def model_graph_state(model):
+    """Host-side state a captured step froze: conditioner flags / exponents / buffer addresses
+    (DAGConditioner.graph_state), quadrature steps and precision of the normalizers, and the engine switches."""
+    st = [ops._GEMM_MODE, ops.UMNN_ENGINE, ops.UMNN_FWD_FUSED_TC3]
+    for c in model.getConditioners():
+        st.append(c.graph_state() if hasattr(c, "graph_state") else None)
+    for n in model.getNormalizers():
+        st.append((getattr(n, "nb_steps", None), getattr(n, "precision", None), getattr(n, "solver", None)))
+    return tuple(st)
+
+
 def _capture(body, warmup):
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
@@ -44,8 +55,14 @@ class GraphedEvalStep:
     Returns (ll [B], z [B,d]) -- static tensors overwritten by the next call."""
 
     def __init__(self, model, example_x, warmup=3):
+        self.model, self.warmup = model, warmup
         self.static_x = example_x.clone()
-        self.counters = _device_noise_counters(model, example_x.device)
+        self.recaptures = 0
+        self._capture()
+
+    def _capture(self):
+        model = self.model
+        self.counters = _device_noise_counters(model, self.static_x.device)
 
         def body():
             for cnt in self.counters:
@@ -53,20 +70,35 @@ class GraphedEvalStep:
             with torch.no_grad():
                 return model.compute_ll(self.static_x)
 
-        self.graph, self.static_out = _capture(body, warmup)
+        self.graph, self.static_out = _capture(body, self.warmup)
+        self.state = model_graph_state(model)
 
     def __call__(self, x):
+        if model_graph_state(self.model) != self.state:      # e.g. model.step() moved an exponent / a gate flag / A
+            self.recaptures += 1
+            self._capture()
         self.static_x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.static_out
 
 
 class GraphedTrainStep:
+    """One training step as one captured graph.  The capture freezes host-side model state (DAG gate flags, the power-trace
+    exponent, quadrature steps, the addresses of A and of the dual buffers): `model.step()` / `update_dual_param()` /
+    `post_process()` may change it, so every call compares `model_graph_state` with the captured one and RECAPTURES when it
+    differs (`recaptures` counts them).  Note the reference's own quirk: when update_dual_param re-creates A as a new
+    Parameter, an optimizer built earlier no longer owns it -- here as there."""
+
     def __init__(self, model, optimizer, bucket, example_x, allreduce=True, warmup=3):
         self.model, self.opt, self.bucket = model, optimizer, bucket
         self.static_x = example_x.clone()
-        self.counters = _device_noise_counters(model, example_x.device)
-        self.allreduce = allreduce
+        self.allreduce, self.warmup = allreduce, warmup
+        self.recaptures = 0
+        self._capture()
+
+    def _capture(self):
+        model, optimizer, bucket, allreduce = self.model, self.opt, self.bucket, self.allreduce
+        self.counters = _device_noise_counters(model, self.static_x.device)
 
         def body():
             for cnt in self.counters:
@@ -80,9 +112,13 @@ class GraphedTrainStep:
             optimizer.step()
             return loss.detach()
 
-        self.graph, self.static_loss = _capture(body, warmup)
+        self.graph, self.static_loss = _capture(body, self.warmup)
+        self.state = model_graph_state(model)
 
     def __call__(self, x):
+        if model_graph_state(self.model) != self.state:
+            self.recaptures += 1
+            self._capture()
         self.static_x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.static_loss

@@ -712,6 +712,18 @@ _CC_CACHE = {}
 # The strict UMNN forward keeps its hidden activations for the backward when they fit in this many bytes (else the
 # backward recomputes them, as UMNN does).  0 disables.
 SAVE_ACTIVATIONS_MAX_BYTES = 48 << 30
+# ... and never more than this fraction of the device memory that is free at the time of the call (an N-step flow keeps N sets of
+# activations alive until its backward; a smaller GPU falls back to the recomputing backward instead of running out of memory)
+SAVE_ACTIVATIONS_FREE_FRACTION = 0.5
+
+
+def _activation_budget(device):
+    if SAVE_ACTIVATIONS_MAX_BYTES <= 0:
+        return 0
+    if L._SIMULATOR or torch.cuda.is_current_stream_capturing():
+        return SAVE_ACTIVATIONS_MAX_BYTES
+    free, _ = torch.cuda.mem_get_info(device)
+    return min(SAVE_ACTIVATIONS_MAX_BYTES, int(free * SAVE_ACTIVATIONS_FREE_FRACTION))
 
 
 # Engine of the strict UMNN integral: 'fused' = one FFMA kernel per direction (umnn.cu), 'layerwise' = per-layer passes
@@ -724,7 +736,7 @@ UMNN_LAYERWISE_MIN_NODE_ROWS = 16384
 UMNN_FWD_FUSED_TC3 = True
 
 
-def _umnn_layerwise_passes(net, R, S, train):
+def _umnn_layerwise_passes(net, R, S, train, device=None):
     """GEMM passes (0 FFMA / 1 TF32 / 3 3xTF32) for the layer-wise UMNN engine, or None for the fused FFMA kernels."""
     if UMNN_ENGINE == "fused" or net.dims[0] < 2:
         return None
@@ -735,7 +747,7 @@ def _umnn_layerwise_passes(net, R, S, train):
             return None
     need = 4 * (lib().gnf_umnn_lw_saved_floats(C.byref(net), R, S, int(train)) +
                 (lib().gnf_umnn_lw_workspace_bytes(C.byref(net), R, S, int(train)) // 4))
-    if need == 0 or need > SAVE_ACTIVATIONS_MAX_BYTES:
+    if need == 0 or need > _activation_budget(device):
         if UMNN_ENGINE == "layerwise" and need == 0:
             raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
         return None
@@ -805,7 +817,7 @@ class UmnnFn(torch.autograd.Function):
         logdet = torch.empty(B, device=x.device, dtype=x.dtype)
         saved = None
         train = any(ctx.needs_input_grad)
-        lw_passes = None if fast else _umnn_layerwise_passes(net, R, int(S), train)
+        lw_passes = None if fast else _umnn_layerwise_passes(net, R, int(S), train, x.device)
         if fast:
             _call("gnf_umnn_fwd_tc", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
                   ptr(logdet), R, d, ptr(ws), nbytes, stream_ptr())
@@ -838,7 +850,7 @@ class UmnnFn(torch.autograd.Function):
             if train and SAVE_ACTIVATIONS_MAX_BYTES > 0:
                 per_row = lib().gnf_umnn_saved_floats_per_node_row(C.byref(net))
                 need = R * (int(S) + 1) * per_row * 4
-                if 0 < need <= SAVE_ACTIVATIONS_MAX_BYTES:
+                if 0 < need <= _activation_budget(x.device):
                     saved = torch.empty(R * (int(S) + 1) * per_row, device=x.device, dtype=torch.float32)
             _call("gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
                   ptr(logdet), ptr(saved), R, d, ptr(ws), nbytes, stream_ptr())
