@@ -303,7 +303,8 @@ def main():
     d = spec["d"]
     lr, wd = ADAM[cfg]
     bucket = G.dist.GradBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd, fused=True)
+    # the reference's optimizer (torch.optim.Adam(lr, weight_decay), UCIExperiments.py:100) as one multi-tensor launch per step
+    opt = G.FusedAdam(model.parameters(), lr=lr, weight_decay=wd)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     n_pool = 8
     pool = [torch.randn(B, d, device=dev, generator=gen) for _ in range(n_pool)]
@@ -483,9 +484,6 @@ def main():
 
     use_graph_any = args.cuda_graph in ("on", "auto")
     use_graph = use_graph_any
-    opt_kwargs = dict(lr=lr, weight_decay=wd, fused=True, capturable=True) if use_graph else None
-    if use_graph and args.mode == "train":
-        opt = torch.optim.Adam(model.parameters(), **opt_kwargs)
     main_res = measure(args.mode, args.precision, args.gemm, S, args.steps, args.warmup, True, use_graph)
     extra = None
     if args.mode == "train" and not args.no_eval:

@@ -14,8 +14,10 @@ from .normalizers import AffineNormalizer, ELUPlus, IntegrandNet, MonotonicNorma
 from . import dist
 from .graphs import GraphedEvalStep, GraphedTrainStep
 from .configs import CONFIGS, build_from_spec
+from .optim import FusedAdam
 
 __all__ = [
+    "FusedAdam",
     "AutoregressiveConditioner", "Conditioner", "ConditionnalMADE", "CouplingConditioner", "CouplingMLP", "DAGConditioner",
     "DAGMLP", "MADE", "MaskedLinear", "FCNormalizingFlow", "MNIST_A_prior", "NormalLogDensity", "NormalizingFlow",
     "NormalizingFlowStep", "buildFCNormalizingFlow", "AffineNormalizer", "ELUPlus", "IntegrandNet", "MonotonicNormalizer",

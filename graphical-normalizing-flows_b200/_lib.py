@@ -32,6 +32,11 @@ class MlpT(C.Structure):
                 ("W", C.c_void_p * GNF_MAX_LAYERS), ("b", C.c_void_p * GNF_MAX_LAYERS)]
 
 
+class AdamTensorT(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64)]
+
+
 class MlpGradT(C.Structure):
     _fields_ = [("dW", C.c_void_p * GNF_MAX_LAYERS), ("db", C.c_void_p * GNF_MAX_LAYERS)]
 
@@ -111,6 +116,7 @@ _PROTOS = {
     "gnf_broadcast_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_counter_add": ([_P, C.c_uint64, _P], C.c_int),
     "gnf_axpy": ([_F, _P, _P, _SZ, _P], C.c_int),
+    "gnf_adam_step": ([C.POINTER(AdamTensorT), _I, _P, _F, _F, _F, _F, _F, _P], C.c_int),
     "gnf_dag_loss_fwd": ([_P, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "gnf_dag_loss_bwd": ([_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
 }

@@ -289,6 +289,21 @@ int gnf_umnn_fwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
                      float* z, float* zrev, float* jac, float* logdet, float* saved, int train, int order, int R, int d,
                      void* work, size_t work_bytes, gnf_stream_t stream);
 
+/* One Adam step over a list of parameter tensors in one launch (per 48 tensors): the optimizer of the reference's training
+ * loops (torch.optim.Adam(model.parameters(), lr, weight_decay), UCIExperiments.py:100, ToyExperiments.py:59; L2 weight decay,
+ * no amsgrad):  g += wd*p;  m += (1-b1)(g-m);  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * with t = *step_dev + 1.  `tensors` is a HOST array (device pointers inside); step_dev a device int64 counter of the steps done
+ * so far -- the caller increments it after the call (gnf_counter_add), which keeps the pair capturable in a CUDA graph. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} gnf_adam_tensor_t;
+int gnf_adam_step(const gnf_adam_tensor_t* tensors, int n_tensors, const int64_t* step_dev, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, gnf_stream_t stream);
+
 /* DAGConditioner.loss (DAGConditioner.py:268-271) fused:  out = dag_const*(lambd*t + c/2*t^2) + l1_weight*mean|A|, with the
  * dual variables read from their device buffers (lambd, c, dag_const, l1_weight: one float each, as registered by the
  * reference's constructor :86-91) and t = the power trace (gnf_power_trace_fwd).  fp32, reference evaluation order (t^2

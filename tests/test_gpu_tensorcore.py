@@ -48,7 +48,7 @@ def test_umnn_tensorcore_forward_matches_strict(cfg, B, S):
     assert float((z_f - z_s).abs().max()) < 5e-3
 
 
-def test_umnn_tensorcore_forward_vs_oracle_and_strict_backward():
+def test_umnn_tensorcore_forward_with_strict_backward_trains():
     """fast forward + strict backward still trains: ll within the TF32 bar of the CPU oracle, gradients finite and
     close to the strict ones (they are the strict kernel's gradients of the same weights)."""
     import model_vs_oracle as M

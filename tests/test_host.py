@@ -150,9 +150,14 @@ def test_data_parallel_gradients_match_single_process():
 
 
 def test_shard_batch_covers_the_batch():
-    x = torch.arange(10).view(10, 1)
+    x = torch.arange(12).view(12, 1)
     parts = [G.dist.shard_batch(x, r, 4) for r in range(4)]
-    assert torch.equal(torch.cat(parts), x)
+    assert torch.equal(torch.cat(parts), x) and all(p.shape[0] == 3 for p in parts)
+    # unequal / empty shards would bias the AVG all-reduce and poison it with the NaN mean of an empty shard: refused loudly
+    with pytest.raises(ValueError):
+        G.dist.shard_batch(torch.arange(10).view(10, 1), 0, 4)
+    with pytest.raises(ValueError):
+        G.dist.shard_batch(torch.arange(3).view(3, 1), 3, 4)
 
 
 def test_tensor_core_gemm_plan_fills_the_last_round_of_work_items():
