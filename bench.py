@@ -249,8 +249,6 @@ def main():
                     help="conditioner GEMM engine: fp32 FFMA, tensor-core 3xTF32 (fp32-equivalent) or single-pass TF32")
     ap.add_argument("--umnn-engine", default="auto", choices=["auto", "fused", "layerwise"],
                     help="strict UMNN integral: fused FFMA kernels, layer-wise passes on the GEMM engine, or auto")
-    ap.add_argument("--dag-l1", default="resident", choices=["resident", "generic"],
-                    help="DAG layer 1 of narrow flows: gate tile resident in shared memory (default) or the functor-loader tile GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="train mode: skip the additional log-lik eval measurement")
     ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
@@ -351,7 +349,6 @@ def main():
         the roofline object are then taken from a short eager pass first (a replay has no per-launch host hooks)."""
         G.ops.set_gemm_mode(gemm)
         G.ops.UMNN_ENGINE = args.umnn_engine
-        G._lib.lib().gnf_dag_l1_set_resident(1 if args.dag_l1 == "resident" else 0)
         for n in model.getNormalizers():
             if hasattr(n, "nb_steps"):
                 n.nb_steps = S_

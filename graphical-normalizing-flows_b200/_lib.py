@@ -18,7 +18,8 @@ GATE_TABLE, GATE_GUMBEL, GATE_NOISER = 0, 1, 2
 IMP_RAW, IMP_SOFT, IMP_HARD_SOFT, IMP_HARD_SQ = 0, 1, 2, 3
 
 _lib = None
-# Set only by tests/emu (host SIMT simulator build of the same kernels, CPU tensors). Never set by the product.
+# True only while tests/emu/sim_hook.py has swapped in the host SIMT-simulator build of the same kernels (CPU tensors): the
+# argument checks then accept CPU tensors.  Nothing in the product sets it.
 _SIMULATOR = False
 
 
@@ -94,24 +95,13 @@ _PROTOS = {
                          _P, _SZ, _P], C.c_int),
     "gnf_umnn_tc3_workspace_bytes": ([C.POINTER(MlpT), _I], _SZ),
     "gnf_umnn_fwd_tc3": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
-    "gnf_umnn_lw_set_rw": ([_I], C.c_int),
     "gnf_linear_rw_workspace_bytes": ([_I, _I], _SZ),
     "gnf_linear_wgrad_rw_workspace_bytes": ([_I, _I], _SZ),
     "gnf_linear_wgrad_rw": ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
-    "gnf_linear_wgrad_rw_set_trace": ([_P], C.c_int),
-    "gnf_linear_rw_set_trace": ([_P], C.c_int),
-    "gnf_linear_rw_set_debug": ([_I], C.c_int),
     "gnf_linear_fwd_rw": ([_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
     "gnf_linear_dgrad_rw": ([_P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
-    "gnf_tc_gemm_set_tma": ([_I], C.c_int),
-    "gnf_tc_gemm_set_fold": ([_I], C.c_int),
-    "gnf_tc_gemm_set_tile": ([_I, _I], C.c_int),
-    "gnf_dag_l1_set_resident": ([_I], C.c_int),
     "gnf_tc_gemm_plan": ([_I, _I, _I, _I, _I, _P, _P], C.c_int),
-    "gnf_tc_gemm_set_trace": ([_P], C.c_int),
     "gnf_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
-    "gnf_tc_probe": ([_I, _I, _P, _P], C.c_int),
-    "gnf_tc_set_trace": ([_P], C.c_int),
     "gnf_reverse_cols": ([_P, _P, _I, _I, _P], C.c_int),
     "gnf_broadcast_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_counter_add": ([_P, C.c_uint64, _P], C.c_int),
@@ -146,19 +136,6 @@ def lib():
     if _lib is None:
         _lib = load_library()
     return _lib
-
-
-def _install_simulator_for_tests(path):
-    """tests/emu only: route calls to the host SIMT-simulator build of the same .cu sources."""
-    global _lib, _SIMULATOR
-    _lib = _bind(C.CDLL(path))
-    _SIMULATOR = True
-
-
-def _uninstall_simulator_for_tests():
-    global _lib, _SIMULATOR
-    _lib = None
-    _SIMULATOR = False
 
 
 def check(rc):

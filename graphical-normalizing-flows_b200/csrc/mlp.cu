@@ -806,10 +806,12 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   return check_launch("gnf_dag_l1_dgrad");
 }
 
+#ifdef GNF_DEVTOOLS
 int gnf_dag_l1_set_resident(int enable) {
   g_dag_l1_resident = enable != 0;
   return 0;
 }
+#endif
 
 int gnf_dag_finish_dA(const float* dP, const float* dPdA, float* dA, int d, int accumulate, gnf_stream_t stream) {
   if (!dP || !dPdA || !dA || d <= 0) return fail(GNF_ERR_INVALID, "gnf_dag_finish_dA: bad arguments");

@@ -810,6 +810,7 @@ int gnf_linear_tc_ps2(int op, const float* A_hi, const float* A_lo, int lda, con
 #endif
 }
 
+#ifdef GNF_DEVTOOLS
 int gnf_tc_gemm_set_trace(long long* buf) {
 #ifdef GNF_EMU
   (void)buf;
@@ -819,7 +820,9 @@ int gnf_tc_gemm_set_trace(long long* buf) {
   return 0;
 #endif
 }
+#endif
 
+#ifdef GNF_DEVTOOLS
 int gnf_tc_gemm_set_fold(int chunks) {
 #ifdef GNF_EMU
   (void)chunks;
@@ -830,7 +833,9 @@ int gnf_tc_gemm_set_fold(int chunks) {
   return 0;
 #endif
 }
+#endif
 
+#ifdef GNF_DEVTOOLS
 int gnf_tc_gemm_set_tile(int bn, int splits) {
 #ifdef GNF_EMU
   (void)bn; (void)splits;
@@ -843,6 +848,7 @@ int gnf_tc_gemm_set_tile(int bn, int splits) {
   return 0;
 #endif
 }
+#endif
 
 int gnf_tc_gemm_plan(int M, int N, int K, int passes, int wgrad, int* bn, int* splits) {
 #ifdef GNF_EMU
@@ -855,6 +861,7 @@ int gnf_tc_gemm_plan(int M, int N, int K, int passes, int wgrad, int* bn, int* s
 #endif
 }
 
+#ifdef GNF_DEVTOOLS
 int gnf_tc_gemm_set_tma(int enable) {
 #ifdef GNF_EMU
   (void)enable;
@@ -864,6 +871,7 @@ int gnf_tc_gemm_set_tma(int enable) {
   return 0;
 #endif
 }
+#endif
 
 int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K, int passes,
                         gnf_stream_t stream) {

@@ -87,6 +87,12 @@ struct RwTrace {
 };
 
 // NB = NP / 32 output column blocks, NCH = ceil(KP / 32) input column chunks (compile time: whole rows live in registers).
+// ablation bits (skip stores / loads / MMAs) exist in the development build only
+#ifdef GNF_DEVTOOLS
+#define RW_DEBUG (p.debug)
+#else
+#define RW_DEBUG 0
+#endif
 template <int NB, int NCH>
 __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) {
   using namespace tc;
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
         for (int c = 0; c < NCH; ++c) {
           mbar_wait(&a_full[c], (uint32_t)(tl & 1));
           fence_after_sync();
-          const int k0 = c * 4, k1 = (p.debug & 4) ? k0 + (c == 0 ? 1 : 0) : ((k0 + 4 < nksteps) ? k0 + 4 : nksteps);
+          const int k0 = c * 4, k1 = (RW_DEBUG & 4) ? k0 + (c == 0 ? 1 : 0) : ((k0 + 4 < nksteps) ? k0 + 4 : nksteps);
           if (split) {
             for (int kk = k0; kk < k1; ++kk) mma_tf32_ts_w(tD, tAlo + kk * 8, dhi0 + dstep * kk, idesc, (c == 0 && kk == k0) ? 0u : 1u);
             for (int kk = k0; kk < k1; ++kk) mma_tf32_ts_w(tD, tAhi + kk * 8, dlo0 + dstep * kk, idesc, 1u);
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
           }
           trm.stamp();
         }
-        if (split && !(p.debug & 4))
+        if (split && !(RW_DEBUG & 4))
           for (int kk = 0; kk < nksteps; ++kk) mma_tf32_ts_w(tD, tAhi + kk * 8, dhi0 + dstep * kk, idesc, 1u);
         mma_commit_w(a_empty);
         mma_commit_w(d_full);
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
     // the wgrad loader: 100 clocks per load to issue).  Rows past M and prefetches past the end read valid memory whose
     // values are never used: rows >= M are never stored by the epilogue.
     auto issue = [&](long long tl, int c) {
-      if (p.debug & 2) {
+      if (RW_DEBUG & 2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) rw_gemm_kernel(RwGemmParams p) 
         for (int i = 0; i < 8; ++i) {
           const int R = 4 * i + sub;
           const uint4 q = *reinterpret_cast<const uint4*>(stage + R * 32 + 4 * (piece ^ (R & 7)));
-          if (row0 + 4 * i < p.M && !(p.debug & 1)) *reinterpret_cast<uint4*>(p.C + (row0 + 4 * i) * p.ldc + c + 4 * piece) = q;
+          if (row0 + 4 * i < p.M && !(RW_DEBUG & 1)) *reinterpret_cast<uint4*>(p.C + (row0 + 4 * i) * p.ldc + c + 4 * piece) = q;
         }
         __syncwarp();
         tr.stamp();
@@ -415,6 +421,7 @@ size_t gnf_linear_rw_workspace_bytes(int N, int K) {
 #endif
 }
 
+#ifdef GNF_DEVTOOLS
 int gnf_linear_rw_set_debug(int bits) {
 #ifndef GNF_EMU
   gnf::g_rw_debug = bits;
@@ -423,7 +430,9 @@ int gnf_linear_rw_set_debug(int bits) {
 #endif
   return 0;
 }
+#endif
 
+#ifdef GNF_DEVTOOLS
 int gnf_linear_rw_set_trace(long long* buf) {
 #ifndef GNF_EMU
   gnf::g_rw_trace = buf;
@@ -432,6 +441,7 @@ int gnf_linear_rw_set_trace(long long* buf) {
 #endif
   return 0;
 }
+#endif
 
 int gnf_linear_fwd_rw(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, uint32_t* bits_out,
                       int M, int N, int K, int relu, int passes, void* work, size_t work_bytes, gnf_stream_t stream) {

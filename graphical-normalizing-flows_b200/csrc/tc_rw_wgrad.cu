@@ -365,6 +365,7 @@ size_t gnf_linear_wgrad_rw_workspace_bytes(int N, int K) {
 #endif
 }
 
+#ifdef GNF_DEVTOOLS
 int gnf_linear_wgrad_rw_set_trace(long long* buf) {
 #ifndef GNF_EMU
   gnf::g_wg_trace = buf;
@@ -373,6 +374,7 @@ int gnf_linear_wgrad_rw_set_trace(long long* buf) {
 #endif
   return 0;
 }
+#endif
 
 int gnf_linear_wgrad_rw(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K, int passes,
                         void* work, size_t work_bytes, gnf_stream_t stream) {

@@ -715,6 +715,7 @@ int gnf_umnn_fwd_tc(const float* x, const float* h, const gnf_mlp_t* net, int S,
 #endif
 }
 
+#ifdef GNF_DEVTOOLS
 /* Debug: subsequent gnf_umnn_fwd_tc calls record SM-clock stamps of CTA 0's phases into `buf`
  * (48 x 8 x int64, device); NULL disables.  Not thread safe; measurement tool only. */
 int gnf_tc_set_trace(long long* buf) {
@@ -725,7 +726,9 @@ int gnf_tc_set_trace(long long* buf) {
 #endif
   return 0;
 }
+#endif
 
+#ifdef GNF_DEVTOOLS
 /* Measurement tool: see tc_probe_kernel.  out: 4 x int64 (device). */
 int gnf_tc_probe(int mode, int iters, long long* out, gnf_stream_t stream) {
 #ifdef GNF_EMU
@@ -737,6 +740,7 @@ int gnf_tc_probe(int mode, int iters, long long* out, gnf_stream_t stream) {
   return check_launch("gnf_tc_probe");
 #endif
 }
+#endif
 
 /* C[128,N] = A[128,K] W[N,K]^T on one CTA through tcgen05 (mode 0: A staged in TMEM, mode 1: A in shared memory). */
 int gnf_tc_selftest(const float* A, const float* W, float* C, int N, int K, int mode, gnf_stream_t stream) {

@@ -472,11 +472,13 @@ using namespace gnf;
 
 extern "C" {
 
+#ifdef GNF_DEVTOOLS
 int gnf_umnn_lw_set_rw(int enable) {
   g_lw_use_rw = (enable & 1) != 0;
   g_lw_use_rw_wgrad = (enable & 1) != 0 && (enable & 2) == 0;      // 1: everything resident; 3: forward/dgrad only; 0: generic engine
   return 0;
 }
+#endif
 
 size_t gnf_umnn_lw_saved_floats(const gnf_mlp_t* net, int R, int S, int train) {
   LwPlan pl;

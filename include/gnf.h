@@ -13,7 +13,9 @@
  *  - all entry points are asynchronous on `stream` (a cudaStream_t) and re-entrant;
  *  - return 0 on success, non-zero on error (a cudaError_t value, or GNF_ERR_*);
  *    gnf_last_error() gives a thread-local message; an unsupported shape / mode is an
- *    error, never a silent fallback.
+ *    error, never a silent fallback;
+ *  - the product library has NO process-global switches: measurement knobs (traces, ablation bits, tiling / engine overrides)
+ *    exist only in the development build (-DGNF_DEVTOOLS, libgnf_sm100_dev.so, declared in include/gnf_devtools.h).
  */
 #ifndef GNF_H_
 #define GNF_H_
@@ -133,21 +135,9 @@ int gnf_linear_dgrad_tc_ps(const float* dY, int lddy, const float* W_hi, const f
 int gnf_linear_tc_ps2(int op, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                       const float* bias, int bias_period, const float* act, int ldact, float* C, int ldc, int M, int N, int K,
                       int relu, gnf_stream_t stream);
-/* Measurement switch: 0 makes the tensor-core GEMM stage every operand with cp.async (the path taken anyway by operands
- * whose base / leading dimension are not 16-byte aligned) instead of TMA tensor maps.  Default 1. */
-int gnf_tc_gemm_set_tma(int enable);
-/* Measurement switch: force the tensor-core GEMM's tile width (64, 96, ... 256 columns; 3xTF32 is capped at 160) and / or the
- * split-K factor of the wgrad orientation; 0 = planned per shape (fill of the last round of work items over the SMs). */
-int gnf_tc_gemm_set_tile(int bn, int splits);
 /* Host-only query of that plan for a GEMM of M x N outputs reduced over K (wgrad != 0: the split-K orientation, where M x N is
  * the weight shape and K the number of rows): writes the tile width and the split-K factor the engine would use. */
 int gnf_tc_gemm_plan(int M, int N, int K, int passes, int wgrad, int* bn, int* splits);
-/* 3xTF32 accuracy knob: k-chunks (of 32) accumulated inside the tensor core (round-toward-zero accumulation) before the
- * partial sum is folded into a round-to-nearest running sum.  Default 2; a huge value disables folding. */
-int gnf_tc_gemm_set_fold(int chunks);
-/* Measurement: later tensor-core GEMM launches write SM-clock stamps of CTA 0's warp roles into buf (8 x 256 int64, device;
- * rows: TMA issue, stager landed, stager published, MMA chunk ready, MMA tile committed, epilogue start, epilogue end). */
-int gnf_tc_gemm_set_trace(long long* buf);
 
 /* MaskedLinear's `mask * weight` (AutoregressiveConditioner.py:24-25) fused with the output-row
  * permutation that turns MADE's view(B,out,d).permute(0,2,1) (:108-109) into a plain row-major
@@ -205,9 +195,6 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
  * dx [B,d] and dP [d,d] are zero-filled by the call. */
 int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const float* x, const float* P,
                      const gnf_gate_t* gate, float* dx, float* dP, int B, int d, int N, gnf_stream_t stream);
-/* Measurement switch: 1 (default) = narrow flows (d <= 64) run layer 1 on the kernels that keep the gate tile of a row block
- * resident in shared memory (every gate evaluated once per direction); 0 = functor-loader tile GEMM for every d. */
-int gnf_dag_l1_set_resident(int enable);
 /* dA[i,j] (+)= dP[i,j]*dPdA[i,j]. */
 int gnf_dag_finish_dA(const float* dP, const float* dPdA, float* dA, int d, int accumulate, gnf_stream_t stream);
 /* Debug / parity hook: materialise the in-kernel Philox draws for (seed, offset) as [B,d,d] tensors. */
@@ -314,9 +301,6 @@ int gnf_dag_loss_fwd(const float* A, int d, const float* t, const float* lambd, 
 int gnf_dag_loss_bwd(const float* A, int d, const float* t, const float* lambd, const float* c, const float* dag_const,
                      const float* l1_weight, const float* gout, float* dA, float* dt, gnf_stream_t stream);
 
-/* Measurement switch: 0 routes the layer-wise engine's hidden GEMMs to the generic tensor-core engine (gnf_linear_*_tc)
- * instead of the resident-weight kernels below; 3 keeps forward/dgrad resident but runs wgrad on the generic engine.  Default 1. */
-int gnf_umnn_lw_set_rw(int enable);
 
 /* Resident-weight tensor-core layer GEMM (tc_rw.cu) -- the hidden x hidden layers of IntegrandNet
  * (MonotonicNormalizer.py:12-38) over all quadrature node-rows, forward and dgrad.  The layer's weights (N, K <= 160) are
@@ -327,11 +311,6 @@ int gnf_umnn_lw_set_rw(int enable);
  * bits_out (nullable): ReLU bit mask of Y, [M][round_up(N,32)/32] words; mask_bits (nullable, same layout) or act select
  * the ReLU mask of dgrad.  work: gnf_linear_rw_workspace_bytes(N, K) bytes (0 = shape unsupported, see gnf_last_error). */
 size_t gnf_linear_rw_workspace_bytes(int N, int K);
-/* Measurement: later resident-weight GEMM launches write SM-clock stamps of CTA 0 into buf (4 x 256 int64, device; rows:
- * MMA issuer, loader of even chunks, loader of odd chunks, epilogue).  NULL disables. */
-int gnf_linear_rw_set_trace(long long* buf);
-/* Measurement: bit0 skips the kernel's global stores, bit1 its global loads, bit2 its MMAs (results are then garbage). */
-int gnf_linear_rw_set_debug(int bits);
 int gnf_linear_fwd_rw(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, uint32_t* bits_out,
                       int M, int N, int K, int relu, int passes, void* work, size_t work_bytes, gnf_stream_t stream);
 int gnf_linear_dgrad_rw(const float* dY, int lddy, const float* W, int ldw, const float* act, int ldact,
@@ -345,17 +324,9 @@ int gnf_linear_dgrad_rw(const float* dY, int lddy, const float* W, int ldw, cons
  * [M][round_up(K,32)] plane (ldx = round_up(K,32), 16-byte aligned) and is streamed once by bulk async copies; per-CTA partial
  * tiles in `work` (gnf_linear_wgrad_rw_workspace_bytes(N, K)) are summed by a second kernel (deterministic). */
 size_t gnf_linear_wgrad_rw_workspace_bytes(int N, int K);
-/* Measurement: later gnf_linear_wgrad_rw launches write SM-clock stamps of CTA 0 into buf (3 x 256 int64, device; rows: MMA
- * issuer, first stager thread, first loader thread).  NULL disables. */
-int gnf_linear_wgrad_rw_set_trace(long long* buf);
 int gnf_linear_wgrad_rw(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
                         int passes, void* work, size_t work_bytes, gnf_stream_t stream);
 
-/* Measurement tool (not on the product path): TMEM-read bandwidth / MMA issue rate / overlap probe on one CTA.
- * mode bit0: stream tcgen05.ld; bit1: issue TF32 MMAs; out[0], out[1]: elapsed SM clocks of the two roles. */
-int gnf_tc_probe(int mode, int iters, long long* out, gnf_stream_t stream);
-/* Debug / measurement: later gnf_umnn_fwd_tc calls write per-phase SM-clock stamps of CTA 0 into buf (48*8 int64). */
-int gnf_tc_set_trace(long long* buf);
 /* Self-test of the tcgen05 conventions: C[128,N] = A[128,K] W[N,K]^T on one CTA (mode 0: A staged in TMEM,
  * mode 1: A staged in shared memory).  N, K <= 256. */
 int gnf_tc_selftest(const float* A, const float* W, float* C, int N, int K, int mode, gnf_stream_t stream);

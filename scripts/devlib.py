@@ -9,7 +9,19 @@ sys.path.insert(0, ROOT)
 import gnf_b200 as G  # noqa: E402
 
 _P, _I = C.c_void_p, C.c_int
+_F, _SZ = C.c_float, C.c_size_t
 DEV_PROTOS = {
+    "gnf_tc_gemm_set_tma": ([_I], C.c_int),
+    "gnf_tc_gemm_set_tile": ([_I, _I], C.c_int),
+    "gnf_tc_gemm_set_fold": ([_I], C.c_int),
+    "gnf_tc_gemm_set_trace": ([_P], C.c_int),
+    "gnf_dag_l1_set_resident": ([_I], C.c_int),
+    "gnf_umnn_lw_set_rw": ([_I], C.c_int),
+    "gnf_linear_rw_set_trace": ([_P], C.c_int),
+    "gnf_linear_rw_set_debug": ([_I], C.c_int),
+    "gnf_linear_wgrad_rw_set_trace": ([_P], C.c_int),
+    "gnf_tc_probe": ([_I, _I, _P, _P], C.c_int),
+    "gnf_tc_set_trace": ([_P], C.c_int),
     "gnf_umnn_tc3_set_trace": ([_P], C.c_int),
     "gnf_umnn_tc3_set_debug": ([_I], C.c_int),
 }

@@ -1,8 +1,12 @@
+import os
 """Tile-width / split-K sweep of the generic tcgen05 GEMM engine (run on the GPU box): forced tiles vs the planner."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gnf_b200 as G
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import devlib  # noqa: E402  (measurement knobs live in the -DGNF_DEVTOOLS build only)
+devlib.install()
 
 lib = G._lib.lib()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

@@ -1,3 +1,4 @@
+import os
 """Warp-role timeline of the tcgen05 GEMM engine (CTA 0) for one shape; run on the GPU box.
 usage: gemm_trace.py M N K op(fwd|dgrad|wgrad) passes(1|3)"""
 import sys, os
@@ -5,6 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import torch
 import gnf_b200 as G
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import devlib  # noqa: E402  (measurement knobs live in the -DGNF_DEVTOOLS build only)
+devlib.install()
 lib = G._lib.lib()
 M, N, K = (int(v) for v in sys.argv[1:4])
 op, passes = sys.argv[4], int(sys.argv[5])

@@ -1,8 +1,12 @@
+import os
 """Ablation timing of the resident-weight GEMM: which of loads / stores / MMAs bounds it (GPU box)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gnf_b200 as G
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import devlib  # noqa: E402  (measurement knobs live in the -DGNF_DEVTOOLS build only)
+devlib.install()
 lib = G._lib.lib()
 M, N, K = 1419264, 150, 150
 X = torch.zeros(M, 160, device="cuda"); X[:, :K] = torch.randn(M, K, device="cuda")

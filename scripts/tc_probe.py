@@ -1,9 +1,13 @@
+import os
 """TMEM-read bandwidth / TF32 MMA rate / overlap probe (run on the GPU box)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import torch
 import gnf_b200 as G
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import devlib  # noqa: E402  (measurement knobs live in the -DGNF_DEVTOOLS build only)
+devlib.install()
 lib = G._lib.lib()
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
 iters = 200

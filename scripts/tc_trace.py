@@ -1,9 +1,13 @@
+import os
 """Phase timeline of the two-tile tcgen05 UMNN forward kernel (CTA 0), run on the GPU box."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import torch
 import gnf_b200 as G
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import devlib  # noqa: E402  (measurement knobs live in the -DGNF_DEVTOOLS build only)
+devlib.install()
 lib = G._lib.lib()
 model = G.build_from_spec(G.CONFIGS["cfg4"], "cuda", seed=0)
 for n in model.getNormalizers():

@@ -9,6 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import gnf_b200 as G  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import devlib  # noqa: E402  (measurement knobs live in the -DGNF_DEVTOOLS build only)
+devlib.install()
 import gnf_oracle as O  # noqa: E402
 
 

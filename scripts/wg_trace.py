@@ -1,9 +1,13 @@
+import os
 """Warp-role timeline of the resident wgrad kernel (CTA 0); run on the GPU box.  usage: wg_trace.py M N K passes"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import torch
 import gnf_b200 as G
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import devlib  # noqa: E402  (measurement knobs live in the -DGNF_DEVTOOLS build only)
+devlib.install()
 lib = G._lib.lib()
 M, N, K, passes = (int(v) for v in sys.argv[1:5])
 NPn, KP = (N + 31) // 32 * 32, (K + 31) // 32 * 32

@@ -10,6 +10,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 
 import gnf_b200 as G
+import sim_hook
 from helpers import golden_names
 import parity
 
@@ -18,9 +19,9 @@ import parity
 def emu():
     import build_emu
     path = build_emu.build()
-    G._lib._install_simulator_for_tests(path)
+    sim_hook.install(path)
     yield
-    G._lib._uninstall_simulator_for_tests()
+    sim_hook.uninstall()
 
 
 @pytest.mark.parametrize("name", golden_names())

@@ -332,7 +332,15 @@ def test_rw_gemm_unsupported_width_is_loud():
 
 def test_umnn_layerwise_rw_and_generic_engines_agree(umnn_engine):
     """Same layer-wise step through the resident-weight kernel and through the generic tensor-core engine."""
+    import ctypes as C
+    import os
     import model_vs_oracle as M
+    dev_so = os.path.join(os.path.dirname(G._lib.LIB_PATH), "libgnf_sm100_dev.so")
+    if not os.path.isfile(dev_so):
+        pytest.skip("engine override is a development-build knob (build.py --dev): libgnf_sm100_dev.so not built")
+    devlib = C.CDLL(dev_so)          # the knob is process-global state of THAT library: route the package through it for this test
+    product = G._lib._lib
+    G._lib._lib = G._lib._bind(devlib)
     umnn_engine("layerwise", "tf32x3")
     model = M.build(M.CONFIGS["cfg4"], "cuda")
     parity.set_modes(model, dict(stoch_gate=False))
@@ -340,13 +348,14 @@ def test_umnn_layerwise_rw_and_generic_engines_agree(umnn_engine):
     outs = []
     try:
         for rw in (1, 0, 3):
-            G._lib.lib().gnf_umnn_lw_set_rw(rw)
+            devlib.gnf_umnn_lw_set_rw(rw)
             model.zero_grad()
             z, jac = model(x)
             model.loss(z, jac).backward()
             outs.append((z.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
     finally:
-        G._lib.lib().gnf_umnn_lw_set_rw(1)
+        devlib.gnf_umnn_lw_set_rw(1)
+        G._lib._lib = product
     for other in (1, 2):
         assert float((outs[0][0] - outs[other][0]).abs().max()) < 1e-4
         for k in outs[0][1]:

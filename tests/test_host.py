@@ -23,6 +23,20 @@ def _header_symbols():
     return sorted(set(re.findall(r"\b(gnf_[A-Za-z0-9_]+)\s*\(", src)))
 
 
+def test_product_library_has_no_measurement_knobs():
+    """The process-global switches (traces, ablation bits, tiling / engine overrides) live in the -DGNF_DEVTOOLS build only
+    (include/gnf_devtools.h): the product library neither declares nor exports them."""
+    import __graft_entry__
+    __graft_entry__.build()
+    lib = G._lib.load_library()
+    src = open(os.path.join(ROOT, "include", "gnf_devtools.h")).read()
+    knobs = sorted(set(re.findall(r"\b(gnf_[A-Za-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", src, flags=re.S))))
+    assert len(knobs) >= 10
+    for name in knobs:
+        assert not hasattr(lib, name), f"{name} is exported by the product library"
+        assert name not in G._lib.EXPORTED_SYMBOLS
+
+
 def test_library_exports_every_declared_symbol():
     import __graft_entry__
     __graft_entry__.build()
@@ -98,7 +112,8 @@ def _dp_worker(rank, world, port, emu_path, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
-    G._lib._install_simulator_for_tests(emu_path)
+    import sim_hook
+    sim_hook.install(emu_path)
     spec = dict(nb_flow=1, d=4, cond="DAG", hidden=[8, 8], out=3, hot_encoding=True, gumble_T=.5, l1=.1, norm="monotonic",
                 int_net=[6, 6], nb_steps=5, solver="CC")
     model = G.build_from_spec(spec, "cpu", seed=100 + rank)       # different init per rank on purpose
@@ -187,4 +202,3 @@ def test_tensor_core_gemm_plan_fills_the_last_round_of_work_items():
         b, s, _ = plan(M, N, K, p, w)
         assert b % 32 == 0 and 64 <= b <= (160 if p == 3 else 256) and s >= 1
     assert lib.gnf_tc_gemm_plan(0, 1, 1, 3, 0, C.byref(bn), C.byref(sp)) != 0
-    assert lib.gnf_tc_gemm_set_tile(100, 0) != 0 and lib.gnf_tc_gemm_set_tile(0, 0) == 0
