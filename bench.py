@@ -249,6 +249,11 @@ def main():
                     help="conditioner GEMM engine: fp32 FFMA, tensor-core 3xTF32 (fp32-equivalent) or single-pass TF32")
     ap.add_argument("--umnn-engine", default="auto", choices=["auto", "fused", "layerwise"],
                     help="strict UMNN integral: fused FFMA kernels, layer-wise passes on the GEMM engine, or auto")
+    ap.add_argument("--random-steps", action="store_true",
+                    help="train: S = nb_steps + U{0..9} per step as the reference's UCI driver does (UCIExperiments.py:131-133); one "
+                         "captured graph per S")
+    ap.add_argument("--allreduce", default="single", choices=["overlap", "single", "none"],
+                    help="N > 1: one flat bucket all-reduced after the backward (default); sub-buckets overlapped with the rest of the backward (measured slower: the NCCL CTAs displace CTAs of the 148-CTA persistent GEMMs); none = measurement only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="train mode: skip the additional log-lik eval measurement")
     ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
@@ -274,6 +279,9 @@ def main():
     config["gemm_engine"] = args.gemm
     config["umnn_engine"] = args.umnn_engine
     config["cuda_graph"] = args.cuda_graph in ("on", "auto")
+    config["allreduce"] = args.allreduce
+    if args.random_steps:
+        config["nb_steps"] = f"{S}+U{{0..9}} per step (UCIExperiments.py:131-133)"
 
     # ---------------- reference arm ----------------
     if args.impl == "reference":
@@ -300,7 +308,7 @@ def main():
     G.dist.decorrelate_gate_noise(model, rank)
     d = spec["d"]
     lr, wd = ADAM[cfg]
-    bucket = G.dist.GradBucket(model.parameters())
+    bucket = G.dist.GradBucket(model.parameters(), overlap=(args.allreduce == "overlap"))
     # the reference's optimizer (torch.optim.Adam(lr, weight_decay), UCIExperiments.py:100) as one multi-tensor launch per step
     opt = G.FusedAdam(model.parameters(), lr=lr, weight_decay=wd)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -328,7 +336,8 @@ def main():
         z, jac = model(x)
         loss = model.loss(z, jac)
         loss.backward()
-        bucket.finish_step()
+        if args.allreduce != "none":      # "none" = measurement only: ranks train independently (how much of the N-GPU step is the collective)
+            bucket.finish_step()
         opt.step()
         return loss
 
@@ -368,8 +377,28 @@ def main():
             eager_kflops = G.ops.collect_call_flops()
             G.ops.enable_kernel_timing(False)
             eager_launches = (G.ops.launch_count() - l0) // n_eager
-            if mode == "train":
-                step = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=True, warmup=3)
+            if mode == "train" and args.random_steps:
+                # the reference draws S per batch: the graph is keyed by S (GraphedTrainStep recaptures when nb_steps changes; here
+                # ten graphs are kept instead of recapturing)
+                import random
+                rnd = random.Random(1234 + rank)
+                graphs = {}
+
+                def step(x):
+                    Sx = S_ + rnd.randrange(10)
+                    for n in model.getNormalizers():
+                        if hasattr(n, "nb_steps"):
+                            n.nb_steps = Sx
+                    if Sx not in graphs:
+                        graphs[Sx] = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=2)
+                    return graphs[Sx](x)
+                for Sx in range(S_, S_ + 10):             # capture outside the timed region
+                    for n in model.getNormalizers():
+                        if hasattr(n, "nb_steps"):
+                            n.nb_steps = Sx
+                    graphs[Sx] = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=2)
+            elif mode == "train":
+                step = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=3)
             else:
                 graphed_eval = G.GraphedEvalStep(model, pool[0], warmup=3)
                 step = lambda x: graphed_eval(x)[0].mean()
@@ -438,13 +467,36 @@ def main():
                                            "3x the achieved figure") +
                                         "; the same kernel also runs the wgrad GEMMs inside the layer-wise UMNN backward, which are "
                                         "timed with that composite call, not here")))
+        if spec["cond"] == "DAG":
+            # DAG layer 1 (K1): gnf_dag_l1_{fwd,wgrad,dgrad} = one kernel each, 2*B*d*d*H1 FLOPs (the one-hot half is a bias gather)
+            H1 = spec["hidden"][0]
+            for kname, kern in (("gnf_dag_l1_fwd", "dag_l1_fwd_kernel"), ("gnf_dag_l1_wgrad", "dag_l1_wgrad_kernel"), ("gnf_dag_l1_dgrad", "dag_l1_dgrad_kernel")):
+                if not ktimes.get(kname):
+                    continue
+                ms, n = sum(ktimes[kname]), len(ktimes[kname])
+                cands.append(dict(kernel=kern, entries=[kname], flops_per_launch=2. * B * d * d * H1, avg_launch_ms=ms / n,
+                                  launches_per_step=n / n_timed, ms_per_step=ms / n_timed,
+                                  note="DAG masked embedding fused into layer 1: strict-fp32 FFMA kernel, the gate (Philox + Gumbel "
+                                       "sigmoid) is generated on chip; the fp32 CUDA-core ceiling is ~74 TFLOP/s, the fraction is quoted "
+                                       "against the measured bf16 tensor peak as the contract asks"))
         if spec["norm"] == "monotonic":
             for kname, bwd in (("gnf_umnn_bwd", True), ("gnf_umnn_bwd_lw", True), ("gnf_umnn_fwd", False), ("gnf_umnn_fwd_lw", False),
-                               ("gnf_umnn_fwd_tc", False)):
-                if not ktimes.get(kname) or (mode == "train" and not bwd):
+                               ("gnf_umnn_fwd_tc", False), ("gnf_umnn_fwd_tc3", False)):
+                if not ktimes.get(kname) or (mode == "train" and not bwd and kname != "gnf_umnn_fwd_tc3"):
                     continue
                 ms = sum(ktimes[kname])
                 n = len(ktimes[kname])
+                if kname == "gnf_umnn_fwd_tc3":
+                    nodes = S_ + (2 if mode == "train" else 1)
+                    I = list(spec["int_net"])
+                    fl = 2. * B * d * (nodes * (I[0] + sum(a * b for a, b in zip(I[:-1], I[1:])) + I[-1]) + spec["out"] * I[0])
+                    cands.append(dict(kernel="umnn_fwd_tc3_kernel", entries=[kname], flops_per_launch=fl, avg_launch_ms=ms / n,
+                                      launches_per_step=n / n_timed, ms_per_step=ms / n_timed,
+                                      note="fused strict UMNN forward: tcgen05 kind::tf32 in 3xTF32 (3 tensor-core passes per algorithmic "
+                                           "FLOP), activation chain resident in TMEM, hidden weights streamed as pre-split hi/lo K-chunks; "
+                                           "the call also runs the pack kernel and the once-per-row conditioning GEMM; training stores "
+                                           "the three activation planes (267 MB at cfg4 B=100) for the layer-wise backward"))
+                    continue
                 note = ("tcgen05 kind::tf32 kernel, activation chain resident in TMEM (the TF32 dense peak is half the bf16 peak the "
                         "fraction is quoted against)" if kname.endswith("_tc") else
                         "layer-wise engine: ONE C-ABI call = per-layer launches (hidden GEMMs on tcgen05 in 3xTF32: rw_gemm_kernel for "
@@ -471,7 +523,19 @@ def main():
                 others.append({k: obj[k] for k in ("kernel", "achieved", "frac", "avg_launch_ms", "launches_per_step", "share_of_step")})
         if roofline is not None and others:
             roofline["other_kernels"] = others
-        return {"value": world * B * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps,
+        # ---- K4 (HBM-bound elementwise + row reductions): algorithmic bytes / CUDA-event duration of the call (forward
+        #      16*B*d + 8*B bytes, backward the same order) against the measured copy bandwidth
+        peak_gbs = peaks.get("hbm_gbs", 6650.)
+        k4 = []
+        for kname, nbytes in (("gnf_affine_fwd", 16. * B * d + 8. * B), ("gnf_affine_bwd", 24. * B * d + 4. * B),
+                              ("gnf_normal_ll_fwd", 4. * B * d + 8. * B), ("gnf_normal_ll_bwd", 8. * B * d + 8. * B)):
+            if ktimes.get(kname):
+                ms = sum(ktimes[kname]) / len(ktimes[kname])
+                k4.append({"bound": "hbm", "kernel": kname, "achieved": nbytes / (ms / 1e3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                           "frac": nbytes / (ms / 1e3) / 1e9 / peak_gbs, "bytes_per_launch": nbytes, "avg_launch_ms": ms,
+                           "note": "eager call bracketed by CUDA events: at this size the call is launch-latency bound (see "
+                                   "profiles/r02*_k4_roofline.json for the same kernels at sizes beyond L2)" if nbytes < 64e6 else ""})
+        return {"value": world * B * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps, "k4_roofline": k4,
                 "e2e": {"value": world * B * steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": B * d * 4,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -506,7 +570,7 @@ def main():
             "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "roofline": main_res["roofline"],
             "cpu_baseline": cpu_baseline, "achieved_tflops_step": main_res["achieved_tflops_step"],
             "algorithmic_gflop_per_step": main_res["algorithmic_gflop_per_step"], "last_loss": main_res["last_loss"],
-            "kernel_ms": main_res["kernel_ms"]}
+            "kernel_ms": main_res["kernel_ms"], "k4_roofline": main_res["k4_roofline"]}
     if extra is not None:
         line["eval"] = {"metric": "loglik_eval_samples_per_s", "unit": "samples/s",
                         "precision_mode": ("tf32 (tcgen05 UMNN forward + single-pass TF32 conditioner GEMMs), ll tolerance 2e-3"

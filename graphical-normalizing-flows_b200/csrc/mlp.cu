@@ -561,76 +561,6 @@ static inline int ew_blocks(size_t n) {
 
 using namespace gnf;
 
-#ifndef GNF_EMU
-namespace gnf {
-// Skinny forward  Y[M, N<=32] = act(X[M, K] W[N, K]^T + b)  for tall inputs (the conditioner's output layer: 6300 x 630 -> 30).
-// The 32x32x64 register tile of the generic engine leaves ~2.6 warps per SM on this shape (36 us for 0.24 GFLOP, latency
-// bound).  Here W^T stays in shared memory for the CTA's lifetime ([K][33]: lane n reads bank (k + n) % 32), a warp owns R rows
-// at a time, keeps their K-panel in registers (lane holds k = lane mod 32), and per k spends one LDS + R shuffles + R FMAs.
-constexpr int kSkinnyWarps = 8, kSkinnyR = 4, kSkinnyPanel = 256, kSkinnyMaxK = 1024;
-__global__ void __launch_bounds__(kSkinnyWarps * 32) skinny_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
-                                                                        const float* __restrict__ bias, int bias_period, float* __restrict__ Y,
-                                                                        int ldy, int M, int N, int K, int relu) {
-  GNF_SMEM(float, Ws);                                       // [K][33]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int n = warp; n < 32; n += kSkinnyWarps)
-    for (int k = lane; k < K; k += 32) Ws[k * 33 + n] = (n < N) ? __ldg(W + (size_t)n * ldw + k) : 0.f;
-  __syncthreads();
-  const int groups = (M + kSkinnyR - 1) / kSkinnyR;
-  for (int gidx = blockIdx.x * kSkinnyWarps + warp; gidx < groups; gidx += gridDim.x * kSkinnyWarps) {
-    const int r0 = gidx * kSkinnyR;
-    float acc[kSkinnyR];
-#pragma unroll
-    for (int r = 0; r < kSkinnyR; ++r) acc[r] = 0.f;
-    for (int kp = 0; kp < K; kp += kSkinnyPanel) {
-      float xr[kSkinnyR][kSkinnyPanel / 32];
-#pragma unroll
-      for (int r = 0; r < kSkinnyR; ++r) {
-        const int row = (r0 + r < M) ? r0 + r : M - 1;       // clamped address, masked at the store
-#pragma unroll
-        for (int j = 0; j < kSkinnyPanel / 32; ++j) {
-          const int k = kp + j * 32 + lane;
-          xr[r][j] = (k < K) ? __ldg(X + (size_t)row * ldx + k) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kSkinnyPanel / 32; ++j) {
-        const int kb = kp + j * 32;
-        if (kb >= K) break;
-        const int kn = (K - kb < 32) ? K - kb : 32;
-        const float* wp = Ws + (size_t)kb * 33 + lane;
-        if (kn == 32) {
-#pragma unroll 8
-          for (int jj = 0; jj < 32; ++jj) {
-            const float w = wp[jj * 33];
-#pragma unroll
-            for (int r = 0; r < kSkinnyR; ++r) acc[r] = fmaf(__shfl_sync(0xffffffffu, xr[r][j], jj), w, acc[r]);
-          }
-        } else {
-          for (int jj = 0; jj < kn; ++jj) {
-            const float w = wp[jj * 33];
-#pragma unroll
-            for (int r = 0; r < kSkinnyR; ++r) acc[r] = fmaf(__shfl_sync(0xffffffffu, xr[r][j], jj), w, acc[r]);
-          }
-        }
-      }
-    }
-    if (lane < N) {
-#pragma unroll
-      for (int r = 0; r < kSkinnyR; ++r) {
-        const int row = r0 + r;
-        if (row < M) {
-          float v = acc[r] + (bias ? __ldg(bias + (size_t)(row % bias_period) * N + lane) : 0.f);
-          if (relu) v = fmaxf(v, 0.f);
-          Y[(size_t)row * ldy + lane] = v;
-        }
-      }
-    }
-  }
-}
-}  // namespace gnf
-#endif
-
 extern "C" {
 
 int gnf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, int bias_period, float* Y,
@@ -638,19 +568,6 @@ int gnf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float
   if (!X || !W || !Y || M < 0 || N <= 0 || K <= 0 || ldx < K || ldw < K || ldy < N) return fail(GNF_ERR_INVALID, "gnf_linear_fwd: bad arguments");
   if (M == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-#ifndef GNF_EMU
-  if (N <= 32 && K <= kSkinnyMaxK && M >= 2048) {            // tall and skinny: W^T resident in shared memory
-    const size_t smem = (size_t)K * 33 * sizeof(float);
-    const int groups = (M + kSkinnyR - 1) / kSkinnyR;
-    int per_sm = (int)((200 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
-    int grid = (groups + kSkinnyWarps - 1) / kSkinnyWarps;
-    if (grid > per_sm * kNumSMs) grid = per_sm * kNumSMs;
-    cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    GNF_LAUNCH(skinny_fwd_kernel, grid, kSkinnyWarps * 32, smem, s, X, ldx, W, ldw, bias, bias_period < 1 ? 1 : bias_period, Y, ldy, M, N, K, relu);
-    return check_launch("gnf_linear_fwd");
-  }
-#endif
   LoadRowMajorA al{X, ldx};
   LoadWeightT bl{W, ldw};
   EpiBiasAct epi{Y, ldy, bias, N, bias_period < 1 ? 1 : bias_period, relu};
