@@ -14,10 +14,14 @@ from .normalizers import AffineNormalizer, ELUPlus, IntegrandNet, MonotonicNorma
 from . import dist
 from .graphs import GraphedEvalStep, GraphedTrainStep
 from .configs import CONFIGS, build_from_spec
+from .image_flows import CIFAR10CNN, CNNormalizingFlow, MNISTCNN, buildCIFAR10NormalizingFlow, buildMNISTNormalizingFlow
 from .optim import FusedAdam
+from . import experiments
+from .experiments import compute_bpp, load_checkpoint, strip_data_parallel_prefix
 
 __all__ = [
-    "FusedAdam",
+    "CIFAR10CNN", "CNNormalizingFlow", "MNISTCNN", "buildCIFAR10NormalizingFlow", "buildMNISTNormalizingFlow",
+    "FusedAdam", "experiments", "compute_bpp", "load_checkpoint", "strip_data_parallel_prefix",
     "AutoregressiveConditioner", "Conditioner", "ConditionnalMADE", "CouplingConditioner", "CouplingMLP", "DAGConditioner",
     "DAGMLP", "MADE", "MaskedLinear", "FCNormalizingFlow", "MNIST_A_prior", "NormalLogDensity", "NormalizingFlow",
     "NormalizingFlowStep", "buildFCNormalizingFlow", "AffineNormalizer", "ELUPlus", "IntegrandNet", "MonotonicNormalizer",

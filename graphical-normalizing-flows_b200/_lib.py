@@ -94,6 +94,10 @@ _PROTOS = {
     "gnf_umnn_bwd_lw": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MlpGradT), _I, _I, _I,
                          _P, _SZ, _P], C.c_int),
     "gnf_umnn_tc3_workspace_bytes": ([C.POINTER(MlpT), _I], _SZ),
+    "gnf_umnn_tc3_saved_floats": ([C.POINTER(MlpT), _I, _I], _SZ),
+    "gnf_umnn_bwd_tc3_workspace_bytes": ([C.POINTER(MlpT), _I, _I], _SZ),
+    "gnf_umnn_bwd_tc3": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MlpGradT), _I, _I,
+                          _P, _SZ, _P], C.c_int),
     "gnf_umnn_fwd_tc3": ([_P, _P, C.POINTER(MlpT), _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P], C.c_int),
     "gnf_linear_rw_workspace_bytes": ([_I, _I], _SZ),
     "gnf_linear_wgrad_rw_workspace_bytes": ([_I, _I], _SZ),

@@ -73,10 +73,16 @@ class DAGConditioner(Conditioner):
         self.stoch_gate = True
         self.noise_gate = False
         in_net = in_size * 2 if hot_encoding else in_size
-        if isinstance(hidden, nn.Module):
-            raise NotImplementedError("DAGConditioner(hidden=<nn.Module>) (CNN embedding nets, SURVEY.md §8f rank 3) is "
-                                      "not covered by the fused kernel; there is no eager fallback")
-        self.embedding_net = DAGMLP(in_net, hidden, out_size, cond_in)
+        self._module_embedding = isinstance(hidden, nn.Module)
+        if self._module_embedding:
+            # an arbitrary embedding module (the reference's image flows pass MNISTCNN / CIFAR10CNN, DAGConditioner.py:38-39):
+            # the gated, masked copies e[b,i,:] = x[b,:] * G[b,i,:] are produced by the fused DAG layer-1 kernels run with an
+            # identity "first layer" (exact in fp32: one product by 1 plus zeros), then handed to the module as the reference does
+            self.embedding_net = hidden
+            self.register_buffer("_expand_weight", torch.eye(in_size), persistent=False)
+            self.register_buffer("_expand_bias", torch.zeros(in_size), persistent=False)
+        else:
+            self.embedding_net = DAGMLP(in_net, hidden, out_size, cond_in)
         self.gumble = True
         self.hutchinson = False
         self.gumble_T = gumble_T
@@ -175,6 +181,12 @@ class DAGConditioner(Conditioner):
         # context is accepted and ignored exactly like the reference (quirk Q8)
         gate = self._gate_spec(x)
         self._last_gate = gate          # lets tests dump the Philox draws this forward used
+        if self._module_embedding:
+            B, d = x.shape
+            e = ops.DagMlpFn.apply(x.contiguous(), self.A, gate, False, self._expand_weight, self._expand_bias).reshape(B * d, d)
+            if self.hot_encoding:       # DAGConditioner.py:155-166: the one-hot block goes in front of the embedding net
+                e = torch.cat((e, torch.eye(d, device=e.device, dtype=e.dtype).repeat(B, 1)), 1)
+            return self.embedding_net(e).view(B, d, -1)
         return ops.DagMlpFn.apply(x.contiguous(), self.A, gate, self.hot_encoding, *_stack_params(self.embedding_net.net))
 
     def _alpha_host(self):

@@ -433,6 +433,7 @@ __global__ void __launch_bounds__((4 * NB + 2) * 32, 1) umnn_fwd_tc3_kernel(U3Pa
             v[j4 + 0] = __float_as_uint(a0); v[j4 + 1] = __float_as_uint(a1); v[j4 + 2] = __float_as_uint(a2); v[j4 + 3] = __float_as_uint(a3);
           }
           ypart[ci * kU3Rows + t] = (y0 + y1) + (y2 + y3);
+          if (bits && cur.q < Q) bits[(size_t)l * Q * NB + (size_t)cur.q * NB + ci] = mask_word(v);   // mask of a_L: the fused backward starts from it
           if (p.saved) store_block(p.saved + (size_t)l * plane, v, cur.q);
           named_bar_sync(1, EW * 32);
           const bool cur_valid = cur.q < Q;
@@ -472,6 +473,431 @@ __global__ void __launch_bounds__((4 * NB + 2) * 32, 1) umnn_fwd_tc3_kernel(U3Pa
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
+// Backward chain (UMNN NeuralIntegral.backward's dgrad pass over all quadrature node-rows): from the cotangent of
+// the integrand's pre-ELU output down to the first layer, in ONE kernel with the same structure as the forward:
+//   delta_L = (g_q w_L) o relu'(a_L)            generated in registers from the saved ReLU bit mask of a_L and the saved y
+//   delta_l = (delta_{l+1} W_l) o relu'(a_l)    l = L-1 .. 1: 3xTF32 tcgen05 GEMMs, A = delta in TMEM, W_l^T streamed as hi/lo chunks
+// What leaves the chip: the delta_l planes the weight-gradient GEMMs (tc_rw_wgrad.cu) consume (l >= 2), the column sums
+// db_{l-1} = sum_q delta_l, and the first-layer reductions D[r] = sum_k delta_1[(r,k)], dW0[:,0] = sum_q delta_1[q] t_q,
+// dx[r] = delta_1[(r,S+1)] . W0[:,0] + jac[r] gz[r] -- taken with warp shuffles (16 columns x 32 rows per pass) and atomics.
+// Replaces two resident-weight dgrad GEMMs, the colsum pass and the layer-1 reduction pass of gnf_umnn_bwd_lw.
+// =====================================================================================================================
+struct U3BParams {
+  const float *x, *ccw, *ccn, *jac, *gz, *gzrev, *gjac, *glogdet, *image, *saved;
+  float* dplanes;                       // [L-2][Q][NP]: delta_{L-1} .. delta_2 (delta_l at plane L-1-l)
+  float *D, *dx, *dW0;                  // D [R][NP], dx [R], dW0 = W0 gradient (column 0 written, row stride ldw0): atomic accumulation
+  float* db[GNF_MAX_LAYERS];            // db[l-1] for l = 2..L-1 (atomic)
+  int R, d, E, S, nodes, L, ldw0;
+  long long Q;
+  int dims[GNF_MAX_LAYERS + 1];
+  int kp[GNF_MAX_LAYERS], nch[GNF_MAX_LAYERS];      // per GEMM layer l: reduction = dims[l+1] padded to 8, its 32-chunks
+  unsigned off_img[GNF_MAX_LAYERS], off_tail, chunk_floats;
+};
+
+// sum over the 32 lanes of each of 16 columns held as w[16]; lane i (and i + 16) ends with column (i & 15)
+__device__ __forceinline__ float u3_colsum16(float (&w)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] += __shfl_xor_sync(0xffffffffu, w[i], 16);
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? w[i] : w[i + o];
+      const float keep = up ? w[i + o] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return w[0];
+}
+
+template <int NB>
+__global__ void __launch_bounds__((4 * NB + 2) * 32, 1) umnn_bwd_tc3_kernel(U3BParams p) {
+  using namespace tc;
+  constexpr int NP = NB * 32;
+  constexpr int EW = 4 * NB;
+  constexpr int NT = (EW + 2) * 32;
+  constexpr uint32_t kChunkBytes = 2u * 8u * NP * 16u;
+  constexpr uint32_t kHalfBytes = 8u * NP * 16u;
+  GNF_SMEM(float, smem);
+  float* ring = smem;
+  float* tail = ring + (size_t)kU3Stages * (kChunkBytes / 4);   // w_L[NP], W0[:,0][NP]
+  float* stage_all = tail + 2 * NP;
+  float* ccs = stage_all + EW * kU3StageBlock;                  // ccn, ccw
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ccs + 2 * kU3MaxNodes);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + kU3Stages;
+  uint64_t* a_full = w_empty + kU3Stages;
+  uint64_t* a_free = a_full + NB;
+  uint64_t* d_full = a_free + NB;
+  uint64_t* d_empty = d_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) {
+    for (int s = 0; s < kU3Stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int c = 0; c < NB; ++c) { mbar_init(&a_full[c], 4); mbar_init(&a_free[c], 1); }
+    mbar_init(d_full, 1);
+    mbar_init(d_empty, EW);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 2 * NP; i += NT) tail[i] = __ldg(p.image + p.off_tail + i);
+  for (int i = tid; i <= p.S; i += NT) { ccs[i] = __ldg(p.ccn + i); ccs[kU3MaxNodes + i] = __ldg(p.ccw + i); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int Q = (int)p.Q, nodes = p.nodes;
+  const int ntiles = (Q + kU3Rows - 1) / kU3Rows;
+  const int n_local = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int L = p.L;
+
+  if (warp == EW + 1) {
+    // ===================== producer: W_l^T chunks, l = L-1 .. 1 per tile =====================
+    if (lane == 0) {
+      int g = 0;
+      for (int tl = 0; tl < n_local; ++tl)
+        for (int l = L - 1; l >= 1; --l) {
+          const int nch = p.nch[l], nk = p.kp[l] / 8;
+          const char* src0 = reinterpret_cast<const char*>(p.image + p.off_img[l]);
+          for (int i = 0; i < 2 * nch; ++i, ++g) {                             // corrections first, then the a_hi * b_hi chain
+            const int c = i < nch ? i : i - nch;
+            const bool want_lo = i < nch;
+            const int ks = (nk - c * 4 < 4) ? nk - c * 4 : 4;
+            const uint32_t bytes = (uint32_t)ks * 2u * NP * 16u;
+            const int s = g % kU3Stages;
+            if (g >= kU3Stages) mbar_wait(&w_empty[s], (uint32_t)(((g / kU3Stages) - 1) & 1));
+            char* dst = reinterpret_cast<char*>(ring) + (size_t)s * kChunkBytes;
+            const char* src = src0 + (size_t)c * kChunkBytes;
+            mbar_expect_tx(&w_full[s], want_lo ? 2u * bytes : bytes);
+            bulk_g2s(dst, src, bytes, &w_full[s]);
+            if (want_lo) bulk_g2s(dst + kHalfBytes, src + kHalfBytes, bytes, &w_full[s]);
+          }
+        }
+    }
+  } else if (warp == EW) {
+    // ===================== MMA issuer (warp-converged) =====================
+    constexpr uint32_t idesc = make_idesc_tf32(kU3Rows, NP);
+    constexpr uint32_t dstep = (2u * NP * 16u) >> 4;
+    const uint32_t tAhi = tmem_base, tAlo = tmem_base + NP, tD = tmem_base + 2 * NP;
+    const uint32_t ring_addr = smem_u32(ring);
+    int g = 0, it = 0;
+    for (int tl = 0; tl < n_local; ++tl)
+      for (int l = L - 1; l >= 1; --l, ++it) {
+        const int nch = p.nch[l], nk = p.kp[l] / 8;
+        const bool release_a = (l == 1) && (tl + 1 < n_local);
+        if (it > 0) mbar_wait(d_empty, (uint32_t)((it - 1) & 1));
+        uint32_t acc = 0u;
+        for (int i = 0; i < 2 * nch; ++i, ++g) {
+          const int c = i < nch ? i : i - nch;
+          const bool corr = i < nch;
+          const int ks = (nk - c * 4 < 4) ? nk - c * 4 : 4;
+          const int s = g % kU3Stages;
+          if (corr) mbar_wait(&a_full[c], (uint32_t)(it & 1));
+          mbar_wait(&w_full[s], (uint32_t)((g / kU3Stages) & 1));
+          fence_after_sync();
+          const uint32_t base = ring_addr + (uint32_t)s * kChunkBytes;
+          const uint64_t dhi = make_smem_desc(base, NP * 16u, 128u), dlo = make_smem_desc(base + kHalfBytes, NP * 16u, 128u);
+          const uint32_t a0 = (uint32_t)c * 32u;
+          if (corr) {
+#pragma unroll 4
+            for (int kk = 0; kk < ks; ++kk) { mma_tf32_ts_w(tD, tAlo + a0 + kk * 8, dhi + (uint64_t)(dstep * kk), idesc, acc); acc = 1u; }
+#pragma unroll 4
+            for (int kk = 0; kk < ks; ++kk) mma_tf32_ts_w(tD, tAhi + a0 + kk * 8, dlo + (uint64_t)(dstep * kk), idesc, 1u);
+          } else {
+#pragma unroll 4
+            for (int kk = 0; kk < ks; ++kk) mma_tf32_ts_w(tD, tAhi + a0 + kk * 8, dhi + (uint64_t)(dstep * kk), idesc, 1u);
+          }
+          mma_commit_w(&w_empty[s]);
+          if (release_a && !corr) mma_commit_w(&a_free[c]);
+        }
+        if (release_a)
+          for (int c = nch; c < NB; ++c) mma_commit_w(&a_free[c]);
+        mma_commit_w(d_full);
+      }
+  } else {
+    // ===================== epilogue / generator warps: warp = (column block ci, lane quarter) =====================
+    const int quarter = warp & 3, ci = warp >> 2, c = ci * 32;
+    const int t = quarter * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tAhi = tmem_base + lane_sel + c, tAlo = tAhi + NP, tD = tAhi + 2 * NP;
+    float* stage = stage_all + warp * kU3StageBlock;
+    const float* wL = tail + c;
+    const float* w0col = tail + NP + c;
+    const size_t plane = (size_t)Q * NP;
+    const float* ysave = p.saved + (size_t)L * plane;
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(p.saved + (size_t)L * plane + Q);   // [L][Q][NB]: masks of a_1 .. a_L
+    const size_t bplane = (size_t)Q * NB;
+
+    struct Row { int q, r, kn; float gq, tq, jg; uint32_t mtop; };
+    // row context of tile tl: cotangent of the pre-ELU output (lw_out_bwd_kernel's formula), node abscissa, top-layer mask word
+    auto row_of = [&](int tl) {
+      Row w;
+      const int q0 = ((int)blockIdx.x + tl * (int)gridDim.x) * kU3Rows;
+      w.q = q0 + t;
+      const bool valid = w.q < Q;
+      const int qc = valid ? w.q : Q - 1;
+      w.r = qc / nodes; w.kn = qc - w.r * nodes;
+      const int r = w.r;
+      const float xv = ldg_pinned(p.x + r);
+      float gzt = p.gz ? ldg_pinned(p.gz + r) : 0.f;
+      if (p.gzrev) { const int b = r / p.d, i = r - b * p.d; gzt += ldg_pinned(p.gzrev + (size_t)b * p.d + (p.d - 1 - i)); }
+      const float y = ldg_pinned(ysave + qc);
+      float gq;
+      if (w.kn <= p.S) {
+        gq = (gzt * xv / 2.f) * ccs[kU3MaxNodes + w.kn];
+        w.tq = (xv * (ccs[w.kn] + 1.f)) / 2.f;
+      } else {
+        gq = p.gjac ? ldg_pinned(p.gjac + r) : 0.f;
+        if (p.glogdet) gq += ldg_pinned(p.glogdet + r / p.d) / ldg_pinned(p.jac + r);
+        w.tq = xv;
+      }
+      gq *= (y > 0.f) ? 1.f : expf(y);
+      w.gq = valid ? gq : 0.f;
+      w.jg = ldg_pinned(p.jac + r) * gzt;
+      w.mtop = valid ? __ldg(bits + (size_t)(L - 1) * bplane + (size_t)qc * NB + ci) : 0u;
+      return w;
+    };
+    auto store_block = [&](float* dstplane, const uint32_t* v, int q_row) {
+      const int sub = lane >> 2, piece = lane & 3;
+      const int row0 = q_row - lane + sub;
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          *reinterpret_cast<uint4*>(stage + lane * 16 + 4 * (j4 ^ ((lane >> 1) & 3))) =
+              make_uint4(v[16 * hb + 4 * j4], v[16 * hb + 4 * j4 + 1], v[16 * hb + 4 * j4 + 2], v[16 * hb + 4 * j4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int Rr = 8 * i + sub;
+          const uint4 o = *reinterpret_cast<const uint4*>(stage + Rr * 16 + 4 * (piece ^ ((Rr >> 1) & 3)));
+          if (row0 + 8 * i < Q) *reinterpret_cast<uint4*>(dstplane + (size_t)(row0 + 8 * i) * NP + c + 16 * hb + 4 * piece) = o;
+        }
+        __syncwarp();
+      }
+    };
+    auto split_store = [&](const uint32_t* v) {
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          hi[j] = u3_rn_tf32(v[16 * hb + j]);
+          lo[j] = __float_as_uint(__uint_as_float(v[16 * hb + j]) - __uint_as_float(hi[j])) + 0x1000u;
+        }
+        tmem_st16p(tAhi + 16 * hb, hi);
+        tmem_st16p(tAlo + 16 * hb, lo);
+      }
+    };
+    // top of the chain: delta_L[q][n] = g_q w_L[n] where a_L[q][n] > 0
+    auto gen_top = [&](const Row& w) {
+      uint32_t v[32];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wL + 4 * j4);
+        v[4 * j4 + 0] = ((w.mtop >> (4 * j4 + 0)) & 1u) ? __float_as_uint(w.gq * w4.x) : 0u;
+        v[4 * j4 + 1] = ((w.mtop >> (4 * j4 + 1)) & 1u) ? __float_as_uint(w.gq * w4.y) : 0u;
+        v[4 * j4 + 2] = ((w.mtop >> (4 * j4 + 2)) & 1u) ? __float_as_uint(w.gq * w4.z) : 0u;
+        v[4 * j4 + 3] = ((w.mtop >> (4 * j4 + 3)) & 1u) ? __float_as_uint(w.gq * w4.w) : 0u;
+      }
+      split_store(v);
+      tmem_wait_st();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) u3_arrive(&a_full[ci]);
+    };
+
+    Row cur;
+    cur.q = 0; cur.r = 0; cur.kn = 0; cur.gq = 0.f; cur.tq = 0.f; cur.jg = 0.f; cur.mtop = 0u;
+    if (n_local > 0) { cur = row_of(0); gen_top(cur); }
+    int it = 0;
+    for (int tl = 0; tl < n_local; ++tl) {
+      for (int l = L - 1; l >= 1; --l, ++it) {
+        Row nxt = cur;
+        const bool gen_next = (l == 1) && (tl + 1 < n_local);
+        const bool gen_late = gen_next && ci >= p.nch[l] - 1;
+        // ReLU mask of a_l for this row / column block (dependent global load: issued before the waits)
+        const bool valid = cur.q < Q;
+        const uint32_t m = valid ? __ldg(bits + (size_t)(l - 1) * bplane + (size_t)cur.q * NB + ci) : 0u;
+        if (gen_next) nxt = row_of(tl + 1);
+        if (gen_next && !gen_late) {
+          mbar_wait(&a_free[ci], (uint32_t)(tl & 1));
+          fence_after_sync();
+          gen_top(nxt);
+        }
+        mbar_wait(d_full, (uint32_t)(it & 1));
+        fence_after_sync();
+        uint32_t v[32];
+        tmem_ld32p(tD, v);
+        tmem_wait_ld();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) u3_arrive(d_empty);
+        if (gen_late) {
+          mbar_wait(&a_free[ci], (uint32_t)(tl & 1));
+          fence_after_sync();
+          gen_top(nxt);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0u;        // delta_l = (delta_{l+1} W_l) o relu'(a_l); rows >= Q: 0
+        if (l > 1) {
+          split_store(v);
+          tmem_wait_st();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) u3_arrive(&a_full[ci]);
+          // db_{l-1} = column sums of delta_l; the plane goes to the weight-gradient GEMM of W_{l-1}
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            float w16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w16[j] = __uint_as_float(v[16 * hb + j]);
+            const float sum = u3_colsum16(w16, lane);
+            const int n = c + 16 * hb + (lane & 15);
+            if (lane < 16 && n < p.dims[l]) atomicAdd(p.db[l - 1] + n, sum);
+          }
+          store_block(p.dplanes + (size_t)(L - 1 - l) * plane, v, cur.q);
+        } else {
+          // first layer: dx (the row of node S+1 carries the jac output's chain rule), dW0[:,0], D[r] = sum over the row's nodes
+          float dot = 0.f;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w0col + 4 * j4);
+            dot = fmaf(__uint_as_float(v[4 * j4 + 0]), w4.x, dot); dot = fmaf(__uint_as_float(v[4 * j4 + 1]), w4.y, dot);
+            dot = fmaf(__uint_as_float(v[4 * j4 + 2]), w4.z, dot); dot = fmaf(__uint_as_float(v[4 * j4 + 3]), w4.w, dot);
+          }
+          if (valid && cur.kn == p.S + 1) atomicAdd(p.dx + cur.r, dot + (ci == 0 ? cur.jg : 0.f));
+          const int r_lo = __shfl_sync(0xffffffffu, cur.r, 0), r_hi = __shfl_sync(0xffffffffu, cur.r, 31);
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const int n = c + 16 * hb + (lane & 15);
+            const bool col_ok = lane < 16 && n < p.dims[1];
+            float w16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w16[j] = __uint_as_float(v[16 * hb + j]) * cur.tq;
+            const float st = u3_colsum16(w16, lane);
+            if (col_ok) atomicAdd(p.dW0 + (size_t)n * p.ldw0, st);
+            for (int rr = r_lo; rr <= r_hi; ++rr) {                    // warp-uniform trip count: the rows this warp's 32 node-rows span
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w16[j] = (cur.r == rr) ? __uint_as_float(v[16 * hb + j]) : 0.f;
+              const float sd = u3_colsum16(w16, lane);
+              if (col_ok) atomicAdd(p.D + (size_t)rr * NP + n, sd);
+            }
+          }
+        }
+        cur = nxt;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t u3b_smem_bytes(int NP) {
+  const int NB = NP / 32, EW = 4 * NB;
+  return ((size_t)kU3Stages * 2 * 8 * NP * 4 + (size_t)2 * NP + (size_t)EW * kU3StageBlock + 2 * kU3MaxNodes) * sizeof(float) +
+         (2 * kU3Stages + 2 * NB + 2) * sizeof(uint64_t) + 16;
+}
+
+// Packed operands of the chain: for GEMM layer l the image of W_l^T (B[n'][k'] = W_l[k'][n'], n' = in-feature, reduction k' =
+// out-feature) in the forward's chunk format, then w_L and W0[:,0].
+struct U3BPlan {
+  int L, NP;
+  int kp[GNF_MAX_LAYERS], nch[GNF_MAX_LAYERS];
+  size_t off_img[GNF_MAX_LAYERS], chunk_floats, off_tail, image_floats;
+};
+static int u3b_plan(const gnf_mlp_t* net, U3BPlan* pl) {
+  U3Plan f;
+  if (int e = u3_plan(net, 0, &f)) return e;
+  pl->L = f.L; pl->NP = f.NP; pl->chunk_floats = f.chunk_floats;
+  size_t off = 0;
+  for (int l = 0; l < GNF_MAX_LAYERS; ++l) { pl->kp[l] = 0; pl->nch[l] = 0; pl->off_img[l] = 0; }
+  for (int l = 1; l < f.L; ++l) {
+    pl->kp[l] = (net->dims[l + 1] + 7) / 8 * 8;
+    pl->nch[l] = (pl->kp[l] + 31) / 32;
+    pl->off_img[l] = off;
+    off += (size_t)pl->nch[l] * pl->chunk_floats;
+  }
+  pl->off_tail = off;
+  pl->image_floats = off + (size_t)2 * f.NP;
+  return 0;
+}
+
+__global__ void u3_pack_bwd_kernel(U3PackArgs a, float* __restrict__ img) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += gridDim.x * blockDim.x) {
+    float out = 0.f;
+    if (i >= a.off_tail) {
+      const int e = (int)(i - a.off_tail), j = e / a.NP, n = e % a.NP;
+      if (j == 0) { if (n < a.dims[a.L]) out = a.W[a.L][n]; }                                 // output Linear [1, dims[L]]
+      else { if (n < a.dims[1]) out = a.W[0][(size_t)n * a.dims[0]]; }                        // W0[:, 0]
+    } else {
+      int l = 1;
+      while (l + 1 < a.L && i >= a.off_img[l + 1]) ++l;
+      const unsigned e = i - a.off_img[l];
+      const unsigned c = e / a.chunk_floats, e2 = e % a.chunk_floats;
+      const unsigned half = 8u * a.NP * 4u;
+      const unsigned part = e2 / half, e3 = e2 % half;
+      const int k4 = (int)(e3 / (a.NP * 4u)), n = (int)((e3 / 4u) % a.NP), kk = (int)(e3 % 4u);
+      const int k = (int)c * 32 + k4 * 4 + kk;                                                // k = out-feature (reduction), n = in-feature
+      float v = 0.f;
+      if (n < a.dims[l] && k < a.dims[l + 1]) v = a.W[l][(size_t)k * a.dims[l] + n];
+      const float hi = __uint_as_float(u3_rn_tf32(__float_as_uint(v)));
+      out = part ? __uint_as_float(u3_rn_tf32(__float_as_uint(v - hi))) : hi;
+    }
+    img[i] = out;
+  }
+}
+
+size_t u3_bwd_image_floats(const gnf_mlp_t* net) {
+  U3BPlan pl;
+  if (u3b_plan(net, &pl)) return 0;
+  return (pl.image_floats + 3) / 4 * 4;
+}
+
+// image: u3_bwd_image_floats(net) floats of scratch; dplanes: (L-2) planes; D, dx and the db / dW0 targets must be zeroed by the caller.
+int launch_u3_bwd_chain(const float* x, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn, const float* jac, const float* gz,
+                        const float* gzrev, const float* gjac, const float* glogdet, const float* saved, float* image, float* dplanes, float* D,
+                        float* dx, const gnf_mlp_grad_t* grads, int R, int d, cudaStream_t s) {
+  U3BPlan pl;
+  if (int e = u3b_plan(net, &pl)) return e;
+  const int NP = pl.NP, L = pl.L;
+  const int nodes = S + 2;
+  const long long Q = (long long)R * nodes;
+  if (Q > 0x7fffffffLL - 2 * kU3Rows || S + 1 > kU3MaxNodes) return fail(GNF_ERR_UNSUPPORTED, "umnn tc3 backward: problem size out of range");
+  U3PackArgs a;
+  for (int l = 0; l < GNF_MAX_LAYERS; ++l) { a.W[l] = nullptr; a.b[l] = nullptr; a.nch[l] = pl.nch[l]; a.off_img[l] = (unsigned)pl.off_img[l]; }
+  for (int l = 0; l <= L; ++l) { a.W[l] = net->W[l]; a.b[l] = net->b[l]; }
+  for (int l = 0; l <= net->n_layers; ++l) a.dims[l] = net->dims[l];
+  a.chunk_floats = (unsigned)pl.chunk_floats; a.off_tail = (unsigned)pl.off_tail; a.total = (unsigned)pl.image_floats; a.L = L; a.NP = NP;
+  int blocks = (int)((pl.image_floats + 255) / 256);
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  GNF_LAUNCH(u3_pack_bwd_kernel, blocks, 256, 0, s, a, image);
+  U3BParams p;
+  p.x = x; p.ccw = ccw; p.ccn = ccn; p.jac = jac; p.gz = gz; p.gzrev = gzrev; p.gjac = gjac; p.glogdet = glogdet; p.image = image; p.saved = saved;
+  p.dplanes = dplanes; p.D = D; p.dx = dx; p.dW0 = grads->dW[0]; p.ldw0 = net->dims[0];
+  for (int l = 0; l < GNF_MAX_LAYERS; ++l) p.db[l] = grads->db[l];
+  p.R = R; p.d = d; p.E = net->dims[0] - 1; p.S = S; p.nodes = nodes; p.L = L; p.Q = Q;
+  for (int l = 0; l <= GNF_MAX_LAYERS; ++l) p.dims[l] = l <= net->n_layers ? net->dims[l] : 0;
+  for (int l = 0; l < GNF_MAX_LAYERS; ++l) { p.kp[l] = pl.kp[l]; p.nch[l] = pl.nch[l]; p.off_img[l] = (unsigned)pl.off_img[l]; }
+  p.off_tail = (unsigned)pl.off_tail; p.chunk_floats = (unsigned)pl.chunk_floats;
+  const size_t smem = u3b_smem_bytes(NP);
+  const long long ntiles = (Q + kU3Rows - 1) / kU3Rows;
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+#define U3B_CASE(nb)                                                                                             \
+  case nb:                                                                                                       \
+    cudaFuncSetAttribute(umnn_bwd_tc3_kernel<nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    GNF_LAUNCH(umnn_bwd_tc3_kernel<nb>, grid, (4 * nb + 2) * 32, smem, s, p);                                    \
+    break;
+  switch (NP / 32) { U3B_CASE(1) U3B_CASE(2) U3B_CASE(3) U3B_CASE(4) U3B_CASE(5) default: return fail(GNF_ERR_UNSUPPORTED, "umnn tc3 backward: width"); }
+#undef U3B_CASE
+  return 0;
 }
 
 static size_t u3_smem_bytes(int NP) {

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "tc_gemm.h"
 #include "tc_rw.h"
+#include "tc_umnn3.h"
 
 namespace gnf {
 
@@ -592,6 +593,91 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   if (int e = gnf_linear_dgrad(D, NP, net->W[0] + 1, 1 + E, nullptr, 0, dh, E, R, net->dims[1], E, stream)) return e;
   GNF_LAUNCH(lw_finish_dh_kernel, lw_blocks(R, 256, 4), 256, 0, s, dh, E, gz, gzrev, R, d);
   return check_launch("gnf_umnn_bwd_lw");
+}
+
+
+/* Fused-chain flavour of gnf_umnn_bwd_lw (same cotangents, outputs and gradient conventions; 3xTF32): the output pass
+ * (lw_out_bwd_kernel: delta_L, dW_L, db_L, db_{L-1}), then ONE tensor-core kernel for the whole dgrad chain delta_L -> delta_1
+ * with the column sums and the first-layer reductions taken on chip (tc_umnn3.cu), then the weight-gradient GEMMs over the delta /
+ * activation planes (tc_rw_wgrad.cu) and the small per-row GEMMs of the first layer.  `saved` must come from gnf_umnn_fwd_tc3
+ * (it also holds the ReLU mask of the last hidden activation). */
+size_t gnf_umnn_bwd_tc3_workspace_bytes(const gnf_mlp_t* net, int R, int S) {
+#ifdef GNF_EMU
+  (void)net; (void)R; (void)S;
+  gnf::set_error("tensor-core kernels have no host-simulator flavour");
+  return 0;
+#else
+  LwPlan pl;
+  if (lw_plan(net, R, S, 1, 1, &pl)) return 0;
+  const size_t img = u3_bwd_image_floats(net);
+  if (img == 0) return 0;
+  if (!pl.rw) { set_error("umnn tc3 backward: the hidden layers do not fit the resident weight-gradient kernel"); return 0; }
+  const size_t plane = (size_t)pl.Q * pl.NP;
+  return ((size_t)R * pl.NP + (size_t)(pl.L - 1) * plane + rw_wgrad_partial_floats(pl.NP) + img + 8) * sizeof(float);
+#endif
+}
+
+int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn, const float* jac,
+                     const float* gz, const float* gzrev, const float* gjac, const float* glogdet, const float* saved, float* dx,
+                     float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work, size_t work_bytes, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!x || !h || !net || !ccw || !ccn || !jac || !saved || !dx || !dh || !grads || R < 0 || d <= 0 || S < 1 || (R % d) != 0) return fail(GNF_ERR_INVALID, "gnf_umnn_bwd_tc3: bad arguments");
+  LwPlan pl;
+  if (int e = lw_plan(net, R, S, 1, 1, &pl)) return e;
+  const size_t need = gnf_umnn_bwd_tc3_workspace_bytes(net, R, S);
+  if (need == 0) return GNF_ERR_UNSUPPORTED;
+  if (!work || work_bytes < need) return fail(GNF_ERR_WORKSPACE, "gnf_umnn_bwd_tc3: workspace too small (%zu < %zu)", work_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(work) & 15) != 0) return fail(GNF_ERR_INVALID, "gnf_umnn_bwd_tc3: workspace must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int NP = pl.NP, L = pl.L, E = pl.E;
+  for (int l = 0; l < net->n_layers; ++l) {
+    if (!grads->dW[l] || !grads->db[l]) return fail(GNF_ERR_INVALID, "gnf_umnn_bwd_tc3: gradient pointer %d is NULL", l);
+    cudaMemsetAsync(grads->dW[l], 0, (size_t)net->dims[l] * net->dims[l + 1] * sizeof(float), s);
+    cudaMemsetAsync(grads->db[l], 0, (size_t)net->dims[l + 1] * sizeof(float), s);
+  }
+  if (R == 0) return check_launch("gnf_umnn_bwd_tc3");
+  float* ws = (float*)work;
+  const size_t plane = (size_t)pl.Q * NP;
+  float* D = ws;
+  float* dplanes = ws + (((size_t)R * NP + 3) / 4) * 4;            // plane 0: delta_L, planes 1..L-2: delta_{L-1} .. delta_2
+  float* part = dplanes + (size_t)(L - 1) * plane;
+  float* image = part + ((rw_wgrad_partial_floats(NP) + 3) / 4) * 4;
+  LwGeom g;
+  g.R = R; g.d = d; g.E = E; g.S = S; g.nodes = pl.nodes; g.NP = NP; g.L = L; g.Q = pl.Q;
+  const int red_threads = (NP / 4) * kLwRL;
+  const size_t red_smem = ((size_t)kLwRL * NP + kLwRL + 4) * sizeof(float);
+  const float* ysave = saved + (size_t)L * plane;
+  // output layer: delta_L (plane for the weight gradient of W_{L-1}), dW_L, db_L, db_{L-1}
+  const int out_bwd_per_sm = 65536 / (64 * red_threads) < 1 ? 1 : (65536 / (64 * red_threads) > 4 ? 4 : 65536 / (64 * red_threads));
+  GNF_LAUNCH(lw_out_bwd_kernel, lw_blocks(pl.Q, 64, out_bwd_per_sm), red_threads, red_smem, s, saved + (size_t)(L - 1) * plane, ysave, net->W[L],
+             net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dplanes, grads->dW[L], grads->db[L], grads->db[L - 1], g);
+  // the dgrad chain on the tensor cores: delta_{L-1} .. delta_2 planes, hidden db, dW0[:,0], D, dx
+  cudaMemsetAsync(D, 0, (size_t)R * NP * sizeof(float), s);
+  cudaMemsetAsync(dx, 0, (size_t)R * sizeof(float), s);
+  if (int e = launch_u3_bwd_chain(x, net, S, ccw, ccn, jac, gz, gzrev, gjac, glogdet, saved, image, dplanes + plane, D, dx, grads, R, d, s)) return e;
+  // weight gradients of the hidden GEMM layers: dW_l = delta_{l+1}^T a_l
+  for (int l = L - 1; l >= 1; --l) {
+    const float* dnext = dplanes + (size_t)(L - 1 - l) * plane;    // delta_{l+1}
+    const float* a_l = saved + (size_t)(l - 1) * plane;
+    if (int e = launch_rw_wgrad(dnext, NP, a_l, NP, grads->dW[l], net->dims[l], (int)pl.Q, net->dims[l + 1], net->dims[l], 3, part, s)) return e;
+  }
+  // first layer: db0 = colsum(D), dW0[:,1:] = D^T h, dh = D W0[:,1:] (+ gz on the first conditioning feature)
+  if (int e = gnf_colsum(D, NP, grads->db[0], R, net->dims[1], 1, stream)) return e;
+  if (int e = gnf_linear_wgrad(D, NP, h, E, grads->dW[0] + 1, 1 + E, R, net->dims[1], E, stream)) return e;
+  if (int e = gnf_linear_dgrad(D, NP, net->W[0] + 1, 1 + E, nullptr, 0, dh, E, R, net->dims[1], E, stream)) return e;
+  GNF_LAUNCH(lw_finish_dh_kernel, lw_blocks(R, 256, 4), 256, 0, s, dh, E, gz, gzrev, R, d);
+  return check_launch("gnf_umnn_bwd_tc3");
+#endif
+}
+
+/* Floats of the saved-activation buffer written by gnf_umnn_fwd_tc3 in training: gnf_umnn_lw_saved_floats(net, R, S, 1) plus
+ * the ReLU bit mask of the last hidden activation ([Q][NP/32] words), which the fused backward chain starts from. */
+size_t gnf_umnn_tc3_saved_floats(const gnf_mlp_t* net, int R, int S) {
+  LwPlan pl;
+  if (lw_plan(net, R, S, 1, 0, &pl)) return 0;
+  return gnf_umnn_lw_saved_floats(net, R, S, 1) + (size_t)pl.Q * (pl.NP / 32);
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@ def _device_noise_counters(model, dev):
 def model_graph_state(model):
     """Host-side state a captured step froze: conditioner flags / exponents / buffer addresses
     (DAGConditioner.graph_state), quadrature steps and precision of the normalizers, and the engine switches."""
-    st = [ops._GEMM_MODE, ops.UMNN_ENGINE, ops.UMNN_FWD_FUSED_TC3]
+    st = [ops._GEMM_MODE, ops.UMNN_ENGINE, ops.UMNN_FWD_FUSED_TC3, ops.UMNN_BWD_FUSED_TC3]
     for c in model.getConditioners():
         st.append(c.graph_state() if hasattr(c, "graph_state") else None)
     for n in model.getNormalizers():
@@ -35,8 +35,12 @@ def model_graph_state(model):
     return tuple(st)
 
 
-def _capture(body, warmup):
-    s = torch.cuda.Stream()
+def _capture(body, warmup, stream=None):
+    """Warm-up runs and the capture on ONE side stream (`stream`, or a fresh one).  A training loop that keeps capturing new graphs
+    (one per quadrature-step count, recaptures after model.step()) should pass the stream it runs its eager steps on: autograd
+    binds a parameter's gradient accumulator to the stream of the backward that created it, and a capture that has to
+    synchronise with another stream for it -- the legacy default stream in particular -- is invalidated."""
+    s = stream if stream is not None else torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
         for _ in range(warmup):
@@ -44,7 +48,7 @@ def _capture(body, warmup):
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, stream=s):
         out = body()
     return graph, out
 
@@ -89,10 +93,10 @@ class GraphedTrainStep:
     differs (`recaptures` counts them).  Note the reference's own quirk: when update_dual_param re-creates A as a new
     Parameter, an optimizer built earlier no longer owns it -- here as there."""
 
-    def __init__(self, model, optimizer, bucket, example_x, allreduce=True, warmup=3):
+    def __init__(self, model, optimizer, bucket, example_x, allreduce=True, warmup=3, stream=None):
         self.model, self.opt, self.bucket = model, optimizer, bucket
         self.static_x = example_x.clone()
-        self.allreduce, self.warmup = allreduce, warmup
+        self.allreduce, self.warmup, self.stream = allreduce, warmup, stream
         self.recaptures = 0
         self._capture()
 
@@ -112,7 +116,7 @@ class GraphedTrainStep:
             optimizer.step()
             return loss.detach()
 
-        self.graph, self.static_loss = _capture(body, self.warmup)
+        self.graph, self.static_loss = _capture(body, self.warmup, self.stream)
         self.state = model_graph_state(model)
 
     def __call__(self, x):

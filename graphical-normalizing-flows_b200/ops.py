@@ -734,6 +734,8 @@ UMNN_LAYERWISE_MIN_NODE_ROWS = 16384
 # The strict forward of the layer-wise engine runs as ONE fused tensor-core kernel (gnf_umnn_fwd_tc3) when the integrand fits it
 # (>= 3 linear layers, hidden widths <= 160); False = per-layer passes (gnf_umnn_fwd_lw).
 UMNN_FWD_FUSED_TC3 = True
+# ... and its backward runs the dgrad chain as one fused tensor-core kernel too (gnf_umnn_bwd_tc3); False = gnf_umnn_bwd_lw
+UMNN_BWD_FUSED_TC3 = True
 
 
 def _umnn_layerwise_passes(net, R, S, train, device=None):
@@ -828,7 +830,8 @@ class UmnnFn(torch.autograd.Function):
             # full accumulator magnitude; with order 0 the saved activations carry a one-sided 5e-7 error that the backward's
             # cancelling sums amplify to 1e-3 .. 2e-3 on the integrand's bias gradients); evaluation = per-chunk order 0
             if train:
-                saved = torch.empty(lib().gnf_umnn_lw_saved_floats(C.byref(net), R, int(S), 1), device=x.device, dtype=torch.float32)
+                saved = torch.empty(lib().gnf_umnn_tc3_saved_floats(C.byref(net), R, int(S)), device=x.device, dtype=torch.float32)
+                ctx.fused_bwd = UMNN_BWD_FUSED_TC3 and lib().gnf_umnn_bwd_tc3_workspace_bytes(C.byref(net), R, int(S)) != 0
             nbytes = lib().gnf_umnn_tc3_workspace_bytes(C.byref(net), R)
             ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
             _call("gnf_umnn_fwd_tc3", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
@@ -855,6 +858,7 @@ class UmnnFn(torch.autograd.Function):
             _call("gnf_umnn_fwd", ptr(x), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(z), ptr(zrev), ptr(jac),
                   ptr(logdet), ptr(saved), R, d, ptr(ws), nbytes, stream_ptr())
         ctx.lw_passes = lw_passes if (lw_passes is not None and train) else None
+        ctx.fused_bwd = getattr(ctx, "fused_bwd", False)
         _count(2)
         ctx.saved_acts = saved
         ctx.save_for_backward(x, h, jac, *weights, *biases)
@@ -889,7 +893,14 @@ class UmnnFn(torch.autograd.Function):
         for l in range(n):
             grads.dW[l] = dWs[l].data_ptr()
             grads.db[l] = dbs[l].data_ptr()
-        if ctx.lw_passes is not None:
+        if ctx.lw_passes is not None and getattr(ctx, "fused_bwd", False):
+            # dgrad chain fused on the tensor cores (tc_umnn3.cu), then the resident weight-gradient GEMMs
+            nbytes = lib().gnf_umnn_bwd_tc3_workspace_bytes(C.byref(net), R, ctx.S)
+            ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+            _call("gnf_umnn_bwd_tc3", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev),
+                  ptr(gjac), ptr(glogdet), ptr(ctx.saved_acts), ptr(dx), ptr(dh), C.byref(grads), R, d, ptr(ws), nbytes, stream_ptr())
+            _count(6 + 2 * n)
+        elif ctx.lw_passes is not None:
             nbytes = lib().gnf_umnn_lw_workspace_bytes(C.byref(net), R, ctx.S, 1)
             ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
             _call("gnf_umnn_bwd_lw", ptr(x), ptr(h), C.byref(net), ctx.S, ptr(ccw), ptr(ccn), ptr(jac), ptr(gz), ptr(gzrev),

@@ -266,12 +266,14 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
  * hi/lo split), the activation chain of a 128-node-row tile resident in TMEM from the first to the last hidden layer, the
  * hidden weights streamed through shared memory as pre-split hi/lo K-chunks.  Replaces the per-layer passes of
  * gnf_umnn_fwd_lw (MonotonicNormalizer.py:51-66 / UMNN ParallelNeuralIntegral forward): same outputs, and -- when
- * `saved` is given -- the same saved-activation buffer ([gnf_umnn_lw_saved_floats(net, R, S, train)] floats), so that
- * gnf_umnn_bwd_lw consumes it unchanged.  saved == NULL (evaluation): no activation touches HBM.
+ * `saved` is given -- the same saved-activation buffer, so that gnf_umnn_bwd_lw consumes it unchanged; in training
+ * (train != 0) the buffer holds gnf_umnn_tc3_saved_floats(net, R, S) floats: the layer-wise layout followed by the ReLU bit
+ * mask of the last hidden activation, which gnf_umnn_bwd_tc3 starts from.  saved == NULL (evaluation): no activation touches HBM.
  * order: 0 = per K-chunk a_lo*b_hi, a_hi*b_lo, a_hi*b_hi; 1 = all correction products of a layer first (the hi images
  * are streamed twice).  Hidden widths <= 160, >= 3 linear layers; otherwise GNF_ERR_UNSUPPORTED.
  * work: gnf_umnn_tc3_workspace_bytes(net, R) bytes, 16-byte aligned. */
 size_t gnf_umnn_tc3_workspace_bytes(const gnf_mlp_t* net, int R);
+size_t gnf_umnn_tc3_saved_floats(const gnf_mlp_t* net, int R, int S);
 int gnf_umnn_fwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
                      float* z, float* zrev, float* jac, float* logdet, float* saved, int train, int order, int R, int d,
                      void* work, size_t work_bytes, gnf_stream_t stream);
@@ -290,6 +292,18 @@ typedef struct {
 } gnf_adam_tensor_t;
 int gnf_adam_step(const gnf_adam_tensor_t* tensors, int n_tensors, const int64_t* step_dev, float lr, float beta1, float beta2,
                   float eps, float weight_decay, gnf_stream_t stream);
+
+/* Backward of the integral with the dgrad chain fused on the tensor cores (UMNN NeuralIntegral.backward; same
+ * cotangents, outputs and gradient conventions as gnf_umnn_bwd / gnf_umnn_bwd_lw; 3xTF32): the cotangent of the pre-ELU output is
+ * pushed from the last hidden layer down to the first in ONE kernel (delta planes for the weight-gradient GEMMs, bias gradients and
+ * the first layer's per-row reductions leave the chip; no dgrad activation plane is re-read), followed by the resident
+ * weight-gradient GEMMs.  `saved` must have been written by gnf_umnn_fwd_tc3 with train != 0.
+ * work: gnf_umnn_bwd_tc3_workspace_bytes(net, R, S) bytes (0 = integrand not covered, see gnf_last_error), 16-byte aligned. */
+size_t gnf_umnn_bwd_tc3_workspace_bytes(const gnf_mlp_t* net, int R, int S);
+int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
+                     const float* jac, const float* gz, const float* gzrev, const float* gjac, const float* glogdet,
+                     const float* saved, float* dx, float* dh, const gnf_mlp_grad_t* grads, int R, int d, void* work,
+                     size_t work_bytes, gnf_stream_t stream);
 
 /* DAGConditioner.loss (DAGConditioner.py:268-271) fused:  out = dag_const*(lambd*t + c/2*t^2) + l1_weight*mean|A|, with the
  * dual variables read from their device buffers (lambd, c, dag_const, l1_weight: one float each, as registered by the

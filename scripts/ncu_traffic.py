@@ -1,6 +1,6 @@
 """profiles/ncu_traffic.json from `ncu --set full` captures: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of
 every kernel in the given .ncu-rep files, averaged over the captured launches, keyed "<kernel>@<cfg>" (bench.py's roofline.traffic).
-usage: ncu_traffic.py cfg4:gpurun_out/x/prof_cfg4.ncu-rep [cfg5:...]   (runs `ncu -i ... --page raw --csv`; no GPU needed)"""
+usage: ncu_traffic.py cfg4:gpurun_out/x/prof_cfg4.ncu-rep [cfg5:...raw.csv]   (.ncu-rep: runs `ncu -i ... --page raw --csv`; or that csv itself)"""
 import csv
 import io
 import json
@@ -23,7 +23,7 @@ def main():
     meta = {}
     for arg in sys.argv[1:]:
         cfg, rep = arg.split(":", 1)
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, unit = rows[0], rows[1]
         ix = {k: i for i, k in enumerate(hdr)}

@@ -11,7 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not p.endswith(("power_trace.npz", "dag_control.npz")))
+                  if not p.endswith(("power_trace.npz", "dag_control.npz", "image_cnn_flow.npz")))
 
 
 def load_golden(name):

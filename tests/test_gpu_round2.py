@@ -280,3 +280,101 @@ def test_skinny_forward_layer(M, N, K, period, relu):
     if relu:
         ref = ref.clamp_min(0)
     assert float((Y.double() - ref).abs().max()) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# experiment plumbing: the reference driver's loop on the CUDA path
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_uci_training_loop_runs_and_checkpoints(tmp_path, engine_reset, use_graph):
+    """G.experiments.train_uci = the loop of UCIExperiments.py:117-220 (constrainA, random S, Adam, model.step, validation at S + 20,
+    checkpoints): three epochs on a standardised synthetic mixture; the loss must fall, the checkpoints must load back --
+    also with the `module.` prefix of a DataParallel checkpoint."""
+    import numpy as np
+    rng = np.random.RandomState(0)
+    mk = lambda n: (rng.randn(n, 4) * np.array([1., .3, 2., .7]) + np.array([0., 1., -1., 2.])).astype(np.float32)
+    trn, val, tst = mk(2048), mk(512), mk(512)
+    cfg = dict(G.experiments.DRIVER_DEFAULTS, conditioner="DAG", normalizer="monotonic", emb_net=[32, 32, 8], int_net=[40, 40, 40],
+               b_size=256, nb_steps=10, nb_steps_dual=2, l1=.1, learning_rate=5e-3)
+    G.ops.set_gemm_mode("auto")
+    model, hist = G.experiments.train_uci(trn, val, tst, cfg, path=str(tmp_path), nb_epoch=3, use_graph=use_graph, log=lambda s: None, seed=0)
+    assert len(hist) == 3 and all(np.isfinite(h["train_loss"]) and np.isfinite(h["valid_ll"]) for h in hist)
+    assert hist[-1]["train_loss"] < hist[0]["train_loss"]
+    for f in ("model.pt", "ADAM.pt", "model_2.pt"):
+        assert (tmp_path / f).is_file()
+    sd = torch.load(str(tmp_path / "model.pt"), map_location="cpu")
+    fresh = G.experiments.build_uci_flow(4, cfg).to("cuda")
+    G.load_checkpoint(fresh, {"module." + k: v for k, v in sd.items()})
+    fresh.getNormalizers()[0].nb_steps = model.getNormalizers()[0].nb_steps
+    for c_new, c_old in zip(fresh.getConditioners(), model.getConditioners()):
+        c_new.stoch_gate = c_old.stoch_gate = False
+        c_new.exponent = c_old.exponent
+    x = torch.from_numpy(val[:64]).cuda()
+    with torch.no_grad():
+        assert torch.allclose(fresh.compute_ll(x)[0], model.compute_ll(x)[0], atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# image flows: DAGConditioner(hidden=<nn.Module>), CNN embedding nets, multi-scale CNNormalizingFlow (SURVEY 8f rank 3)
+# ---------------------------------------------------------------------------------------------------------------------
+def _build_image_flow():
+    outer = []
+    for img, fc, ntype in (([1, 14, 14], [400, 64], "affine"), ([1, 7, 7], [16, 16], "monotonic")):
+        d = img[1] * img[2]
+        emb = 2 if ntype == "affine" else 6
+        cond = G.DAGConditioner(d, G.MNISTCNN(fc_l=fc, size_img=img, out_d=emb), emb, l1=.3, nb_epoch_update=10, hot_encoding=False,
+                                A_prior=G.MNIST_A_prior(img[1], 2))
+        norm = G.AffineNormalizer() if ntype == "affine" else G.MonotonicNormalizer(integrand_net=[20, 20], cond_size=emb, nb_steps=12, solver="CC")
+        flow = G.FCNormalizingFlow([G.NormalizingFlowStep(cond, norm)], None)
+        flow.img_sizes = img
+        outer.append(flow)
+    return G.CNNormalizingFlow(outer, G.NormalLogDensity(), [[1, 2, 2], [1, 1, 1]])
+
+
+def test_image_cnn_flow_matches_the_reference():
+    """tests/golden/image_cnn_flow.npz (reference run, make_image_golden.py): a two-scale CNNormalizingFlow of
+    DAGConditioner(hidden=MNISTCNN) steps.  The reference's state_dict loads strictly; z, log-det, loss and every gradient agree."""
+    import numpy as np
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "image_cnn_flow.npz"))
+    model = _build_image_flow().to("cuda")
+    sd = {k[3:]: torch.from_numpy(f[k]).cuda() for k in f.files if k.startswith("sd.")}
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for c in model.getConditioners():
+        c.stoch_gate = False
+    G.ops.set_gemm_mode("ffma")
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the CNN body is the user's module on cuDNN: keep its convolutions in fp32 here
+    try:
+        x = torch.from_numpy(f["x"]).cuda()
+        z, jac = model(x)
+        loss = model.loss(z, jac)
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert float((z.detach().cpu() - torch.from_numpy(f["z"])).abs().max()) < 5e-5
+    assert float((jac.detach().cpu() - torch.from_numpy(f["logdet"])).abs().max()) < 1e-4
+    assert abs(float(loss) - float(f["loss"])) < 1e-4 * abs(float(f["loss"]))
+    for k, p in model.named_parameters():
+        if "grad." + k in f.files:
+            g = torch.from_numpy(f["grad." + k])
+            assert p.grad is not None, k
+            assert float((p.grad.cpu() - g).norm() / g.norm().clamp_min(1e-12)) < 1e-3, k
+    # sampling through the multi-scale structure: invert(forward(x)) on a flow whose conditioners are exact DAGs
+    for c in model.getConditioners():
+        with torch.no_grad():
+            c.A.copy_(torch.tril((c.A.detach() != 0).float(), -1))
+        c.s_thresh, c.h_thresh, c.is_invertible = False, 0., True
+    with torch.no_grad():
+        z2, _ = model(x)
+        x_rec = model.invert(z2)
+    assert float((x_rec - x).abs().max()) < 2e-4
+
+
+def test_mnist_and_cifar_factories_build_the_reference_structure():
+    m = G.buildMNISTNormalizingFlow([1, 1, 1], G.AffineNormalizer, {}, prior_kernel=2)
+    assert isinstance(m, G.CNNormalizingFlow) and [s.img_sizes for s in m.steps] == [[1, 28, 28], [1, 14, 14], [1, 7, 7]]
+    assert m.steps[0].steps[0].conditioner.embedding_net.fc1.in_features == 2304
+    assert G.buildMNISTNormalizingFlow([1, 1], G.AffineNormalizer, {}) is None
+    c = G.buildCIFAR10NormalizingFlow([1], G.AffineNormalizer, {})
+    assert isinstance(c, G.FCNormalizingFlow) and c.steps[0].conditioner.in_size == 3072

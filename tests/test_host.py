@@ -5,6 +5,7 @@ import os
 import re
 import sys
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -202,3 +203,34 @@ def test_tensor_core_gemm_plan_fills_the_last_round_of_work_items():
         b, s, _ = plan(M, N, K, p, w)
         assert b % 32 == 0 and 64 <= b <= (160 if p == 3 else 256) and s >= 1
     assert lib.gnf_tc_gemm_plan(0, 1, 1, 3, 0, C.byref(bn), C.byref(sp)) != 0
+
+
+# ---------------- experiment plumbing ----------------
+def test_reference_yaml_preset_and_driver_defaults(tmp_path):
+    """A preset in the reference's YAML format (UCIExperimentsConfigurations.yml:1-14) merged over the driver's argparse defaults;
+    the flow it builds has the reference's parameter count (cfg2 = 33 467)."""
+    y = tmp_path / "cfg.yml"
+    y.write_text("power-mono-DAG:\n  dataset: 'power'\n  nb_flow: 1\n  b_size: 2500\n  nb_epoch: 10000\n  conditioner: 'DAG'\n"
+                 "  emb_net: [60, 60, 60, 30]\n  nb_steps_dual: 30\n  l1: 0.\n  gumble_T: .5\n  normalizer: 'monotonic'\n"
+                 "  int_net: [100, 100, 100]\n  nb_steps: 20\n  solver: 'CC'\n  weight_decay: 1e-5\n")
+    cfg = G.experiments.load_preset(str(y), "power-mono-DAG")
+    assert cfg["b_size"] == 2500 and cfg["emb_net"] == [60, 60, 60, 30] and cfg["weight_decay"] == 1e-5 and cfg["learning_rate"] == 1e-3
+    model = G.experiments.build_uci_flow(6, cfg)
+    assert sum(p.numel() for p in model.parameters()) == 33467
+    c = model.getConditioners()[0]
+    assert c.nb_epoch_update == 30 and c.hot_encoding and c.gumble_T == .5
+    with pytest.raises(KeyError):
+        G.experiments.load_preset(str(y), "nope")
+
+
+def test_data_parallel_checkpoint_prefix_and_bpp():
+    model = G.build_from_spec(G.CONFIGS["cfg2"])
+    sd = {"module." + k: v.clone() + 1 for k, v in model.state_dict().items()}          # what nn.DataParallel(model).state_dict() saves
+    G.load_checkpoint(model, sd)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd["module." + k]), k
+    # bits per pixel (ImageExperiments.py:33-37) against the formula written out in float64
+    x, ll = torch.randn(5, 12), torch.randn(5) * 10 - 50
+    ref = (-ll.double() / (12 * np.log(2)) - np.log2(1 - 2e-6) + 8 +
+           (torch.log2(torch.sigmoid(x.double())) + torch.log2(1 - torch.sigmoid(x.double()))).sum(1) / 12)
+    assert torch.allclose(G.compute_bpp(ll, x).double(), ref, atol=1e-5)
