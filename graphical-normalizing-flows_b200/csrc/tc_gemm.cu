@@ -634,6 +634,7 @@ static bool make_operand_map(CUtensorMap* map, const float* base, long long ld, 
 static long long* g_tc_gemm_trace = nullptr;
 static int g_tc_gemm_fold = 2;      // k-chunks accumulated inside the tensor core before a round-to-nearest fold (3xTF32)
 static bool g_tc_gemm_tma = true;   // measurement switch (gnf_tc_gemm_set_tma): 0 forces the cp.async staging path
+static bool g_tc_gemm_v2 = true;    // measurement switch (gnf_tc_gemm_set_v2, dev build): 0 keeps forward / dgrad on the engine above
 
 // hi = rn_tf32(W), lo = rn_tf32(W - hi), both [N][ld] with zero padding columns (ld >= K)
 __global__ void split_tf32_kernel(const float* __restrict__ W, long long ldw, float* __restrict__ hi, float* __restrict__ lo, int ld, int N, int K) {
@@ -645,6 +646,272 @@ __global__ void split_tf32_kernel(const float* __restrict__ W, long long ldw, fl
     hi[i] = h;
     lo[i] = rn_tf32(v - h);
   }
+}
+
+// =====================================================================================================================
+// Engine v2 for the conditioner's hidden layers (DAGMLP, DAGConditioner.py:7-20), forward and dgrad, 3xTF32 with pre-split
+// weights.  What the traces of the kernel above said (profiles/r01zb_tc_gemm_trace_tma_path.txt): its k-chunk cadence is
+// 2.2-2.7 k clocks against 0.77 k of MMA time -- the 8 stager warps need ~1.7 k clocks to turn a landed 16 KB activation
+// tile into hi / lo tiles in shared memory -- and the 16-column transposing epilogue takes 24 k clocks per tile.  Here:
+//   * the activation operand never exists as an MMA tile in shared memory: four A-writer warps (thread = tile row = TMEM
+//     lane) read their row of the TMA-landed raw tile (conflict-free through the 128B swizzle), split it in registers and
+//     write A_hi / A_lo into a two-deep TMEM ring (tcgen05.st); the MMAs are TS form, B = the pre-split weight tiles;
+//   * a stage is 48 KB (raw A + B_hi + B_lo) instead of 64 KB: four stages in flight;
+//   * same accumulation discipline as above (K = 630 is too long for one truncating chain): two partial accumulators and a
+//     round-to-nearest running sum in TMEM, a fold every `fold` k-chunks -- by EIGHT epilogue warps (two per lane quarter,
+//     64 columns each), so that a fold is short and the output pass of a tile hides behind the next tile's first groups
+//     (a version that kept the running sum in registers spilled and was slower: profiles/r02k_gemm2_fold*.txt);
+//   * the final epilogue moves 32-column blocks through a 4 KB XOR-swizzled staging block per warp (rw_gemm_kernel's):
+//     every global instruction covers 4 rows x 128 bytes, the dgrad ReLU mask is applied on the coalesced side.
+// TMEM columns: partials 0 / 128, running sum 256, A ring 384 (two buffers of hi 32 + lo 32).
+// =====================================================================================================================
+constexpr int kG2BN = 128, kG2Stages = 4, kG2Threads = 14 * 32;   // 8 epilogue + 4 A-writer + MMA issuer + TMA producer warps
+constexpr uint32_t kG2TileBytes = 128u * 128u;                    // one 128-row x 32-k fp32 tile
+constexpr uint32_t kG2StageBytes = 3u * kG2TileBytes;             // raw A, B_hi, B_lo
+constexpr int kG2EpiStageFloats = 32 * 32;
+constexpr int kG2ARing = 2;                                       // TMEM: partials at 0 / 128, running sum at 256, A ring at 384 (2 x (hi 32 + lo 32))
+constexpr uint32_t kG2ColRun = 256, kG2ColA = 384;
+
+__global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p, const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo) {
+  using namespace tc;
+  GNF_SMEM(char, smem);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)kG2Stages * kG2StageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 8 * kG2EpiStageFloats);
+  uint64_t* landed = bars;                     // [stages] TMA -> A-writers / MMA (transaction bytes)
+  uint64_t* empty = landed + kG2Stages;        // [stages] MMA -> producer (tcgen05.commit)
+  uint64_t* a_full = empty + kG2Stages;        // [kG2ARing] A-writers -> MMA (one arrive per writer warp)
+  uint64_t* a_empty = a_full + kG2ARing;       // [kG2ARing] MMA -> A-writers (tcgen05.commit)
+  uint64_t* tfull = a_empty + kG2ARing;        // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA (one arrive per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) {
+    for (int s = 0; s < kG2Stages; ++s) { mbar_init(&landed[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < kG2ARing; ++b) { mbar_init(&a_full[b], 4); mbar_init(&a_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM, tiles_n = (p.N + kG2BN - 1) / kG2BN;
+  const int total = tiles_m * tiles_n;
+  const int nchunks = (p.K + kGemmKC - 1) / kGemmKC;
+  const int fold = p.fold < 1 ? 1 : p.fold;
+  const bool b_mn = p.b_src == TCG_SRC_MN;
+
+  if (warp == 13) {
+    // ===================== producer: one thread issues the TMA loads of a stage (raw A, B_hi, B_lo) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tm = w % tiles_m, tn = w / tiles_m;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int s = it % kG2Stages, k0 = c * kGemmKC;
+          mbar_wait(&empty[s], (uint32_t)(((it / kG2Stages) & 1) ^ 1));
+          char* st = smem + (size_t)s * kG2StageBytes;
+          mbar_expect_tx(&landed[s], kG2StageBytes);
+          tma_load_2d(st, &tmA, k0, tm * kGemmBM, &landed[s]);
+          if (!b_mn) {
+            tma_load_2d(st + kG2TileBytes, &tmB, k0, tn * kG2BN, &landed[s]);
+            tma_load_2d(st + 2 * kG2TileBytes, &tmBlo, k0, tn * kG2BN, &landed[s]);
+          } else {
+            for (int sl = 0; sl < kG2BN / 32; ++sl) {
+              tma_load_2d(st + kG2TileBytes + sl * 4096, &tmB, tn * kG2BN + 32 * sl, k0, &landed[s]);
+              tma_load_2d(st + 2 * kG2TileBytes + sl * 4096, &tmBlo, tn * kG2BN + 32 * sl, k0, &landed[s]);
+            }
+          }
+          trace_stamp(p.trace, 0, it);
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ===================== MMA issuer (the whole warp runs the loop converged, one elected lane issues) =====================
+    const uint32_t idesc = make_idesc_tf32(kGemmBM, kG2BN) | (b_mn ? (1u << 16) : 0u);
+    const uint32_t b_step = b_mn ? 64u : 2u;
+    int it = 0, gcount = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int c0 = 0; c0 < nchunks; c0 += fold, ++gcount) {
+        const int acc = gcount & 1;
+        mbar_wait(&tempty[acc], (uint32_t)(((gcount >> 1) & 1) ^ 1));
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kG2BN;
+        const int c1 = (c0 + fold < nchunks) ? c0 + fold : nchunks;
+        uint32_t first = 0u;
+        for (int c = c0; c < c1; ++c, ++it) {
+          const int s = it % kG2Stages, b = it % kG2ARing;
+          mbar_wait(&a_full[b], (uint32_t)((it / kG2ARing) & 1));
+          mbar_wait(&landed[s], (uint32_t)((it / kG2Stages) & 1));
+          fence_after_sync();
+          if (lane == 0) trace_stamp(p.trace, 3, it);
+          const uint32_t st = smem_u32(smem + (size_t)s * kG2StageBytes);
+          const uint64_t db_hi = make_sw128_desc(st + kG2TileBytes, b_mn), db_lo = make_sw128_desc(st + 2 * kG2TileBytes, b_mn);
+          const uint32_t ta_hi = tmem_base + kG2ColA + (uint32_t)b * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+          for (int ks = 0; ks < kGemmKC / 8; ++ks) {
+            const uint64_t ob = (uint64_t)(b_step * ks);
+            mma_tf32_ts_w(d_tmem, ta_hi + ks * 8, db_hi + ob, idesc, first);
+            first = 1u;
+            mma_tf32_ts_w(d_tmem, ta_lo + ks * 8, db_hi + ob, idesc, 1u);
+            mma_tf32_ts_w(d_tmem, ta_hi + ks * 8, db_lo + ob, idesc, 1u);
+          }
+          mma_commit_w(&empty[s]);
+          mma_commit_w(&a_empty[b]);
+        }
+        mma_commit_w(&tfull[acc]);
+        if (lane == 0) trace_stamp(p.trace, 4, gcount);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== A-writers: raw tile row -> TF32 hi / lo in registers -> TMEM ring =====================
+    const int q = warp - 8, row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        const int s = it % kG2Stages, b = it % kG2ARing;
+        mbar_wait(&landed[s], (uint32_t)((it / kG2Stages) & 1));
+        if (tid == 256) trace_stamp(p.trace, 1, it);
+        const char* rp = smem + (size_t)s * kG2StageBytes + row * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = *reinterpret_cast<const uint4*>(rp + ((j ^ (row & 7)) << 4));
+          const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t h = (e[k] + 0x1000u) & 0xffffe000u;
+            hi[4 * j + k] = h;
+            lo[4 * j + k] = __float_as_uint(__uint_as_float(e[k]) - __uint_as_float(h)) + 0x1000u;   // the tensor core drops the low bits
+          }
+        }
+        mbar_wait(&a_empty[b], (uint32_t)(((it / kG2ARing) & 1) ^ 1));
+        fence_after_sync();
+        const uint32_t ta = tmem_base + lane_sel + kG2ColA + (uint32_t)b * 64u;
+        tmem_st32p(ta, hi);
+        tmem_st32p(ta + 32, lo);
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[b]);
+        if (tid == 256) trace_stamp(p.trace, 2, it);
+      }
+    }
+  } else {
+    // ===================== epilogue: folds of the partial accumulators, then the tile's output =====================
+    // Eight warps: warp = (TMEM lane quarter, column half); each folds / emits 64 of the tile's 128 columns of its 32 rows.
+    // The last partial is folded like the others and released at once; the output pass reads the running sum only.
+    const int quarter = warp & 3, half = warp >> 2, ch = 64 * half;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    float* stage = epi_stage + warp * kG2EpiStageFloats;
+    const int sub = lane >> 3, piece = lane & 7;
+    const bool mask = p.epi == TCG_EPI_MASK;
+    const int ngroups = (nchunks + fold - 1) / fold;
+    const uint32_t run = tmem_base + lane_sel + kG2ColRun + (uint32_t)ch;
+    int gcount = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int tm = w % tiles_m, tn = w / tiles_m;
+      const int n0 = tn * kG2BN + ch, m0 = tm * kGemmBM + quarter * 32;
+      for (int g = 0; g < ngroups; ++g, ++gcount) {
+        const int acc = gcount & 1;
+        mbar_wait(&tfull[acc], (uint32_t)((gcount >> 1) & 1));
+        fence_after_sync();
+        if (tid == 0) trace_stamp(p.trace, 5, gcount);
+        const uint32_t part = tmem_base + lane_sel + (uint32_t)acc * kG2BN + (uint32_t)ch;
+        if (ngroups > 1) {
+#pragma unroll
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t a[32];
+            tmem_ld32p(part + c, a);
+            if (g > 0) {
+              uint32_t r[32];
+              tmem_ld32p(run + c, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(r[j]));
+            } else {
+              tmem_wait_ld();
+            }
+            tmem_st32p(run + c, a);
+          }
+          tmem_wait_st();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (tid == 0) trace_stamp(p.trace, 6, gcount);
+        }
+        if (g + 1 < ngroups) continue;
+        // ---- output pass (from the running sum; from the only partial when there was nothing to fold)
+        const uint32_t src = ngroups > 1 ? run : part;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          if (n0 + c >= p.N) break;
+          uint32_t a[32];
+          tmem_ld32p(src + c, a);
+          tmem_wait_ld();
+          if (!mask) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const int nb = n0 + c + 4 * j4;
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias && nb + 4 <= p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb));
+              else if (p.bias && nb < p.N) {               // ragged tail of the bias vector
+                b4.x = __ldg(p.bias + nb);
+                if (nb + 1 < p.N) b4.y = __ldg(p.bias + nb + 1);
+                if (nb + 2 < p.N) b4.z = __ldg(p.bias + nb + 2);
+              }
+              float v0 = __uint_as_float(a[4 * j4]) + b4.x, v1 = __uint_as_float(a[4 * j4 + 1]) + b4.y;
+              float v2 = __uint_as_float(a[4 * j4 + 2]) + b4.z, v3 = __uint_as_float(a[4 * j4 + 3]) + b4.w;
+              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+              *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (j4 ^ (lane & 7))) = make_float4(v0, v1, v2, v3);
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<uint4*>(stage + lane * 32 + 4 * (j4 ^ (lane & 7))) = make_uint4(a[4 * j4], a[4 * j4 + 1], a[4 * j4 + 2], a[4 * j4 + 3]);
+          }
+          __syncwarp();
+          const int n = n0 + c + 4 * piece;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int R = 4 * i + sub, m = m0 + R;
+            uint4 o = *reinterpret_cast<const uint4*>(stage + R * 32 + 4 * (piece ^ (R & 7)));
+            if (m < p.M && n < p.N) {                    // pieces straddling N end in the row's padding (ldc >= round_up(N, 4)): zeros
+              if (mask) {
+                const float4 av = __ldg(reinterpret_cast<const float4*>(p.act + (long long)m * p.ldact + n));
+                o.x = av.x > 0.f ? o.x : 0u; o.y = av.y > 0.f ? o.y : 0u; o.z = av.z > 0.f ? o.z : 0u; o.w = av.w > 0.f ? o.w : 0u;
+              }
+              *reinterpret_cast<uint4*>(p.C + (long long)m * p.ldc + n) = o;
+            }
+          }
+          __syncwarp();
+        }
+        if (ngroups == 1) {                              // nothing was folded: the partial itself was the source, release it now
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static bool g2_eligible(const TcGemmParams& p) {
+  if (p.passes != 3 || !p.B_lo || p.A_lo || p.a_src != TCG_SRC_K || p.epi == TCG_EPI_ATOMIC || p.bits_out || p.mask_bits) return false;
+  if (p.epi == TCG_EPI_BIAS_ACT && p.bias && (p.bias_period > 1 || (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0)) return false;
+  if (p.epi == TCG_EPI_MASK && (!p.act || (reinterpret_cast<uintptr_t>(p.act) & 15) != 0 || (p.ldact % 4) != 0)) return false;
+  const int N4 = (p.N + 3) / 4 * 4;                        // 16-byte pieces: a row's last piece may reach into its padding columns
+  if (p.ldc < N4 || (p.ldc % 4) != 0 || (reinterpret_cast<uintptr_t>(p.C) & 15) != 0) return false;
+  if (p.epi == TCG_EPI_MASK && p.ldact < N4) return false;
+  return p.M >= 1024 && p.N >= 256 && p.K >= 128;          // small problems: the planned tiling of the engine above
 }
 
 int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
@@ -685,6 +952,19 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (!p.B_lo) p.A_lo = nullptr;
   if (p.A_lo && !make_operand_map(&tmAlo, p.A_lo, p.lda, p.a_src, p.M, p.K, kGemmBM))
     return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM: pre-split activations need TMA-loadable operands (16-byte aligned rows)");
+  if (g_tc_gemm_v2 && p.use_tma && g2_eligible(p)) {
+    // engine v2: BN = 128, A through registers into TMEM (the maps of A and of the pre-split B built above already have the
+    // right boxes when the plan chose BN = 128; rebuild B's for that width otherwise)
+    if (p.BN != kG2BN && !(make_operand_map(&tmB, p.B, p.ldb, p.b_src, p.N, p.K, kG2BN) && make_operand_map(&tmBlo, p.B_lo, p.ldb, p.b_src, p.N, p.K, kG2BN)))
+      return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM v2: operand maps");
+    p.BN = kG2BN;
+    p.trace = g_tc_gemm_trace;
+    const size_t smem2 = (size_t)kG2Stages * kG2StageBytes + 8 * kG2EpiStageFloats * sizeof(float) + (2 * kG2Stages + 2 * kG2ARing + 4) * sizeof(uint64_t) + 16;
+    const int total2 = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + kG2BN - 1) / kG2BN);
+    cudaFuncSetAttribute(tc_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    GNF_LAUNCH(tc_gemm2_kernel, total2 < kNumSMs ? total2 : kNumSMs, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
+    return 0;
+  }
   p.trace = g_tc_gemm_trace;
   const long long total = (long long)tiles * p.splits;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
@@ -861,6 +1141,16 @@ int gnf_tc_gemm_plan(int M, int N, int K, int passes, int wgrad, int* bn, int* s
 #endif
 }
 
+#ifdef GNF_DEVTOOLS
+int gnf_tc_gemm_set_v2(int enable) {
+#ifndef GNF_EMU
+  gnf::g_tc_gemm_v2 = enable != 0;
+#else
+  (void)enable;
+#endif
+  return 0;
+}
+#endif
 #ifdef GNF_DEVTOOLS
 int gnf_tc_gemm_set_tma(int enable) {
 #ifdef GNF_EMU

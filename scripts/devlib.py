@@ -22,6 +22,7 @@ DEV_PROTOS = {
     "gnf_linear_wgrad_rw_set_trace": ([_P], C.c_int),
     "gnf_tc_probe": ([_I, _I, _P, _P], C.c_int),
     "gnf_tc_set_trace": ([_P], C.c_int),
+    "gnf_tc_gemm_set_v2": ([_I], C.c_int),
     "gnf_umnn_tc3_set_trace": ([_P], C.c_int),
     "gnf_umnn_tc3_set_debug": ([_I], C.c_int),
 }
