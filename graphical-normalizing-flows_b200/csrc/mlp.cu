@@ -412,6 +412,59 @@ __global__ void __launch_bounds__(kDagDgThreads, 4) dag_l1_dgrad_kernel(GateCtx 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Layer 1 of wide DAG flows (d > 64) for the tensor-core GEMM engine: the masked embedding as a plane
+// ------------------------------------------------------------------------------------------------
+// At d = 784 (cfg5) layer 1 is three 126-GFLOP GEMMs whose operand e[b,i,j] = x[b,j] G[b,i,j] costs a Philox draw, four
+// logarithms and two exponentials per element.  The functor-loader kernels above run them on the FP32 pipe and re-evaluate the
+// gate once per N tile / split-K slice: 9.4 + 15.1 + 5.6 ms per step.  With 180 GB of HBM the other trade is better: write
+// e ONCE as a [B*d, ld] plane (246 MB at cfg5 -- 40 us of HBM time, every gate evaluated once), run forward / wgrad / dgrad on
+// the tcgen05 engine (3xTF32) against it, and fold the gate derivatives into one reduction pass over the [B*d, d] cotangent
+// plane the dgrad GEMM leaves.  Same Philox counters (idx = (b d + i) d + j) as the other kernels: the draws are identical.
+
+// E[m, j] = e[b,i,j], m = b d + i; padding columns [d, ld) = 0.  One CTA per row m.
+__global__ void __launch_bounds__(256) dag_embed_fwd_kernel(GateCtx g, float* __restrict__ E, int lde) {
+  const int m = blockIdx.x, b = m / g.d, i = m - b * g.d;
+  float* row = E + (size_t)m * lde;
+  for (int j4 = threadIdx.x * 4; j4 < lde; j4 += blockDim.x * 4) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (j4 + k < g.d) ? gate_e<false, true>(g, b, i, j4 + k, nullptr, nullptr) : 0.f;
+    *reinterpret_cast<float4*>(row + j4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// dx[b,j] += sum_i dE[(b,i),j] de/dx(b,i,j)  (atomic over the i tiles);  dP[i,j] = sum_b dE[(b,i),j] de/dP(b,i,j)  (owned).
+// CTA = 128 columns j x 8 rows i (two thread rows of four i each), loops over the batch.  grid = (ceil(d/128), ceil(d/8)).
+constexpr int kEmbBwdI = 4;
+__global__ void __launch_bounds__(256) dag_embed_bwd_kernel(GateCtx g, const float* __restrict__ dE, int lde, float* __restrict__ dx,
+                                                            float* __restrict__ dP, int B) {
+  const int j = blockIdx.x * 128 + (threadIdx.x & 127);
+  const int i0 = blockIdx.y * (2 * kEmbBwdI) + (threadIdx.x >> 7) * kEmbBwdI;
+  if (j >= g.d || i0 >= g.d) return;
+  float acc[kEmbBwdI];
+#pragma unroll
+  for (int k = 0; k < kEmbBwdI; ++k) acc[k] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float dxs = 0.f;
+#pragma unroll
+    for (int k = 0; k < kEmbBwdI; ++k) {
+      const int i = i0 + k;
+      if (i < g.d) {
+        const float v = __ldg(dE + ((size_t)b * g.d + i) * lde + j);
+        float ddx, ddp;
+        gate_e<true, true>(g, b, i, j, &ddx, &ddp);
+        dxs = fmaf(v, ddx, dxs);
+        acc[k] = fmaf(v, ddp, acc[k]);
+      }
+    }
+    atomicAdd(dx + (size_t)b * g.d + j, dxs);
+  }
+#pragma unroll
+  for (int k = 0; k < kEmbBwdI; ++k)
+    if (i0 + k < g.d) dP[(size_t)(i0 + k) * g.d + j] = acc[k];
+}
+
 static int g_dag_l1_resident = 1;   // measurement switch (gnf_dag_l1_set_resident): 0 = functor-loader tile GEMM for every d
 
 static int make_gate(GateCtx* out, const float* x, const float* P, const gnf_gate_t* gate, int d) {
@@ -721,6 +774,31 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   if (d >= kGateInlineMinD) launch_gemm_auto(al, bl, EpiDagDgrad<true>{g, dx, dP}, M, d, N, true, s);
   else launch_gemm_auto(al, bl, EpiDagDgrad<false>{g, dx, dP}, M, d, N, true, s);
   return check_launch("gnf_dag_l1_dgrad");
+}
+
+int gnf_dag_embed_fwd(const float* x, const float* P, const gnf_gate_t* gate, float* E, int lde, int B, int d, gnf_stream_t stream) {
+  if (!x || !P || !E || B < 0 || d <= 0 || lde < d || (lde % 4) != 0 || (reinterpret_cast<uintptr_t>(E) & 15) != 0)
+    return fail(GNF_ERR_INVALID, "gnf_dag_embed_fwd: bad arguments (E rows must be 16-byte aligned: lde %% 4 == 0)");
+  GateCtx g;
+  if (int e = make_gate(&g, x, P, gate, d)) return e;
+  if (B == 0) return 0;
+  GNF_LAUNCH(dag_embed_fwd_kernel, B * d, 256, 0, (cudaStream_t)stream, g, E, lde);
+  return check_launch("gnf_dag_embed_fwd");
+}
+
+int gnf_dag_embed_bwd(const float* dE, int lde, const float* x, const float* P, const gnf_gate_t* gate, float* dx, float* dP, int B, int d,
+                      gnf_stream_t stream) {
+  if (!dE || !x || !P || !dx || !dP || B < 0 || d <= 0 || lde < d) return fail(GNF_ERR_INVALID, "gnf_dag_embed_bwd: bad arguments");
+  GateCtx g;
+  if (int e = make_gate(&g, x, P, gate, d)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(dx, 0, (size_t)B * d * sizeof(float), s);
+  if (B == 0) {
+    cudaMemsetAsync(dP, 0, (size_t)d * d * sizeof(float), s);
+    return check_launch("gnf_dag_embed_bwd");
+  }
+  GNF_LAUNCH(dag_embed_bwd_kernel, dim3(ceil_div(d, 128), ceil_div(d, 2 * kEmbBwdI)), 256, 0, s, g, dE, lde, dx, dP, B);
+  return check_launch("gnf_dag_embed_bwd");
 }
 
 #ifdef GNF_DEVTOOLS

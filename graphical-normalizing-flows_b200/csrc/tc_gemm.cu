@@ -324,15 +324,21 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
             const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
             const uint64_t da_hi = make_sw128_desc(st, a_mn), db_hi = make_sw128_desc(st + a_bytes, b_mn);
             const uint64_t da_lo = make_sw128_desc(st + a_bytes + b_bytes, a_mn), db_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes, b_mn);
+            // 3xTF32: the correction products of the chunk first (they accumulate at 2^-11 of the result's magnitude, where the
+            // tensor core's one-sided truncation of the accumulator costs nothing), then the a_hi b_hi chain
+            if (split) {
 #pragma unroll
-            for (int ks = 0; ks < kGemmKC / 8; ++ks) {
-              const uint64_t oa = (uint64_t)(a_step * ks), ob = (uint64_t)(b_step * ks);
-              mma_tf32_ss_w(d_tmem, da_hi + oa, db_hi + ob, idesc, first ? 0u : 1u);
-              first = false;
-              if (split) {
-                mma_tf32_ss_w(d_tmem, da_lo + oa, db_hi + ob, idesc, 1u);
+              for (int ks = 0; ks < kGemmKC / 8; ++ks) {
+                const uint64_t oa = (uint64_t)(a_step * ks), ob = (uint64_t)(b_step * ks);
+                mma_tf32_ss_w(d_tmem, da_lo + oa, db_hi + ob, idesc, first ? 0u : 1u);
+                first = false;
                 mma_tf32_ss_w(d_tmem, da_hi + oa, db_lo + ob, idesc, 1u);
               }
+            }
+#pragma unroll
+            for (int ks = 0; ks < kGemmKC / 8; ++ks) {
+              mma_tf32_ss_w(d_tmem, da_hi + (uint64_t)(a_step * ks), db_hi + (uint64_t)(b_step * ks), idesc, first ? 0u : 1u);
+              first = false;
             }
             mma_commit_w(&empty[s]);
           }
@@ -633,8 +639,15 @@ static bool make_operand_map(CUtensorMap* map, const float* base, long long ld, 
 
 static long long* g_tc_gemm_trace = nullptr;
 static int g_tc_gemm_fold = 2;      // k-chunks accumulated inside the tensor core before a round-to-nearest fold (3xTF32)
+static int g_tc_gemm_fold2 = 2;     // ... of engine v2 (forward / dgrad with pre-split weights).  With the correction products first, fold 2 leaves a
+                                    // relative error of 2.7e-7 (one-sided part 1.4e-7), fold 1 1.1e-7 (4e-8) = the FFMA engine's, at +15 % time
+                                    // (profiles/r02q_gemm2_fold_variants.txt).  The first layer of a wide DAG flow (periodic bias table) always folds
+                                    // every chunk: its rounding error passes through every later layer and through the gate derivative, and the
+                                    // gradients of A / W1 at cfg5 sit on ReLU-flip noise of that size (profiles/r02p_cfg5_grad_accuracy*.txt).
+static bool g_tc_gemm_fold_forced = false;   // dev build: gnf_tc_gemm_set_fold overrides both rules
 static bool g_tc_gemm_tma = true;   // measurement switch (gnf_tc_gemm_set_tma): 0 forces the cp.async staging path
-static bool g_tc_gemm_v2 = true;    // measurement switch (gnf_tc_gemm_set_v2, dev build): 0 keeps forward / dgrad on the engine above
+static int g_tc_gemm_v2 = 1;        // measurement switch (gnf_tc_gemm_set_v2, dev build): 0 keeps forward / dgrad on the engine above,
+                                    // 1 = two partial accumulators + four A buffers, 2 = three partials + two A buffers
 
 // hi = rn_tf32(W), lo = rn_tf32(W - hi), both [N][ld] with zero padding columns (ld >= K)
 __global__ void split_tf32_kernel(const float* __restrict__ W, long long ldw, float* __restrict__ hi, float* __restrict__ lo, int ld, int N, int K) {
@@ -657,20 +670,22 @@ __global__ void split_tf32_kernel(const float* __restrict__ W, long long ldw, fl
 //     lane) read their row of the TMA-landed raw tile (conflict-free through the 128B swizzle), split it in registers and
 //     write A_hi / A_lo into a two-deep TMEM ring (tcgen05.st); the MMAs are TS form, B = the pre-split weight tiles;
 //   * a stage is 48 KB (raw A + B_hi + B_lo) instead of 64 KB: four stages in flight;
-//   * same accumulation discipline as above (K = 630 is too long for one truncating chain): two partial accumulators and a
-//     round-to-nearest running sum in TMEM, a fold every `fold` k-chunks -- by EIGHT epilogue warps (two per lane quarter,
-//     64 columns each), so that a fold is short and the output pass of a tile hides behind the next tile's first groups
-//     (a version that kept the running sum in registers spilled and was slower: profiles/r02k_gemm2_fold*.txt);
+//   * same accumulation discipline as above (the tensor core truncates its accumulator after every MMA, one-sided): two
+//     partial accumulators in TMEM, folded every `fold` k-chunks into a round-to-nearest running sum that EIGHT epilogue
+//     warps (two per lane quarter, 64 columns each) keep in registers, so that a fold is one TMEM read + 64 additions and the
+//     output pass of a tile hides behind the next tile's first groups; correction products go first inside every chunk;
 //   * the final epilogue moves 32-column blocks through a 4 KB XOR-swizzled staging block per warp (rw_gemm_kernel's):
 //     every global instruction covers 4 rows x 128 bytes, the dgrad ReLU mask is applied on the coalesced side.
-// TMEM columns: partials 0 / 128, running sum 256, A ring 384 (two buffers of hi 32 + lo 32).
+// TMEM columns: partials 0 / 128, A ring 256 (four buffers of hi 32 + lo 32).
 // =====================================================================================================================
 constexpr int kG2BN = 128, kG2Stages = 4, kG2Threads = 14 * 32;   // 8 epilogue + 4 A-writer + MMA issuer + TMA producer warps
 constexpr uint32_t kG2TileBytes = 128u * 128u;                    // one 128-row x 32-k fp32 tile
 constexpr uint32_t kG2StageBytes = 3u * kG2TileBytes;             // raw A, B_hi, B_lo
 constexpr int kG2EpiStageFloats = 32 * 32;
-constexpr int kG2ARing = 2;                                       // TMEM: partials at 0 / 128, running sum at 256, A ring at 384 (2 x (hi 32 + lo 32))
-constexpr uint32_t kG2ColRun = 256, kG2ColA = 384;
+constexpr int kG2MaxRing = 4, kG2MaxParts = 3;
+
+// kParts partial accumulators of 128 TMEM columns, then kRing A buffers of (hi 32 + lo 32) columns: (2, 4) or (3, 2) fill 512.
+template <int kParts, int kRing>
 
 __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p, const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo) {
@@ -680,18 +695,20 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 8 * kG2EpiStageFloats);
   uint64_t* landed = bars;                     // [stages] TMA -> A-writers / MMA (transaction bytes)
   uint64_t* empty = landed + kG2Stages;        // [stages] MMA -> producer (tcgen05.commit)
-  uint64_t* a_full = empty + kG2Stages;        // [kG2ARing] A-writers -> MMA (one arrive per writer warp)
-  uint64_t* a_empty = a_full + kG2ARing;       // [kG2ARing] MMA -> A-writers (tcgen05.commit)
-  uint64_t* tfull = a_empty + kG2ARing;        // [2] MMA -> epilogue
-  uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA (one arrive per epilogue warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  constexpr uint32_t kG2ColA = 128u * kParts;
+  static_assert(kG2ColA + 64u * kRing <= 512u && kParts <= kG2MaxParts && kRing <= kG2MaxRing, "TMEM budget");
+  uint64_t* a_full = empty + kG2Stages;        // [kRing] A-writers -> MMA (one arrive per writer warp)
+  uint64_t* a_empty = a_full + kG2MaxRing;     // [kRing] MMA -> A-writers (tcgen05.commit)
+  uint64_t* tfull = a_empty + kG2MaxRing;      // [kParts] MMA -> epilogue
+  uint64_t* tempty = tfull + kG2MaxParts;      // [kParts] epilogue -> MMA (one arrive per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kG2MaxParts);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 32) {
     for (int s = 0; s < kG2Stages; ++s) { mbar_init(&landed[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < kG2ARing; ++b) { mbar_init(&a_full[b], 4); mbar_init(&a_empty[b], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    for (int b = 0; b < kRing; ++b) { mbar_init(&a_full[b], 4); mbar_init(&a_empty[b], 1); }
+    for (int b = 0; b < kParts; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
     fence_mbar_init();
   }
   fence_before_sync();
@@ -737,29 +754,33 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
     int it = 0, gcount = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       for (int c0 = 0; c0 < nchunks; c0 += fold, ++gcount) {
-        const int acc = gcount & 1;
-        mbar_wait(&tempty[acc], (uint32_t)(((gcount >> 1) & 1) ^ 1));
+        const int acc = gcount % kParts;
+        mbar_wait(&tempty[acc], (uint32_t)(((gcount / kParts) & 1) ^ 1));
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kG2BN;
         const int c1 = (c0 + fold < nchunks) ? c0 + fold : nchunks;
         uint32_t first = 0u;
         for (int c = c0; c < c1; ++c, ++it) {
-          const int s = it % kG2Stages, b = it % kG2ARing;
-          mbar_wait(&a_full[b], (uint32_t)((it / kG2ARing) & 1));
+          const int s = it % kG2Stages, b = it % kRing;
+          mbar_wait(&a_full[b], (uint32_t)((it / kRing) & 1));
           mbar_wait(&landed[s], (uint32_t)((it / kG2Stages) & 1));
           fence_after_sync();
           if (lane == 0) trace_stamp(p.trace, 3, it);
           const uint32_t st = smem_u32(smem + (size_t)s * kG2StageBytes);
           const uint64_t db_hi = make_sw128_desc(st + kG2TileBytes, b_mn), db_lo = make_sw128_desc(st + 2 * kG2TileBytes, b_mn);
           const uint32_t ta_hi = tmem_base + kG2ColA + (uint32_t)b * 64u, ta_lo = ta_hi + 32u;
+          // The tensor core truncates its fp32 accumulator after every MMA (one-sided: profiles/r02p_gemm2_fold_cfg5_shapes.txt).
+          // Correction products first: while the partial only holds a_lo b_hi + a_hi b_lo terms (2^-11 of the result) their
+          // truncations cost nothing; only the a_hi b_hi MMAs accumulate at full magnitude.
 #pragma unroll
           for (int ks = 0; ks < kGemmKC / 8; ++ks) {
             const uint64_t ob = (uint64_t)(b_step * ks);
-            mma_tf32_ts_w(d_tmem, ta_hi + ks * 8, db_hi + ob, idesc, first);
+            mma_tf32_ts_w(d_tmem, ta_lo + ks * 8, db_hi + ob, idesc, first);
             first = 1u;
-            mma_tf32_ts_w(d_tmem, ta_lo + ks * 8, db_hi + ob, idesc, 1u);
             mma_tf32_ts_w(d_tmem, ta_hi + ks * 8, db_lo + ob, idesc, 1u);
           }
+#pragma unroll
+          for (int ks = 0; ks < kGemmKC / 8; ++ks) mma_tf32_ts_w(d_tmem, ta_hi + ks * 8, db_hi + (uint64_t)(b_step * ks), idesc, 1u);
           mma_commit_w(&empty[s]);
           mma_commit_w(&a_empty[b]);
         }
@@ -774,7 +795,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       for (int c = 0; c < nchunks; ++c, ++it) {
-        const int s = it % kG2Stages, b = it % kG2ARing;
+        const int s = it % kG2Stages, b = it % kRing;
         mbar_wait(&landed[s], (uint32_t)((it / kG2Stages) & 1));
         if (tid == 256) trace_stamp(p.trace, 1, it);
         const char* rp = smem + (size_t)s * kG2StageBytes + row * 128;
@@ -790,7 +811,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
             lo[4 * j + k] = __float_as_uint(__uint_as_float(e[k]) - __uint_as_float(h)) + 0x1000u;   // the tensor core drops the low bits
           }
         }
-        mbar_wait(&a_empty[b], (uint32_t)(((it / kG2ARing) & 1) ^ 1));
+        mbar_wait(&a_empty[b], (uint32_t)(((it / kRing) & 1) ^ 1));
         fence_after_sync();
         const uint32_t ta = tmem_base + lane_sel + kG2ColA + (uint32_t)b * 64u;
         tmem_st32p(ta, hi);
@@ -804,57 +825,50 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
     }
   } else {
     // ===================== epilogue: folds of the partial accumulators, then the tile's output =====================
-    // Eight warps: warp = (TMEM lane quarter, column half); each folds / emits 64 of the tile's 128 columns of its 32 rows.
-    // The last partial is folded like the others and released at once; the output pass reads the running sum only.
+    // Eight warps: warp = (TMEM lane quarter, column half); each keeps the round-to-nearest running sum of its 32 rows x 64
+    // columns of the tile in REGISTERS (64 per thread): a fold is one TMEM read of the partial + 64 additions, the partial is
+    // released at once, and the output pass works from registers (no running sum in TMEM: its 128 columns widen the A ring).
     const int quarter = warp & 3, half = warp >> 2, ch = 64 * half;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     float* stage = epi_stage + warp * kG2EpiStageFloats;
     const int sub = lane >> 3, piece = lane & 7;
     const bool mask = p.epi == TCG_EPI_MASK;
+    const bool table = !mask && p.bias != nullptr && p.bias_period > 1;   // periodic bias table (DAG layer 1: one row per variable): added on the coalesced side
     const int ngroups = (nchunks + fold - 1) / fold;
-    const uint32_t run = tmem_base + lane_sel + kG2ColRun + (uint32_t)ch;
     int gcount = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int tm = w % tiles_m, tn = w / tiles_m;
       const int n0 = tn * kG2BN + ch, m0 = tm * kGemmBM + quarter * 32;
+      float run[64];
       for (int g = 0; g < ngroups; ++g, ++gcount) {
-        const int acc = gcount & 1;
-        mbar_wait(&tfull[acc], (uint32_t)((gcount >> 1) & 1));
+        const int acc = gcount % kParts;
+        mbar_wait(&tfull[acc], (uint32_t)((gcount / kParts) & 1));
         fence_after_sync();
         if (tid == 0) trace_stamp(p.trace, 5, gcount);
         const uint32_t part = tmem_base + lane_sel + (uint32_t)acc * kG2BN + (uint32_t)ch;
-        if (ngroups > 1) {
 #pragma unroll
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t a[32];
-            tmem_ld32p(part + c, a);
-            if (g > 0) {
-              uint32_t r[32];
-              tmem_ld32p(run + c, r);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(r[j]));
-            } else {
-              tmem_wait_ld();
-            }
-            tmem_st32p(run + c, a);
-          }
-          tmem_wait_st();
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-          if (tid == 0) trace_stamp(p.trace, 6, gcount);
-        }
-        if (g + 1 < ngroups) continue;
-        // ---- output pass (from the running sum; from the only partial when there was nothing to fold)
-        const uint32_t src = ngroups > 1 ? run : part;
-#pragma unroll 1
         for (int c = 0; c < 64; c += 32) {
-          if (n0 + c >= p.N) break;
           uint32_t a[32];
-          tmem_ld32p(src + c, a);
+          tmem_ld32p(part + c, a);
           tmem_wait_ld();
-          if (!mask) {
+          if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) run[c + j] = __uint_as_float(a[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) run[c + j] += __uint_as_float(a[j]);
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (tid == 0) trace_stamp(p.trace, 6, gcount);
+      }
+      // ---- output pass
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        if (n0 + c < p.N) {
+          if (!mask && !table) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const int nb = n0 + c + 4 * j4;
@@ -865,15 +879,15 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
                 if (nb + 1 < p.N) b4.y = __ldg(p.bias + nb + 1);
                 if (nb + 2 < p.N) b4.z = __ldg(p.bias + nb + 2);
               }
-              float v0 = __uint_as_float(a[4 * j4]) + b4.x, v1 = __uint_as_float(a[4 * j4 + 1]) + b4.y;
-              float v2 = __uint_as_float(a[4 * j4 + 2]) + b4.z, v3 = __uint_as_float(a[4 * j4 + 3]) + b4.w;
+              float v0 = run[c + 4 * j4] + b4.x, v1 = run[c + 4 * j4 + 1] + b4.y, v2 = run[c + 4 * j4 + 2] + b4.z, v3 = run[c + 4 * j4 + 3] + b4.w;
               if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
               *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (j4 ^ (lane & 7))) = make_float4(v0, v1, v2, v3);
             }
           } else {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
-              *reinterpret_cast<uint4*>(stage + lane * 32 + 4 * (j4 ^ (lane & 7))) = make_uint4(a[4 * j4], a[4 * j4 + 1], a[4 * j4 + 2], a[4 * j4 + 3]);
+              *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (j4 ^ (lane & 7))) =
+                  make_float4(run[c + 4 * j4], run[c + 4 * j4 + 1], run[c + 4 * j4 + 2], run[c + 4 * j4 + 3]);
           }
           __syncwarp();
           const int n = n0 + c + 4 * piece;
@@ -885,16 +899,16 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
               if (mask) {
                 const float4 av = __ldg(reinterpret_cast<const float4*>(p.act + (long long)m * p.ldact + n));
                 o.x = av.x > 0.f ? o.x : 0u; o.y = av.y > 0.f ? o.y : 0u; o.z = av.z > 0.f ? o.z : 0u; o.w = av.w > 0.f ? o.w : 0u;
+              } else if (table) {                        // N % 4 == 0 here (g2_eligible): the piece is inside the table row
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)(m % p.bias_period) * p.bias_ld + n));
+                float v0 = __uint_as_float(o.x) + b4.x, v1 = __uint_as_float(o.y) + b4.y, v2 = __uint_as_float(o.z) + b4.z, v3 = __uint_as_float(o.w) + b4.w;
+                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                o = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
               }
               *reinterpret_cast<uint4*>(p.C + (long long)m * p.ldc + n) = o;
             }
           }
           __syncwarp();
-        }
-        if (ngroups == 1) {                              // nothing was folded: the partial itself was the source, release it now
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
         }
       }
     }
@@ -906,7 +920,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
 
 static bool g2_eligible(const TcGemmParams& p) {
   if (p.passes != 3 || !p.B_lo || p.A_lo || p.a_src != TCG_SRC_K || p.epi == TCG_EPI_ATOMIC || p.bits_out || p.mask_bits) return false;
-  if (p.epi == TCG_EPI_BIAS_ACT && p.bias && (p.bias_period > 1 || (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0)) return false;
+  if (p.epi == TCG_EPI_BIAS_ACT && p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0) return false;
+  if (p.epi == TCG_EPI_BIAS_ACT && p.bias && p.bias_period > 1 && ((p.N % 4) != 0 || (p.bias_ld % 4) != 0)) return false;
   if (p.epi == TCG_EPI_MASK && (!p.act || (reinterpret_cast<uintptr_t>(p.act) & 15) != 0 || (p.ldact % 4) != 0)) return false;
   const int N4 = (p.N + 3) / 4 * 4;                        // 16-byte pieces: a row's last piece may reach into its padding columns
   if (p.ldc < N4 || (p.ldc % 4) != 0 || (reinterpret_cast<uintptr_t>(p.C) & 15) != 0) return false;
@@ -958,11 +973,21 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
     if (p.BN != kG2BN && !(make_operand_map(&tmB, p.B, p.ldb, p.b_src, p.N, p.K, kG2BN) && make_operand_map(&tmBlo, p.B_lo, p.ldb, p.b_src, p.N, p.K, kG2BN)))
       return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM v2: operand maps");
     p.BN = kG2BN;
+    p.fold = (!g_tc_gemm_fold_forced && p.epi == TCG_EPI_BIAS_ACT && p.bias && p.bias_period > 1) ? 1 : g_tc_gemm_fold2;
     p.trace = g_tc_gemm_trace;
-    const size_t smem2 = (size_t)kG2Stages * kG2StageBytes + 8 * kG2EpiStageFloats * sizeof(float) + (2 * kG2Stages + 2 * kG2ARing + 4) * sizeof(uint64_t) + 16;
+    const size_t smem2 = (size_t)kG2Stages * kG2StageBytes + 8 * kG2EpiStageFloats * sizeof(float) +
+                         (2 * kG2Stages + 2 * kG2MaxRing + 2 * kG2MaxParts) * sizeof(uint64_t) + 16;
     const int total2 = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + kG2BN - 1) / kG2BN);
-    cudaFuncSetAttribute(tc_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    GNF_LAUNCH(tc_gemm2_kernel, total2 < kNumSMs ? total2 : kNumSMs, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
+    const int grid2 = total2 < kNumSMs ? total2 : kNumSMs;
+#ifdef GNF_DEVTOOLS
+    if (g_tc_gemm_v2 == 2) {                     // measured equal to the default below at every fold interval (profiles/r02q_gemm2_fold_variants.txt)
+      cudaFuncSetAttribute(tc_gemm2_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      GNF_LAUNCH((tc_gemm2_kernel<3, 2>), grid2, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
+      return 0;
+    }
+#endif
+    cudaFuncSetAttribute(tc_gemm2_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    GNF_LAUNCH((tc_gemm2_kernel<2, 4>), grid2, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
     return 0;
   }
   p.trace = g_tc_gemm_trace;
@@ -1110,6 +1135,8 @@ int gnf_tc_gemm_set_fold(int chunks) {
 #else
   if (chunks < 1) return fail(GNF_ERR_INVALID, "gnf_tc_gemm_set_fold: need >= 1 k-chunk per fold");
   g_tc_gemm_fold = chunks > (1 << 20) ? (1 << 20) : chunks;
+  g_tc_gemm_fold2 = g_tc_gemm_fold;
+  g_tc_gemm_fold_forced = true;
   return 0;
 #endif
 }
@@ -1144,7 +1171,7 @@ int gnf_tc_gemm_plan(int M, int N, int K, int passes, int wgrad, int* bn, int* s
 #ifdef GNF_DEVTOOLS
 int gnf_tc_gemm_set_v2(int enable) {
 #ifndef GNF_EMU
-  gnf::g_tc_gemm_v2 = enable != 0;
+  gnf::g_tc_gemm_v2 = enable;
 #else
   (void)enable;
 #endif
@@ -1171,7 +1198,7 @@ int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, floa
   if (!dY || !X || !dW || M < 0 || N <= 0 || K <= 0 || lddy < N || ldx < K || lddw < K) return fail(GNF_ERR_INVALID, "gnf_linear_wgrad_tc: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   if (lddw == K) cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s);
-  else for (int n = 0; n < N; ++n) cudaMemsetAsync(dW + (size_t)n * lddw, 0, (size_t)K * sizeof(float), s);
+  else cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)N, s);
   if (M == 0) return check_launch("gnf_linear_wgrad_tc");
   TcGemmParams p = {};
   p.A = dY; p.lda = lddy; p.a_src = TCG_SRC_MN;        // A(n, m) = dY[m*lddy + n]: contiguous along the output row index

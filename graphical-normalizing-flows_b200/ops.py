@@ -428,16 +428,18 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None, dy_split=None):
     return out
 
 
-def linear_wgrad(dY, lddy, X, ldx, M, N, K, dy_split=None, x_split=None):
-    dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
+def linear_wgrad(dY, lddy, X, ldx, M, N, K, dy_split=None, x_split=None, out=None, lddw=None):
+    """dW[n, k] = sum_m dY[m, n] X[m, k]; `out` / `lddw`: write into the first K columns of a wider [N, lddw] matrix."""
+    dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype) if out is None else out
+    lddw = K if out is None else lddw
     passes = _gemm_passes(M, N, K, "wgrad")
     if passes == 3 and PRESPLIT_ACTS and dy_split is not None and x_split is not None:
-        _ps2(2, dy_split, x_split, (dy_split[0].stride(0), x_split[0].stride(0)), None, 1, None, dW, K, M, N, K, 0, "gnf_linear_wgrad_tc")
+        _ps2(2, dy_split, x_split, (dy_split[0].stride(0), x_split[0].stride(0)), None, 1, None, dW, lddw, M, N, K, 0, "gnf_linear_wgrad_tc")
     elif passes:
         _note_flops("gnf_linear_wgrad_tc", 2. * M * N * K)
-        _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, passes, stream_ptr())
+        _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), lddw, M, N, K, passes, stream_ptr())
     else:
-        _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, M, N, K, stream_ptr())
+        _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), lddw, M, N, K, stream_ptr())
     _count()
     return dW
 
@@ -617,6 +619,19 @@ def dag_dump_noise(gate, B, d, device):
     return (n1, n2) if n2 is not None else (n1,)
 
 
+# Wide DAG flows (d > DAG_L1_PLANE_MIN_D, e.g. MNIST d = 784) with a tensor-core GEMM mode: layer 1 runs as three GEMMs of the
+# tcgen05 engine against the masked embedding written once as a [B*d, d] plane (gnf_dag_embed_fwd / _bwd) instead of the FFMA
+# kernels that generate the gate inside their operand loaders: cfg5 layer 1 30 ms -> ~4 ms per step (profiles/r02p_*).
+DAG_L1_PLANE = True
+DAG_L1_PLANE_MIN_D = 65
+
+
+def _dag_l1_plane(M, N1, d, direction):
+    """direction 'fwd' / 'bwd'; DAG_L1_PLANE may also be the string 'fwd' or 'bwd' (measurement: one direction only)."""
+    on = DAG_L1_PLANE is True or DAG_L1_PLANE == direction
+    return on and d >= DAG_L1_PLANE_MIN_D and M > 0 and _gemm_passes(M, N1, d) != 0 and not L._SIMULATOR
+
+
 class DagMlpFn(torch.autograd.Function):
     """DAGConditioner.forward (DAGConditioner.py:126-169): gate/threshold of A, masked expansion of x,
     optional one-hot encoding, embedding MLP — with the [B,d,d] masked tensor generated inside the first
@@ -646,9 +661,17 @@ class DagMlpFn(torch.autograd.Function):
         _call("gnf_dag_bias_table", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st)
         g = gate.c_struct()
         y = _rows(B * d, N1, x) if n > 1 else torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
-        _call("gnf_dag_l1_fwd", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
-                                   ptr(y), y.stride(0), B, d, N1, int(n > 1), st)
-        _count(3)
+        E = W1e = None
+        if _dag_l1_plane(B * d, N1, d, "fwd"):
+            E = _rows(B * d, d, x)
+            _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), E.stride(0), B, d, st)
+            W1e = weights[0][:, :d]                 # the masked-input half of layer 1; the one-hot half is the bias table T
+            linear_fwd(E, W1e, T, relu=(n > 1), bias_period=(d if hot else 1), out=y, ldy=y.stride(0), K=d, ldx=E.stride(0))
+            _count(2)
+        else:
+            _call("gnf_dag_l1_fwd", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
+                                       ptr(y), y.stride(0), B, d, N1, int(n > 1), st)
+            _count(3)
         acts = []
         splits = [None] * n       # splits[l] = TF32 (hi, lo) of layer l's input, when its forward GEMM ran pre-split: reused by its wgrad
         cur = y
@@ -659,6 +682,7 @@ class DagMlpFn(torch.autograd.Function):
                 out = torch.empty(B, d, weights[l].shape[0], device=x.device, dtype=x.dtype)
             cur, splits[l] = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), out=out, ldy=weights[l].shape[0], want_split=True)
         ctx.act_splits = splits if any(ctx.needs_input_grad) else None
+        ctx.E, ctx.W1e = (E, W1e) if any(ctx.needs_input_grad) else (None, None)
         ctx.save_for_backward(x, A, P, dPdA, *weights, *acts)
         ctx.gate, ctx.hot, ctx.n = gate, hot, n
         if n == 1:
@@ -683,7 +707,18 @@ class DagMlpFn(torch.autograd.Function):
         N1 = W1.shape[0]
         g = gate.c_struct()
         dW1 = torch.empty_like(W1)
-        _call("gnf_dag_l1_wgrad", ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st)
+        E, W1e = ctx.E, ctx.W1e
+        ctx.E = ctx.W1e = None
+        if E is not None and not _dag_l1_plane(M, N1, d, "bwd"):
+            E = None
+        elif E is None and _dag_l1_plane(M, N1, d, "bwd"):        # forward ran on the loader kernels: regenerate the plane (same Philox counters)
+            E = _rows(M, d, x)
+            _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), E.stride(0), B, d, st)
+            W1e = W1[:, :d]
+        if E is not None:
+            linear_wgrad(delta, delta.stride(0), E, E.stride(0), M, N1, d, out=dW1, lddw=dW1.stride(0))
+        else:
+            _call("gnf_dag_l1_wgrad", ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st)
         dT = colsum(delta, delta.stride(0), M, N1, period=(d if hot else 1))
         db1 = torch.empty(N1, device=x.device, dtype=x.dtype)
         _call("gnf_dag_bias_table_bwd", ptr(dT), ptr(dW1), W1.stride(0), ptr(db1), d, N1, int(hot), st)
@@ -693,8 +728,13 @@ class DagMlpFn(torch.autograd.Function):
         if needs[0] or needs[1]:
             dx = torch.empty_like(x)
             dP = torch.empty_like(A)
-            _call("gnf_dag_l1_dgrad", ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx),
-                                         ptr(dP), B, d, N1, st)
+            if E is not None:
+                dE = linear_dgrad(delta, delta.stride(0), W1e, None, M)
+                _call("gnf_dag_embed_bwd", ptr(dE), dE.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx), ptr(dP), B, d, st)
+                del dE
+            else:
+                _call("gnf_dag_l1_dgrad", ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx),
+                                             ptr(dP), B, d, N1, st)
             dA = torch.empty_like(A)
             _call("gnf_dag_finish_dA", ptr(dP), ptr(dPdA), ptr(dA), d, 0, st)
             _count(2)

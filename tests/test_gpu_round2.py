@@ -94,6 +94,66 @@ def test_cfg3_vs_oracle_batch512(engine_reset):
     _strict_check(M.compare(M.CONFIGS["cfg3"], 512, "cuda", train=True))
 
 
+def test_bench_eval_mode_cfg5_vs_oracle(engine_reset):
+    """cfg5 (d = 784, Affine) in bench.py's eval mode: with a tensor-core GEMM mode layer 1 of the DAG conditioner runs as a
+    single-pass TF32 GEMM against the masked-embedding plane too (gnf_dag_embed_fwd); ll within the TF32 bar at B = 16."""
+    import model_vs_oracle as M
+    spec = M.CONFIGS["cfg5"]
+    B = 16
+    model = M.build(spec, "cuda")
+    G.ops.set_gemm_mode("auto-fast")
+    x = torch.randn(B, spec["d"], generator=torch.Generator().manual_seed(5)).cuda()
+    step = G.GraphedEvalStep(model, x, warmup=2)
+    ll, z = step(x)
+    ll, z = ll.clone(), z.clone()
+    noises = [tuple(n.cpu() for n in G.ops.dag_dump_noise(c._last_gate, B, spec["d"], x.device)) for c in model.getConditioners()]
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ospec = {k: v for k, v in spec.items() if k != "A_prior"}
+    with torch.no_grad():
+        ll_o, z_o = O.compute_ll(x.cpu(), sd, ospec, None, noises, 20)
+    rel = rel_err(ll.cpu(), ll_o)
+    assert rel < 2e-3, f"cfg5: per-sample ll relative error {rel} (TF32 bar 2e-3)"
+
+
+@pytest.mark.parametrize("mode,imp", [("GATE_GUMBEL", "IMP_SOFT"), ("GATE_TABLE", "IMP_HARD_SOFT"), ("GATE_NOISER", "IMP_SOFT")])
+@pytest.mark.parametrize("B,d,N1,hot", [(40, 96, 160, True), (7, 130, 136, False)])
+@pytest.mark.parametrize("layers", [1, 2])
+def test_dag_layer1_embedding_plane_matches_the_loader_kernels(engine_reset, mode, imp, B, d, N1, hot, layers):
+    """Wide-flow layer 1 (d > 64) on the tensor-core engine: embedding plane + 3xTF32 GEMMs + cotangent reduction
+    (gnf_dag_embed_fwd / gnf_dag_embed_bwd) against the FFMA kernels that generate the gate in their operand loaders --
+    same Philox counters, so the two paths see the same gates: h, dx, dA and every weight gradient agree to fp32 accuracy
+    (1e-5) when layer 1 is the whole net.  With a ReLU and a second layer behind it the two summation orders may put a
+    pre-activation that is zero to 1e-7 on different sides, which moves one row of dx by one unit's share: 5e-3 there."""
+    torch.manual_seed(d + B)
+    dev = "cuda"
+    gate = G.ops.GateSpec(getattr(G._lib, mode), getattr(G._lib, imp), 0.05, .5, seed=77, offset=11)
+    x0 = torch.randn(B, d, device=dev)
+    A0 = torch.rand(d, d, device=dev) * 1.5
+    W = [torch.randn(N1, 2 * d if hot else d, device=dev) / d ** .5, torch.randn(24, N1, device=dev) / N1 ** .5][:layers]
+    b = [torch.randn(N1, device=dev) * .1, torch.randn(24, device=dev) * .1][:layers]
+    gh = torch.randn(B, d, 24 if layers == 2 else N1, device=dev)
+    outs = {}
+    G.ops.set_gemm_mode("tf32x3")
+    for plane in (True, False):
+        G.ops.DAG_L1_PLANE = plane
+        try:
+            x, A = x0.clone().requires_grad_(), A0.clone().requires_grad_()
+            params = [t.clone().requires_grad_() for pair in zip(W, b) for t in pair]
+            G.ops.enable_kernel_timing(True)
+            h = G.ops.DagMlpFn.apply(x, A, gate, hot, *params)
+            h.backward(gh)
+            called = set(G.ops.collect_kernel_timing())
+            G.ops.enable_kernel_timing(False)
+        finally:
+            G.ops.DAG_L1_PLANE = True
+        assert ("gnf_dag_embed_fwd" in called) == plane and ("gnf_dag_embed_bwd" in called) == plane
+        outs[plane] = [h.detach(), x.grad, A.grad] + [p.grad for p in params]
+    for name, a, r in zip(["h", "dx", "dA", "dW1", "db1", "dW2", "db2"], outs[True], outs[False]):
+        assert torch.isfinite(a).all()
+        err = float((a.double() - r.double()).norm() / r.double().norm().clamp_min(1e-30))
+        assert err < (1e-5 if layers == 1 or name == "h" else 5e-3), f"{name}: relative L2 {err}"
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # fused strict UMNN forward
 # ---------------------------------------------------------------------------------------------------------------------
