@@ -929,6 +929,261 @@ static bool g2_eligible(const TcGemmParams& p) {
   return p.M >= 1024 && p.N >= 256 && p.K >= 128;          // small problems: the planned tiling of the engine above
 }
 
+// =====================================================================================================================
+// Engine v2, weight gradient: dW[n, k] = sum_m dY[m, n] X[m, k] (3xTF32, split-K over m with atomic accumulation).  Both
+// operands are activations, contiguous along the OUTPUT index (MN-major sources), so neither can be pre-split per call.
+// The engine above turns both landed tiles into hi / lo tiles in shared memory with eight stager warps (4.4 k clocks per
+// 32-m chunk at 6300 x 632 x 632 against 0.96 k of MMA time).  Here, per chunk:
+//   * dY^T is the A operand and goes through registers into TMEM: thread = output row n = TMEM lane reads its column of the
+//     landed [32 m][128 n] tile (conflict-free: a warp's 32 lanes read one 128-byte row per m), splits it and writes A_hi /
+//     A_lo columns (tcgen05.st) into a four-deep ring; the MMAs are TS form;
+//   * only X is split in shared memory, elementwise and in place (hi) + a lo tile, by two stager warps;
+//   * a stage is raw dY (16 KB) + X hi (16 KB, TMA-loaded raw) + X lo (16 KB): 32 KB of L2 traffic per chunk instead of 36-40;
+//   * partial accumulators are folded into a register running sum by eight epilogue warps (as in the forward engine), the
+//     finished partial tile of a (tile, split) work item is added to dW with coalesced atomics through the staging blocks.
+// TMEM columns: partials 0 / 128, A ring 256 (four buffers of hi 32 + lo 32).
+// =====================================================================================================================
+constexpr int kW2Threads = 16 * 32;              // 8 epilogue + 4 A-writer + 2 X-stager + MMA issuer + TMA producer warps
+constexpr int kW2Ring = 4;
+constexpr uint32_t kW2ColA = 256;
+
+__global__ void __launch_bounds__(kW2Threads, 1) tc_wgrad2_kernel(TcGemmParams p, const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB) {
+  using namespace tc;
+  GNF_SMEM(char, smem);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)kG2Stages * kG2StageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 8 * kG2EpiStageFloats);
+  uint64_t* landed = bars;                     // [stages] TMA -> A-writers / stagers (transaction bytes)
+  uint64_t* empty = landed + kG2Stages;        // [stages] MMA -> producer (tcgen05.commit)
+  uint64_t* b_full = empty + kG2Stages;        // [stages] X-stagers -> MMA (one arrive per stager warp)
+  uint64_t* a_full = b_full + kG2Stages;       // [ring] A-writers -> MMA (one arrive per writer warp)
+  uint64_t* a_empty = a_full + kW2Ring;        // [ring] MMA -> A-writers (tcgen05.commit)
+  uint64_t* tfull = a_empty + kW2Ring;         // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA (one arrive per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) {
+    for (int s = 0; s < kG2Stages; ++s) { mbar_init(&landed[s], 1); mbar_init(&empty[s], 1); mbar_init(&b_full[s], 2); }
+    for (int b = 0; b < kW2Ring; ++b) { mbar_init(&a_full[b], 4); mbar_init(&a_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // GEMM view: rows = dW rows n (p.M of them), columns = dW columns k (p.N), reduction = the batch rows m (p.K)
+  const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM, tiles_n = (p.N + kG2BN - 1) / kG2BN;
+  const int tiles = tiles_m * tiles_n;
+  const int total = tiles * p.splits;
+  const int fold = p.fold < 1 ? 1 : p.fold;
+  auto item_chunks = [&](int w) {                                      // k-chunks of work item w = (tile, split)
+    const int sp = w / tiles;
+    const int kbeg = sp * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+    return (kend - kbeg + kGemmKC - 1) / kGemmKC;
+  };
+
+  if (warp == 15) {
+    // ===================== producer: raw dY tile (four 32-row slabs) + raw X tile =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int t = w % tiles, sp = w / tiles, tm = t % tiles_m, tn = t / tiles_m;
+        const int kbeg = sp * p.k_per_split, nch = item_chunks(w);
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int s = it % kG2Stages, k0 = kbeg + c * kGemmKC;
+          mbar_wait(&empty[s], (uint32_t)(((it / kG2Stages) & 1) ^ 1));
+          char* st = smem + (size_t)s * kG2StageBytes;
+          mbar_expect_tx(&landed[s], 2u * kG2TileBytes);
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            tma_load_2d(st + sl * 4096, &tmA, tm * kGemmBM + 32 * sl, k0, &landed[s]);
+            tma_load_2d(st + kG2TileBytes + sl * 4096, &tmB, tn * kG2BN + 32 * sl, k0, &landed[s]);
+          }
+          trace_stamp(p.trace, 0, it);
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ===================== MMA issuer (warp-converged) =====================
+    const uint32_t idesc = make_idesc_tf32(kGemmBM, kG2BN) | (1u << 16);     // B MN-major
+    int it = 0, gcount = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int nch = item_chunks(w);
+      for (int c0 = 0; c0 < nch; c0 += fold, ++gcount) {
+        const int acc = gcount & 1;
+        mbar_wait(&tempty[acc], (uint32_t)(((gcount >> 1) & 1) ^ 1));
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kG2BN;
+        const int c1 = (c0 + fold < nch) ? c0 + fold : nch;
+        uint32_t first = 0u;
+        for (int c = c0; c < c1; ++c, ++it) {
+          const int s = it % kG2Stages, b = it % kW2Ring;
+          mbar_wait(&a_full[b], (uint32_t)((it / kW2Ring) & 1));
+          mbar_wait(&b_full[s], (uint32_t)((it / kG2Stages) & 1));
+          fence_after_sync();
+          if (lane == 0) trace_stamp(p.trace, 3, it);
+          const uint32_t st = smem_u32(smem + (size_t)s * kG2StageBytes);
+          const uint64_t db_hi = make_sw128_desc(st + kG2TileBytes, true), db_lo = make_sw128_desc(st + 2 * kG2TileBytes, true);
+          const uint32_t ta_hi = tmem_base + kW2ColA + (uint32_t)b * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+          for (int ks = 0; ks < kGemmKC / 8; ++ks) {                          // correction products first (see tc_gemm2_kernel)
+            mma_tf32_ts_w(d_tmem, ta_lo + ks * 8, db_hi + (uint64_t)(64u * ks), idesc, first);
+            first = 1u;
+            mma_tf32_ts_w(d_tmem, ta_hi + ks * 8, db_lo + (uint64_t)(64u * ks), idesc, 1u);
+          }
+#pragma unroll
+          for (int ks = 0; ks < kGemmKC / 8; ++ks) mma_tf32_ts_w(d_tmem, ta_hi + ks * 8, db_hi + (uint64_t)(64u * ks), idesc, 1u);
+          mma_commit_w(&empty[s]);
+          mma_commit_w(&a_empty[b]);
+        }
+        mma_commit_w(&tfull[acc]);
+        if (lane == 0) trace_stamp(p.trace, 4, gcount);
+      }
+    }
+  } else if (warp >= 12) {
+    // ===================== X-stagers: landed raw tile -> hi in place + lo tile (elementwise: the swizzled layout is kept) =====================
+    const int ptid = tid - 12 * 32;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int nch = item_chunks(w);
+      for (int c = 0; c < nch; ++c, ++it) {
+        const int s = it % kG2Stages;
+        mbar_wait(&landed[s], (uint32_t)((it / kG2Stages) & 1));
+        char* hi = smem + (size_t)s * kG2StageBytes + kG2TileBytes;
+#pragma unroll 4
+        for (int i = 0; i < (int)(kG2TileBytes / 16) / 64; ++i) split_vec<4>(hi, hi + kG2TileBytes, (ptid + 64 * i) * 16);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_full[s]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== A-writers: column n of the landed dY tile -> TF32 hi / lo in registers -> TMEM ring =====================
+    const int q = warp - 8;                                              // slab = TMEM lane quarter
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t col_off = (uint32_t)(q * 4096) + (uint32_t)((lane & 3) << 2);
+    const uint32_t g16 = (uint32_t)(lane >> 2);                          // 16-byte group of this lane inside a 128-byte row
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int nch = item_chunks(w);
+      for (int c = 0; c < nch; ++c, ++it) {
+        const int s = it % kG2Stages, b = it % kW2Ring;
+        mbar_wait(&landed[s], (uint32_t)((it / kG2Stages) & 1));
+        if (tid == 256) trace_stamp(p.trace, 1, it);
+        const char* base = smem + (size_t)s * kG2StageBytes + col_off;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {                                // row kk of the slab: 32-byte atoms swizzled by (kk & 3)
+          const uint32_t e = *reinterpret_cast<const uint32_t*>(base + kk * 128 + ((g16 ^ (uint32_t)((kk & 3) << 1)) << 4));
+          const uint32_t h = (e + 0x1000u) & 0xffffe000u;
+          hi[kk] = h;
+          lo[kk] = __float_as_uint(__uint_as_float(e) - __uint_as_float(h)) + 0x1000u;   // the tensor core drops the low bits
+        }
+        mbar_wait(&a_empty[b], (uint32_t)(((it / kW2Ring) & 1) ^ 1));
+        fence_after_sync();
+        const uint32_t ta = tmem_base + lane_sel + kW2ColA + (uint32_t)b * 64u;
+        tmem_st32p(ta, hi);
+        tmem_st32p(ta + 32, lo);
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[b]);
+        if (tid == 256) trace_stamp(p.trace, 2, it);
+      }
+    }
+  } else {
+    // ===================== epilogue: register running sum per work item, then coalesced atomics =====================
+    const int quarter = warp & 3, half = warp >> 2, ch = 64 * half;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    float* stage = epi_stage + warp * kG2EpiStageFloats;
+    const int sub = lane >> 3, piece = lane & 7;
+    int gcount = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int t = w % tiles, tm = t % tiles_m, tn = t / tiles_m;
+      const int n0 = tn * kG2BN + ch, m0 = tm * kGemmBM + quarter * 32;
+      const int ngroups = (item_chunks(w) + fold - 1) / fold;
+      float run[64];
+      for (int g = 0; g < ngroups; ++g, ++gcount) {
+        const int acc = gcount & 1;
+        mbar_wait(&tfull[acc], (uint32_t)((gcount >> 1) & 1));
+        fence_after_sync();
+        if (tid == 0) trace_stamp(p.trace, 5, gcount);
+        const uint32_t part = tmem_base + lane_sel + (uint32_t)acc * kG2BN + (uint32_t)ch;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t a[32];
+          tmem_ld32p(part + c, a);
+          tmem_wait_ld();
+          if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) run[c + j] = __uint_as_float(a[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) run[c + j] += __uint_as_float(a[j]);
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (tid == 0) trace_stamp(p.trace, 6, gcount);
+      }
+      if (ngroups == 0) continue;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        if (n0 + c < p.N) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (j4 ^ (lane & 7))) =
+                make_float4(run[c + 4 * j4], run[c + 4 * j4 + 1], run[c + 4 * j4 + 2], run[c + 4 * j4 + 3]);
+          __syncwarp();
+          const int n = n0 + c + 4 * piece;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int R = 4 * i + sub, m = m0 + R;
+            const float4 o = *reinterpret_cast<const float4*>(stage + R * 32 + 4 * (piece ^ (R & 7)));
+            if (m < p.M) {
+              float* dst = p.C + (long long)m * p.ldc + n;
+              if (n < p.N) atomicAdd(dst, o.x);
+              if (n + 1 < p.N) atomicAdd(dst + 1, o.y);
+              if (n + 2 < p.N) atomicAdd(dst + 2, o.z);
+              if (n + 3 < p.N) atomicAdd(dst + 3, o.w);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static bool w2_eligible(const TcGemmParams& p) {
+  if (p.passes != 3 || p.epi != TCG_EPI_ATOMIC || p.a_src != TCG_SRC_MN || p.b_src != TCG_SRC_MN || p.A_lo || p.B_lo) return false;
+  return p.M >= 256 && p.N >= 256 && p.K >= 2048;          // small problems: the planned tiling of the first engine
+}
+
+// splits of the reduction for the weight-gradient engine: work items = tiles x splits over the persistent grid, cost of a round =
+// its k-chunks + ~6 chunks' worth of fold / atomic epilogue
+static int w2_plan_splits(int tiles, int kchunks) {
+  int best = 1;
+  double best_cost = -1.;
+  const int max_sp = kchunks / 8 < 1 ? 1 : kchunks / 8;
+  for (int sp = 1; sp <= max_sp && sp <= 64; ++sp) {
+    const int per = (kchunks + sp - 1) / sp;
+    if ((kchunks + per - 1) / per != sp) continue;
+    const long long rounds = ((long long)tiles * sp + kNumSMs - 1) / kNumSMs;
+    const double cost = (double)rounds * (per + 6.);
+    if (best_cost < 0. || cost < best_cost * 0.999) { best_cost = cost; best = sp; }
+  }
+  return best;
+}
+
 int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return 0;
   if (p.passes != 1 && p.passes != 3) return fail(GNF_ERR_INVALID, "tensor-core GEMM: passes must be 1 or 3");
@@ -967,6 +1222,21 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   if (!p.B_lo) p.A_lo = nullptr;
   if (p.A_lo && !make_operand_map(&tmAlo, p.A_lo, p.lda, p.a_src, p.M, p.K, kGemmBM))
     return fail(GNF_ERR_UNSUPPORTED, "tensor-core GEMM: pre-split activations need TMA-loadable operands (16-byte aligned rows)");
+  if (g_tc_gemm_v2 && p.use_tma && w2_eligible(p)) {
+    // engine v2, weight gradient: BN = 128, its own split plan (MN-major maps have 32 x 32 boxes whatever the tile width)
+    p.BN = kG2BN;
+    const int tiles2 = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + kG2BN - 1) / kG2BN);
+    const int sp2 = g_tc_gemm_force_splits ? g_tc_gemm_force_splits : w2_plan_splits(tiles2, kchunks);
+    p.k_per_split = ((kchunks + sp2 - 1) / sp2) * kGemmKC;
+    p.splits = (p.K + p.k_per_split - 1) / p.k_per_split;
+    p.fold = g_tc_gemm_fold;
+    p.trace = g_tc_gemm_trace;
+    const size_t smem2 = (size_t)kG2Stages * kG2StageBytes + 8 * kG2EpiStageFloats * sizeof(float) + (3 * kG2Stages + 2 * kW2Ring + 4) * sizeof(uint64_t) + 16;
+    const long long total2 = (long long)tiles2 * p.splits;
+    cudaFuncSetAttribute(tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    GNF_LAUNCH(tc_wgrad2_kernel, (int)(total2 < kNumSMs ? total2 : kNumSMs), kW2Threads, smem2, s, p, tmA, tmB);
+    return 0;
+  }
   if (g_tc_gemm_v2 && p.use_tma && g2_eligible(p)) {
     // engine v2: BN = 128, A through registers into TMEM (the maps of A and of the pre-split B built above already have the
     // right boxes when the plan chose BN = 128; rebuild B's for that width otherwise)

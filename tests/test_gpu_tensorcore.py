@@ -88,7 +88,7 @@ def gemm_mode():
 
 SHAPES = [(1, 1, 1), (127, 33, 65), (300, 630, 126), (1000, 30, 630), (64, 2, 1024), (513, 210, 21), (6300, 630, 630),
           (256, 1024, 784), (300, 160, 160), (1000, 152, 64), (513, 212, 20), (129, 4, 36), (2200, 150, 150),
-          (138600, 152, 148), (6300, 632, 632)]
+          (138600, 152, 148), (6300, 632, 632), (4100, 300, 260), (12544, 1024, 784)]
 
 
 @pytest.mark.parametrize("M_,N,K", SHAPES)
