@@ -225,6 +225,8 @@ __device__ __forceinline__ void last_layer(const float* __restrict__ act, const 
   __syncthreads();
 }
 
+static size_t fwd_smem_bytes_for(int NP) { return ((size_t)2 * NP * kLDR + 2 * kKC * NP + 256 + 64) * sizeof(float); }
+
 struct UmnnFwdParams {
   const float* x; const float* h; const float* ccw; const float* ccn;
   float* z; float* zrev; float* jac; float* logdet;
@@ -317,6 +319,107 @@ __global__ void __launch_bounds__(kUThreads) umnn_fwd_kernel(UmnnFwdParams p) {
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inverse by bisection (MonotonicNormalizer.inverse_transform, MonotonicNormalizer.py:69-83): the reference runs 20 full
+// forward passes, halving [-20, 20] around x_middle after each.  Here the whole search of a row lives in one CTA: a tile
+// holds ALL quadrature nodes of floor(64 / (S+1)) rows, so z(x_middle) is a shared-memory segment sum (no atomics, no
+// global round trip) and the interval update, the next abscissae and the next forward pass follow in the same launch.
+// ------------------------------------------------------------------------------------------------
+struct UmnnInvParams {
+  const float* z; const float* h; const float* ccw; const float* ccn;
+  float* x;
+  int R, E, S, iters;
+  float lo, hi;
+  UmnnPacked pk;
+};
+
+template <int TN>
+__global__ void __launch_bounds__(kUThreads) umnn_invert_kernel(UmnnInvParams p) {
+  constexpr int NP = 16 * TN;
+  GNF_SMEM(float, smem);
+  float* act0 = smem;                       // [NP][kLDR]
+  float* act1 = act0 + NP * kLDR;           // [NP][kLDR]
+  float* wp = act1 + NP * kLDR;             // [2][16][NP]
+  float* red = wp + 2 * kKC * NP;           // [256]
+  float* yout = red + 256;                  // [64]
+  float* xlo = yout + 64;                   // [64] search interval and target of the tile's rows
+  float* xhi = xlo + 64;
+  float* zt = xhi + 64;
+  const int t = threadIdx.x;
+  const int nodes = p.S + 1;
+  const int rows_per = kTileM / nodes;      // >= 1 (checked by the launcher)
+  const int KP0 = p.pk.kpad[0];
+  const int ntiles = (p.R + rows_per - 1) / rows_per;
+  const float blast = __ldg(p.pk.blast_ptr);
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * rows_per;
+    const int nr = (p.R - r0 < rows_per) ? p.R - r0 : rows_per;
+    if (t < kTileM) {
+      xlo[t] = p.lo; xhi[t] = p.hi;
+      zt[t] = t < nr ? __ldg(p.z + r0 + t) : 0.f;
+    }
+    __syncthreads();
+    for (int it = 0; it < p.iters; ++it) {
+      // ---- input tile [KP0][64]: k=0 -> node abscissa of x_middle, k=1..E -> h[r, k-1]
+      for (int idx = t; idx < KP0 * kTileM; idx += kUThreads) {
+        const int row = idx & 63, k = idx >> 6;
+        const int lr = row / nodes, kn = row - lr * nodes;
+        float v = 0.f;
+        if (lr < nr && k <= p.E) {
+          if (k == 0) v = (((xhi[lr] + xlo[lr]) / 2.f) * (__ldg(p.ccn + kn) + 1.f)) / 2.f;
+          else v = __ldg(p.h + (size_t)(r0 + lr) * p.E + (k - 1));
+        }
+        act0[(size_t)k * kLDR + row] = v;
+      }
+      __syncthreads();
+      float* cur = act0;
+      float* nxt = act1;
+      float acc[4][TN];
+      for (int l = 0; l < p.pk.L; ++l) {
+        tile_gemm<TN>(acc, cur, p.pk.Wt[l], p.pk.kpad[l] / kKC, wp);
+        store_bias_relu<TN>(acc, p.pk.bias[l], nxt);
+        float* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
+      }
+      last_layer(cur, p.pk.wlast, blast, NP, red, yout);
+      if (t < kTileM) {
+        const float y = yout[t];
+        const float f = (y > 0.f ? y : expm1f(y)) + 1.05f;
+        const int lr = t / nodes, kn = t - lr * nodes;
+        red[t] = lr < nr ? __ldg(p.ccw + kn) * f : 0.f;
+      }
+      __syncthreads();
+      if (t < nr) {
+        float sacc = 0.f;
+        for (int i = 0; i < nodes; ++i) sacc += red[t * nodes + i];
+        const float xm = (xhi[t] + xlo[t]) / 2.f;
+        const float zm = sacc * xm / 2.f + __ldg(p.h + (size_t)(r0 + t) * p.E);
+        if (zm > zt[t]) xhi[t] = xm; else xlo[t] = xm;          // left = (z_middle > z): x_max = x_middle, else x_min = x_middle
+      }
+      __syncthreads();
+    }
+    if (t < nr) p.x[r0 + t] = (xhi[t] + xlo[t]) / 2.f;
+    __syncthreads();
+  }
+}
+
+template <int TN>
+static int launch_invert(const UmnnInvParams& p, cudaStream_t s) {
+  const size_t smem = fwd_smem_bytes_for(16 * TN) + 3 * 64 * sizeof(float);
+  if (smem > 227 * 1024) return fail(GNF_ERR_UNSUPPORTED, "umnn invert: shared memory %zu B exceeds 227 KB", smem);
+#ifndef GNF_EMU
+  cudaFuncSetAttribute(umnn_invert_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  const int rows_per = kTileM / (p.S + 1);
+  const long long ntiles = ((long long)p.R + rows_per - 1) / rows_per;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024));
+  long long grid = (long long)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
+  if (grid > ntiles) grid = ntiles;
+  GNF_LAUNCH(umnn_invert_kernel<TN>, (unsigned)grid, kUThreads, smem, s, p);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -575,7 +678,7 @@ __global__ void __launch_bounds__(kUThreads) umnn_bwd_kernel(UmnnBwdParams p) {
   }
 }
 
-static size_t fwd_smem_bytes(int NP) { return ((size_t)2 * NP * kLDR + 2 * kKC * NP + 256 + 64) * sizeof(float); }
+static size_t fwd_smem_bytes(int NP) { return fwd_smem_bytes_for(NP); }
 static size_t bwd_smem_bytes(int NP, int KP0, int L) { return ((size_t)KP0 * kLDR + (size_t)L * NP * kLDR + 2 * kKC * NP + 256 + 128) * sizeof(float); }
 
 template <int TN>
@@ -655,6 +758,33 @@ int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, co
   }
   if (e) return e;
   return check_launch("gnf_umnn_fwd");
+}
+
+int gnf_umnn_invert(const float* z, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn, float* x, int iters,
+                    float lo, float hi, int R, void* work, size_t work_bytes, gnf_stream_t stream) {
+  if (!z || !h || !net || !ccw || !ccn || !x || R < 0 || S < 1 || iters < 0) return fail(GNF_ERR_INVALID, "gnf_umnn_invert: bad arguments");
+  if (S + 1 > kTileM) return fail(GNF_ERR_UNSUPPORTED, "gnf_umnn_invert: %d quadrature nodes do not fit one %d-row tile", S + 1, kTileM);
+  PackPlan pl;
+  int TN;
+  if (int e = make_plan(net, &pl, &TN)) return e;
+  if (!work || work_bytes < pl.total * sizeof(float)) return fail(GNF_ERR_WORKSPACE, "gnf_umnn_invert: workspace too small (%zu < %zu)", work_bytes, pl.total * sizeof(float));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (R == 0) return 0;
+  launch_pack(net, pl, (float*)work, s);
+  UmnnInvParams p;
+  p.z = z; p.h = h; p.ccw = ccw; p.ccn = ccn; p.x = x; p.R = R; p.E = net->dims[0] - 1; p.S = S; p.iters = iters; p.lo = lo; p.hi = hi;
+  fill_packed(net, pl, (float*)work, &p.pk);
+  int e = 0;
+  switch (TN) {
+    case 2: e = launch_invert<2>(p, s); break;
+    case 4: e = launch_invert<4>(p, s); break;
+    case 7: e = launch_invert<7>(p, s); break;
+    case 10: e = launch_invert<10>(p, s); break;
+    case 13: e = launch_invert<13>(p, s); break;
+    default: e = launch_invert<16>(p, s); break;
+  }
+  if (e) return e;
+  return check_launch("gnf_umnn_invert");
 }
 
 int gnf_umnn_bwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,

@@ -3,6 +3,7 @@
 import torch
 import torch.nn as nn
 
+from . import _lib as L
 from . import ops
 
 
@@ -114,8 +115,21 @@ class MonotonicNormalizer(Normalizer):
             return None
         return out[0], out[1]
 
+    # inverse_transform runs the whole bisection in one kernel launch (gnf_umnn_invert, FFMA tiles that hold every quadrature node
+    # of their rows: S + 1 <= 64) -- 1.9x the loop of 20 launches of the same FFMA forward (8.1 vs 15.3 ms at cfg4's shape).  Where
+    # the forward itself runs on the fused tcgen05 kernel (large batches in a tensor-core GEMM mode) 20 launches of THAT kernel
+    # are faster still (4.6 ms, profiles/r02t_invert_bench.txt): 'auto' picks by the same rule as the forward.  True / False force.
+    fused_inverse = "auto"
+
     def inverse_transform(self, z, h, context=None):
         # 20-step bisection on [-20, 20] (MonotonicNormalizer.py:69-83); sampling path, SURVEY.md §8f rank 2
+        fused = self.fused_inverse
+        if fused == "auto":
+            fused = not ops.umnn_forward_on_tensor_cores(self.integrand_net.linear_params(), z.numel(), int(self.nb_steps), z.device)
+        if fused and self.solver in ("CC", "CCParallel") and int(self.nb_steps) + 1 <= 64 and (z.is_cuda or L._SIMULATOR):
+            with torch.no_grad():
+                ws = self.integrand_net.linear_params()
+                return ops.umnn_invert(z.contiguous(), h.contiguous(), int(self.nb_steps), ws[0::2], ws[1::2], 20, -20., 20.)
         x_max = torch.ones_like(z) * 20
         x_min = -torch.ones_like(z) * 20
         with torch.no_grad():

@@ -958,6 +958,39 @@ class UmnnFn(torch.autograd.Function):
         return tuple(out)
 
 
+def umnn_forward_on_tensor_cores(params, R, S, device):
+    """Would UmnnFn's evaluation forward of R rows run on the fused tcgen05 kernel (gnf_umnn_fwd_tc3) in the current GEMM mode?"""
+    if L._SIMULATOR:
+        return False
+    weights, biases = [p.detach() for p in params[0::2]], [p.detach() for p in params[1::2]]
+    net = _mlp_struct(weights, biases)
+    return (_umnn_layerwise_passes(net, R, int(S), False, device) == 3 and UMNN_FWD_FUSED_TC3
+            and lib().gnf_umnn_tc3_workspace_bytes(C.byref(net), R) != 0)
+
+
+def umnn_invert(z, h, S, weights, biases, iters=20, lo=-20., hi=20.):
+    """MonotonicNormalizer.inverse_transform (MonotonicNormalizer.py:69-83): x with integral(x; h) + h[..., 0] = z by `iters`
+    bisection steps on [lo, hi], every forward pass of the search inside ONE kernel launch (gnf_umnn_invert).  No autograd
+    (the reference searches under torch.no_grad()).  z [B, d], h [B, d, E] -> x [B, d]."""
+    require(z, "z"), require(h, "h")
+    weights = [require(_contig(w.detach()), "weight") for w in weights]
+    biases = [require(_contig(b.detach()), "bias") for b in biases]
+    B, d = z.shape
+    if weights[0].shape[1] != 1 + h.shape[2]:
+        raise ValueError(f"integrand expects {weights[0].shape[1] - 1} conditioning features, h has {h.shape[2]}")
+    net = _mlp_struct(weights, biases)
+    nbytes = lib().gnf_umnn_workspace_bytes(C.byref(net))
+    if nbytes == 0:
+        raise RuntimeError("libgnf: " + lib().gnf_last_error().decode())
+    ws = torch.empty((nbytes + 3) // 4, device=z.device, dtype=torch.float32)
+    ccw, ccn = cc_weights(S, z.device)
+    x = torch.empty_like(z)
+    _call("gnf_umnn_invert", ptr(z), ptr(h), C.byref(net), int(S), ptr(ccw), ptr(ccn), ptr(x), int(iters), float(lo), float(hi), B * d,
+          ptr(ws), nbytes, stream_ptr())
+    _count(2)
+    return x
+
+
 def _pad32(v):
     return (v + 31) // 32 * 32
 

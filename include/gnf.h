@@ -239,6 +239,12 @@ size_t gnf_umnn_saved_floats_per_node_row(const gnf_mlp_t* net);
 int gnf_umnn_fwd(const float* x, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn,
                  float* z, float* zrev, float* jac, float* logdet, float* saved, int R, int d, void* work,
                  size_t work_bytes, gnf_stream_t stream);
+/* Inverse of the monotonic transform by bisection (MonotonicNormalizer.inverse_transform, MonotonicNormalizer.py:69-83:
+ * 20 halvings of [-20, 20], one full forward pass each; the sampling path FCNormalizingFlow.invert, NormalizingFlow.py:98-107):
+ * x[r] such that int_0^x f(t;h_r)dt + h[r,0] = z[r].  All `iters` forward passes of a row run inside one launch (a tile holds
+ * every quadrature node of its rows: needs S + 1 <= 64); lo / hi = the initial interval, x = midpoint of the final one. */
+int gnf_umnn_invert(const float* z, const float* h, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn, float* x,
+                    int iters, float lo, float hi, int R, void* work, size_t work_bytes, gnf_stream_t stream);
 /* Cotangents: gz [R], gzrev [R] (nullable), gjac [R] (nullable), glogdet [R/d] (nullable).
  * Gradient convention = UMNN's: dtheta, dh by quadrature of the integrand's gradients with weights
  * w_k*gz*x/2; dx by the Leibniz rule f(x)*gz; the jac output is differentiated by the plain chain rule. */

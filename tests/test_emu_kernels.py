@@ -64,3 +64,21 @@ def test_power_trace_golden_in_simulator(emu):
         t.backward()
         assert abs(float(t.detach()) - want) <= tol, key
         assert rel_l2(A.grad, torch.from_numpy(f[key + ".dA"])) < 1e-4, key
+
+
+def test_fused_bisection_inverse_in_simulator(emu):
+    """gnf_umnn_invert (MonotonicNormalizer.inverse_transform's 20 bisection steps in one launch) against the reference's loop of
+    20 forward passes through the same simulated forward kernel, and against the x that produced z."""
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    norm = G.MonotonicNormalizer([16, 16], 3, nb_steps=7, solver="CC")
+    x, h = torch.randn(5, 4) * 2, torch.randn(5, 4, 3)
+    with torch.no_grad():
+        z, _ = norm(x, h)
+        norm.fused_inverse = True
+        x_fused = norm.inverse_transform(z, h)
+        norm.fused_inverse = False
+        x_loop = norm.inverse_transform(z, h)
+    res = 40. / 2 ** 20
+    assert float((x_fused - x_loop).abs().max()) <= res * 1.01
+    assert float((x_fused - x).abs().max()) < 2 * res

@@ -243,6 +243,37 @@ def test_monotonic_invert_of_forward(cond):
     assert err < 2 * 3.8e-5 + 1e-5, err
 
 
+@pytest.mark.parametrize("B,d,S,widths,E", [(100, 63, 20, [150, 150, 150], 30), (33, 5, 30, [50, 50, 50], 8), (7, 3, 63, [16], 1),
+                                            (50, 4, 9, [200, 100], 12)])
+def test_fused_bisection_inverse_matches_the_reference_loop(B, d, S, widths, E):
+    """gnf_umnn_invert (all 20 forward passes of MonotonicNormalizer.inverse_transform in one launch) against
+    (a) the reference's own loop of 20 forward passes on the same CUDA forward kernel: same interval decisions, so the same x
+        except where a z_middle lands within rounding of z (the two evaluate the quadrature in different tile layouts):
+        then they differ by at most the last interval, 40 / 2^20;
+    (b) the oracle's float64 integral: forward(x_found) reproduces z to the slope times the bisection resolution."""
+    torch.manual_seed(S + d)
+    norm = G.MonotonicNormalizer(widths, E, nb_steps=S, solver="CC").to("cuda")
+    h = torch.randn(B, d, E, device="cuda") * .7
+    x_true = torch.randn(B, d, device="cuda") * 3
+    G.ops.set_gemm_mode("ffma")
+    with torch.no_grad():
+        z, jac = norm(x_true, h)
+        G.ops.enable_kernel_timing(True)
+        norm.fused_inverse = True
+        x_fused = norm.inverse_transform(z, h)
+        assert "gnf_umnn_invert" in G.ops.collect_kernel_timing()
+        G.ops.enable_kernel_timing(False)
+        norm.fused_inverse = False
+        x_loop = norm.inverse_transform(z, h)
+    res = 40. / 2 ** 20
+    assert float((x_fused - x_loop).abs().max()) <= res * 1.01
+    assert float((x_fused == x_loop).float().mean()) > .98
+    assert float((x_fused - x_true).abs().max()) < 2 * res
+    sd64 = {"n." + k: v.detach().double().cpu() for k, v in norm.state_dict().items()}
+    z64, _ = O.monotonic_normalizer(x_fused.double().cpu(), h.double().cpu(), sd64, "n.integrand_net.net", len(widths) + 1, S)
+    assert float(((z64 - z.double().cpu()).abs() / jac.double().cpu().clamp_min(1e-3)).max()) < 2 * res
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # DAG dual-ascent control against the reference's recorded trajectories
 # ---------------------------------------------------------------------------------------------------------------------
