@@ -366,7 +366,7 @@ def main():
         for i in range(warmup):
             step(pool[i % n_pool])
         barrier()
-        eager_ktimes, eager_kflops, eager_launches, n_eager = None, None, 0, 0
+        eager_ktimes, eager_kflops, eager_kshapes, eager_launches, n_eager = None, None, None, 0, 0
         if use_graph:
             l0 = G.ops.launch_count()
             G.ops.enable_kernel_timing(True)
@@ -375,6 +375,7 @@ def main():
                 step(pool[i % n_pool])
             eager_ktimes = G.ops.collect_kernel_timing()
             eager_kflops = G.ops.collect_call_flops()
+            eager_kshapes = G.ops.collect_call_shapes()
             G.ops.enable_kernel_timing(False)
             eager_launches = (G.ops.launch_count() - l0) // n_eager
             if mode == "train" and args.random_steps:
@@ -422,11 +423,12 @@ def main():
             evs.append((e0, e1))
         barrier()
         if use_graph:
-            launches, ktimes, kflops = eager_launches * steps, eager_ktimes, eager_kflops
+            launches, ktimes, kflops, kshapes = eager_launches * steps, eager_ktimes, eager_kflops, eager_kshapes
         else:
             launches = G.ops.launch_count() - l0
             ktimes = G.ops.collect_kernel_timing()
             kflops = G.ops.collect_call_flops()
+            kshapes = G.ops.collect_call_shapes()
             G.ops.enable_kernel_timing(False)
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         barrier()
@@ -453,20 +455,28 @@ def main():
         step_ms = dev_ms / steps
         cands = []
         tc_names = [k for k in ("gnf_linear_fwd_tc", "gnf_linear_dgrad_tc", "gnf_linear_wgrad_tc") if ktimes.get(k)]
-        if tc_names:
-            fl = sum(sum(kflops.get(k, [])) for k in tc_names)
-            ms = sum(sum(ktimes[k]) for k in tc_names)
-            n = sum(len(ktimes[k]) for k in tc_names)
-            if fl > 0 and len([f for k in tc_names for f in kflops.get(k, [])]) == n:
-                single = precision == "tf32" or gemm in ("tf32", "auto-fast")
-                cands.append(dict(kernel="tc_gemm_kernel", entries=tc_names, flops_per_launch=fl / n, avg_launch_ms=ms / n,
-                                  launches_per_step=n / n_timed, ms_per_step=ms / n_timed,
-                                  note=("tcgen05 kind::tf32 GEMM engine (conditioner hidden layers: forward, dgrad, wgrad), "
-                                        + ("single-pass TF32" if single else
-                                           "3xTF32 = fp32-equivalent: 3 tensor-core passes per algorithmic FLOP, so the tensor pipe sees "
-                                           "3x the achieved figure") +
-                                        "; the same kernel also runs the wgrad GEMMs inside the layer-wise UMNN backward, which are "
-                                        "timed with that composite call, not here")))
+        single = precision == "tf32" or gemm in ("tf32", "auto-fast")
+        by_kernel = {}                                 # the engine's kernel that each timed C-ABI call launched -> [(ms, flops)]
+        for k in tc_names:
+            shapes, fls = kshapes.get(k, []), kflops.get(k, [])
+            if len(shapes) != len(ktimes[k]) or len(fls) != len(ktimes[k]):
+                continue
+            for ms_, fl_, shp in zip(ktimes[k], fls, shapes):
+                kern = G.ops.tc_kernel_name(k.split("_")[2], *shp, passes=(1 if single else 3)) if shp else "tc_gemm_kernel"
+                by_kernel.setdefault(kern, []).append((ms_, fl_, k))
+        tc_notes = {
+            "tc_gemm2_kernel": "tcgen05 kind::tf32 GEMM engine v2 (conditioner layers, forward + dgrad): 3xTF32 = fp32-equivalent (3 tensor-core "
+                               "passes per algorithmic FLOP: the tensor pipe sees 3x the achieved figure, against a TF32 dense peak of half the "
+                               "bf16 one); activation operand split in registers and fed through TMEM, weights pre-split once per call",
+            "tc_wgrad2_kernel": "tcgen05 kind::tf32 GEMM engine v2, weight gradient (split-K over the batch rows, 3xTF32): dY^T through registers "
+                                "into TMEM, X split in shared memory; the call also zero-fills dW",
+            "tc_gemm_kernel": "tcgen05 kind::tf32 GEMM engine (first engine: both operands staged and split in shared memory), "
+                              + ("single-pass TF32" if single else "3xTF32 = fp32-equivalent: 3 tensor-core passes per algorithmic FLOP")}
+        for kern, rows in by_kernel.items():
+            ms, fl, n = sum(r[0] for r in rows), sum(r[1] for r in rows), len(rows)
+            if fl > 0:
+                cands.append(dict(kernel=kern, entries=sorted({r[2] for r in rows}), flops_per_launch=fl / n, avg_launch_ms=ms / n,
+                                  launches_per_step=n / n_timed, ms_per_step=ms / n_timed, note=tc_notes[kern]))
         if spec["cond"] == "DAG":
             # DAG layer 1 (K1): gnf_dag_l1_{fwd,wgrad,dgrad} = one kernel each, 2*B*d*d*H1 FLOPs (the one-hot half is a bias gather)
             H1 = spec["hidden"][0]

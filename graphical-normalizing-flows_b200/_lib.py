@@ -79,8 +79,8 @@ _PROTOS = {
     "gnf_dag_l1_fwd": ([_P, _P, C.POINTER(GateT), _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_dag_l1_wgrad": ([_P, _I, _P, _P, C.POINTER(GateT), _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_dag_l1_dgrad": ([_P, _I, _P, _I, _P, _P, C.POINTER(GateT), _P, _P, _I, _I, _I, _P], C.c_int),
-    "gnf_dag_embed_fwd": ([_P, _P, C.POINTER(GateT), _P, _I, _I, _I, _P], C.c_int),
-    "gnf_dag_embed_bwd": ([_P, _I, _P, _P, C.POINTER(GateT), _P, _P, _I, _I, _P], C.c_int),
+    "gnf_dag_embed_fwd": ([_P, _P, C.POINTER(GateT), _P, _P, _P, _I, _I, _I, _P], C.c_int),
+    "gnf_dag_embed_bwd": ([_P, _I, _P, _P, C.POINTER(GateT), _P, _P, _P, _P, _I, _I, _P], C.c_int),
     "gnf_dag_finish_dA": ([_P, _P, _P, _I, _I, _P], C.c_int),
     "gnf_dag_dump_noise": ([C.POINTER(GateT), _P, _P, _I, _I, _P], C.c_int),
     "gnf_umnn_workspace_bytes": ([C.POINTER(MlpT)], _SZ),

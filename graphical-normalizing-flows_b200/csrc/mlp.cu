@@ -422,21 +422,77 @@ __global__ void __launch_bounds__(kDagDgThreads, 4) dag_l1_dgrad_kernel(GateCtx 
 // the tcgen05 engine (3xTF32) against it, and fold the gate derivatives into one reduction pass over the [B*d, d] cotangent
 // plane the dgrad GEMM leaves.  Same Philox counters (idx = (b d + i) d + j) as the other kernels: the draws are identical.
 
-// E[m, j] = e[b,i,j], m = b d + i; padding columns [d, ld) = 0.  One CTA per row m.
-__global__ void __launch_bounds__(256) dag_embed_fwd_kernel(GateCtx g, float* __restrict__ E, int lde) {
+// E[m, j] = e[b,i,j], m = b d + i; padding columns [d, ld) = 0.  One CTA per row m.  kGrad (training): the gate's partial
+// derivatives de/dx and de/dP go to two more planes of the same shape, so that the backward reduction is a pure streaming pass
+// (the Philox + Gumbel math of 61 M gates is 0.7 ms at cfg5; reading two planes back is 0.08 ms of HBM time).
+template <bool kGrad>
+__global__ void __launch_bounds__(256) dag_embed_fwd_kernel(GateCtx g, float* __restrict__ E, float* __restrict__ DX, float* __restrict__ DP, int lde) {
   const int m = blockIdx.x, b = m / g.d, i = m - b * g.d;
-  float* row = E + (size_t)m * lde;
+  const size_t row = (size_t)m * lde;
   for (int j4 = threadIdx.x * 4; j4 < lde; j4 += blockDim.x * 4) {
-    float v[4];
+    float v[4], dx[4], dp[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (j4 + k < g.d) ? gate_e<false, true>(g, b, i, j4 + k, nullptr, nullptr) : 0.f;
-    *reinterpret_cast<float4*>(row + j4) = make_float4(v[0], v[1], v[2], v[3]);
+    for (int k = 0; k < 4; ++k) {
+      dx[k] = dp[k] = 0.f;
+      v[k] = (j4 + k < g.d) ? gate_e<kGrad, true>(g, b, i, j4 + k, &dx[k], &dp[k]) : 0.f;
+    }
+    *reinterpret_cast<float4*>(E + row + j4) = make_float4(v[0], v[1], v[2], v[3]);
+    if (kGrad) {
+      *reinterpret_cast<float4*>(DX + row + j4) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+      *reinterpret_cast<float4*>(DP + row + j4) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+    }
   }
 }
 
 // dx[b,j] += sum_i dE[(b,i),j] de/dx(b,i,j)  (atomic over the i tiles);  dP[i,j] = sum_b dE[(b,i),j] de/dP(b,i,j)  (owned).
 // CTA = 128 columns j x 8 rows i (two thread rows of four i each), loops over the batch.  grid = (ceil(d/128), ceil(d/8)).
 constexpr int kEmbBwdI = 4;
+// ... the same reduction from the derivative planes the training forward kept (no gate math: HBM-bound, three planes in).
+// CTA = 256 columns (64 threads x float4) x 8 rows i (four thread rows of two i each); two batch entries in flight per thread.
+constexpr int kEmbSavedI = 2;
+__global__ void __launch_bounds__(256) dag_embed_bwd_saved_kernel(const float* __restrict__ dE, const float* __restrict__ DX,
+                                                                  const float* __restrict__ DP, int lde, float* __restrict__ dx,
+                                                                  float* __restrict__ dP, int B, int d) {
+  const int j = blockIdx.x * 256 + (threadIdx.x & 63) * 4;
+  const int i0 = blockIdx.y * (4 * kEmbSavedI) + (threadIdx.x >> 6) * kEmbSavedI;
+  if (j >= d || i0 >= d) return;                             // lde % 4 == 0 and the padding columns of the planes are zero: float4 is safe
+  const int ni = (d - i0 < kEmbSavedI) ? d - i0 : kEmbSavedI;
+  float4 acc[kEmbSavedI];
+#pragma unroll
+  for (int k = 0; k < kEmbSavedI; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fma4 = [](float4& a, const float4& v, const float4& w) {
+    a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+  };
+#pragma unroll 2
+  for (int b = 0; b < B; ++b) {
+    float4 dxs = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t base = ((size_t)b * d + i0) * lde + j;
+#pragma unroll
+    for (int k = 0; k < kEmbSavedI; ++k) {
+      if (k < ni) {
+        const size_t o = base + (size_t)k * lde;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dE + o));
+        fma4(dxs, v, __ldg(reinterpret_cast<const float4*>(DX + o)));
+        fma4(acc[k], v, __ldg(reinterpret_cast<const float4*>(DP + o)));
+      }
+    }
+    float* dst = dx + (size_t)b * d + j;
+    atomicAdd(dst, dxs.x);
+    if (j + 1 < d) atomicAdd(dst + 1, dxs.y);
+    if (j + 2 < d) atomicAdd(dst + 2, dxs.z);
+    if (j + 3 < d) atomicAdd(dst + 3, dxs.w);
+  }
+#pragma unroll
+  for (int k = 0; k < kEmbSavedI; ++k)
+    if (k < ni) {
+      float* dst = dP + (size_t)(i0 + k) * d + j;
+      dst[0] = acc[k].x;
+      if (j + 1 < d) dst[1] = acc[k].y;
+      if (j + 2 < d) dst[2] = acc[k].z;
+      if (j + 3 < d) dst[3] = acc[k].w;
+    }
+}
+
 __global__ void __launch_bounds__(256) dag_embed_bwd_kernel(GateCtx g, const float* __restrict__ dE, int lde, float* __restrict__ dx,
                                                             float* __restrict__ dP, int B) {
   const int j = blockIdx.x * 128 + (threadIdx.x & 127);
@@ -776,28 +832,39 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   return check_launch("gnf_dag_l1_dgrad");
 }
 
-int gnf_dag_embed_fwd(const float* x, const float* P, const gnf_gate_t* gate, float* E, int lde, int B, int d, gnf_stream_t stream) {
-  if (!x || !P || !E || B < 0 || d <= 0 || lde < d || (lde % 4) != 0 || (reinterpret_cast<uintptr_t>(E) & 15) != 0)
-    return fail(GNF_ERR_INVALID, "gnf_dag_embed_fwd: bad arguments (E rows must be 16-byte aligned: lde %% 4 == 0)");
+int gnf_dag_embed_fwd(const float* x, const float* P, const gnf_gate_t* gate, float* E, float* DX, float* DP, int lde, int B, int d,
+                      gnf_stream_t stream) {
+  if (!x || !P || !E || B < 0 || d <= 0 || lde < d || (lde % 4) != 0 || (reinterpret_cast<uintptr_t>(E) & 15) != 0 || ((DX == nullptr) != (DP == nullptr)) ||
+      (reinterpret_cast<uintptr_t>(DX) & 15) != 0 || (reinterpret_cast<uintptr_t>(DP) & 15) != 0)
+    return fail(GNF_ERR_INVALID, "gnf_dag_embed_fwd: bad arguments (plane rows must be 16-byte aligned: lde %% 4 == 0; DX and DP go together)");
   GateCtx g;
   if (int e = make_gate(&g, x, P, gate, d)) return e;
   if (B == 0) return 0;
-  GNF_LAUNCH(dag_embed_fwd_kernel, B * d, 256, 0, (cudaStream_t)stream, g, E, lde);
+  if (DX) GNF_LAUNCH(dag_embed_fwd_kernel<true>, B * d, 256, 0, (cudaStream_t)stream, g, E, DX, DP, lde);
+  else GNF_LAUNCH(dag_embed_fwd_kernel<false>, B * d, 256, 0, (cudaStream_t)stream, g, E, DX, DP, lde);
   return check_launch("gnf_dag_embed_fwd");
 }
 
-int gnf_dag_embed_bwd(const float* dE, int lde, const float* x, const float* P, const gnf_gate_t* gate, float* dx, float* dP, int B, int d,
-                      gnf_stream_t stream) {
-  if (!dE || !x || !P || !dx || !dP || B < 0 || d <= 0 || lde < d) return fail(GNF_ERR_INVALID, "gnf_dag_embed_bwd: bad arguments");
-  GateCtx g;
-  if (int e = make_gate(&g, x, P, gate, d)) return e;
+int gnf_dag_embed_bwd(const float* dE, int lde, const float* x, const float* P, const gnf_gate_t* gate, const float* DX, const float* DP,
+                      float* dx, float* dP, int B, int d, gnf_stream_t stream) {
+  if (!dE || !dx || !dP || B < 0 || d <= 0 || lde < d || ((DX == nullptr) != (DP == nullptr)) || (!DX && (!x || !P)))
+    return fail(GNF_ERR_INVALID, "gnf_dag_embed_bwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(dx, 0, (size_t)B * d * sizeof(float), s);
   if (B == 0) {
     cudaMemsetAsync(dP, 0, (size_t)d * d * sizeof(float), s);
     return check_launch("gnf_dag_embed_bwd");
   }
-  GNF_LAUNCH(dag_embed_bwd_kernel, dim3(ceil_div(d, 128), ceil_div(d, 2 * kEmbBwdI)), 256, 0, s, g, dE, lde, dx, dP, B);
+  const dim3 grid(ceil_div(d, 128), ceil_div(d, 2 * kEmbBwdI));
+  if (DX) {
+    if ((lde % 4) != 0 || ((reinterpret_cast<uintptr_t>(dE) | reinterpret_cast<uintptr_t>(DX) | reinterpret_cast<uintptr_t>(DP)) & 15) != 0)
+      return fail(GNF_ERR_INVALID, "gnf_dag_embed_bwd: the planes must have 16-byte aligned rows (lde %% 4 == 0)");
+    GNF_LAUNCH(dag_embed_bwd_saved_kernel, dim3(ceil_div(d, 256), ceil_div(d, 4 * kEmbSavedI)), 256, 0, s, dE, DX, DP, lde, dx, dP, B, d);
+  } else {
+    GateCtx g;
+    if (int e = make_gate(&g, x, P, gate, d)) return e;
+    GNF_LAUNCH(dag_embed_bwd_kernel, grid, 256, 0, s, g, dE, lde, dx, dP, B);
+  }
   return check_launch("gnf_dag_embed_bwd");
 }
 

@@ -34,6 +34,7 @@ def enable_kernel_timing(flag):
     if flag:
         _TIMES.clear()
         _FLOPS.clear()
+        _SHAPES.clear()
 
 
 def collect_kernel_timing():
@@ -50,9 +51,29 @@ def collect_call_flops():
     return {k: list(v) for k, v in _FLOPS.items()}
 
 
-def _note_flops(name, flops):
+_SHAPES = {}
+
+
+def collect_call_shapes():
+    """{entry point: [(M, N, K) per call]} for the GEMM entry points timed since enable_kernel_timing(True)."""
+    return {k: list(v) for k, v in _SHAPES.items()}
+
+
+def _note_flops(name, flops, shape=None):
     if _TIMING:
         _FLOPS.setdefault(name, []).append(float(flops))
+        _SHAPES.setdefault(name, []).append(shape)
+
+
+def tc_kernel_name(op, M, N, K, passes=3, presplit=True):
+    """Which kernel of the tcgen05 GEMM engine a layer call of this shape launches (mirrors g2_eligible / w2_eligible in
+    csrc/tc_gemm.cu for TMA-loadable operands): op 'fwd' / 'dgrad' (M rows, N out-features, K in-features) or 'wgrad'."""
+    if passes == 3 and presplit:
+        if op == "wgrad":
+            return "tc_wgrad2_kernel" if (N >= 256 and K >= 256 and M >= 2048) else "tc_gemm_kernel"
+        n, k = (N, K) if op == "fwd" else (K, N)
+        return "tc_gemm2_kernel" if (M >= 1024 and n >= 256 and k >= 128) else "tc_gemm_kernel"
+    return "tc_gemm_kernel"
 
 
 _TIMES_ALIAS = {}    # entry point -> the name its timings are filed under (flavours of one kernel)
@@ -361,7 +382,7 @@ def _split_mat(X, M, K, ldx):
 
 def _ps2(op, A, B, ldab, bias, bias_period, act, C, ldc, M, N, K, relu, name):
     """gnf_linear_tc_ps2 with both operands pre-split; A, B = (hi, lo) pairs."""
-    _note_flops(name, 2. * M * N * K)
+    _note_flops(name, 2. * M * N * K, (M, N, K))
     _TIMES_ALIAS["gnf_linear_tc_ps2"] = name
     _call("gnf_linear_tc_ps2", op, ptr(A[0]), ptr(A[1]), ldab[0], ptr(B[0]), ptr(B[1]), ldab[1], ptr(bias), bias_period,
           ptr(act), (act.stride(0) if act is not None else 0), ptr(C), ldc, M, N, K, int(relu), stream_ptr())
@@ -385,13 +406,13 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
         _ps2(0, used, (wh, wl), (used[0].stride(0), wh.stride(0)), bias, bias_period, None, out, ldy, M, N, K, relu, "gnf_linear_fwd_tc")
     elif passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(X, ldx) and K == W.shape[1]:
         hi, lo = _split_weight(W)
-        _note_flops("gnf_linear_fwd_tc", 2. * M * N * K)
+        _note_flops("gnf_linear_fwd_tc", 2. * M * N * K, (M, N, K))
         _TIMES_ALIAS["gnf_linear_fwd_tc_ps"] = "gnf_linear_fwd_tc"
         _call("gnf_linear_fwd_tc_ps", ptr(X), ldx, ptr(hi), ptr(lo), hi.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K,
               int(relu), stream_ptr())
     elif passes:
         W = _tma_weight(W)
-        _note_flops("gnf_linear_fwd_tc", 2. * M * N * K)
+        _note_flops("gnf_linear_fwd_tc", 2. * M * N * K, (M, N, K))
         _call("gnf_linear_fwd_tc", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
               passes, stream_ptr())
     else:
@@ -412,13 +433,13 @@ def linear_dgrad(dY, lddy, W, act, M, out=None, lddx=None, dy_split=None):
         _ps2(1, dy_split, (wh, wl), (dy_split[0].stride(0), wh.stride(0)), None, 1, act, out, lddx, M, N, K, 0, "gnf_linear_dgrad_tc")
     elif passes == 3 and PRESPLIT_WEIGHTS and _tma_ok(dY, lddy):
         hi, lo = _split_weight(W)
-        _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K)
+        _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K, (M, N, K))
         _TIMES_ALIAS["gnf_linear_dgrad_tc_ps"] = "gnf_linear_dgrad_tc"
         _call("gnf_linear_dgrad_tc_ps", ptr(dY), lddy, ptr(hi), ptr(lo), hi.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
               ptr(out), lddx, M, N, K, stream_ptr())
     elif passes:
         W = _tma_weight(W)
-        _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K)
+        _note_flops("gnf_linear_dgrad_tc", 2. * M * N * K, (M, N, K))
         _call("gnf_linear_dgrad_tc", ptr(dY), lddy, ptr(W), W.stride(0), ptr(act), (act.stride(0) if act is not None else 0),
               ptr(out), lddx, M, N, K, passes, stream_ptr())
     else:
@@ -436,7 +457,7 @@ def linear_wgrad(dY, lddy, X, ldx, M, N, K, dy_split=None, x_split=None, out=Non
     if passes == 3 and PRESPLIT_ACTS and dy_split is not None and x_split is not None:
         _ps2(2, dy_split, x_split, (dy_split[0].stride(0), x_split[0].stride(0)), None, 1, None, dW, lddw, M, N, K, 0, "gnf_linear_wgrad_tc")
     elif passes:
-        _note_flops("gnf_linear_wgrad_tc", 2. * M * N * K)
+        _note_flops("gnf_linear_wgrad_tc", 2. * M * N * K, (M, N, K))
         _call("gnf_linear_wgrad_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), lddw, M, N, K, passes, stream_ptr())
     else:
         _call("gnf_linear_wgrad", ptr(dY), lddy, ptr(X), ldx, ptr(dW), lddw, M, N, K, stream_ptr())
@@ -624,6 +645,7 @@ def dag_dump_noise(gate, B, d, device):
 # kernels that generate the gate inside their operand loaders: cfg5 layer 1 30 ms -> ~4 ms per step (profiles/r02p_*).
 DAG_L1_PLANE = True
 DAG_L1_PLANE_MIN_D = 65
+DAG_L1_PLANE_KEEP_DERIVATIVES = True      # training keeps the de/dx and de/dP planes (2 x 246 MB at cfg5) instead of regenerating the gates
 
 
 def _dag_l1_plane(M, N1, d, direction):
@@ -662,9 +684,12 @@ class DagMlpFn(torch.autograd.Function):
         g = gate.c_struct()
         y = _rows(B * d, N1, x) if n > 1 else torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
         E = W1e = None
+        gate_planes = (None, None)
         if _dag_l1_plane(B * d, N1, d, "fwd"):
             E = _rows(B * d, d, x)
-            _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), E.stride(0), B, d, st)
+            if DAG_L1_PLANE_KEEP_DERIVATIVES and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+                gate_planes = (_rows(B * d, d, x), _rows(B * d, d, x))        # de/dx, de/dP (same row stride as E): the backward reduction streams them
+            _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), ptr(gate_planes[0]), ptr(gate_planes[1]), E.stride(0), B, d, st)
             W1e = weights[0][:, :d]                 # the masked-input half of layer 1; the one-hot half is the bias table T
             linear_fwd(E, W1e, T, relu=(n > 1), bias_period=(d if hot else 1), out=y, ldy=y.stride(0), K=d, ldx=E.stride(0))
             _count(2)
@@ -683,6 +708,7 @@ class DagMlpFn(torch.autograd.Function):
             cur, splits[l] = linear_fwd(cur, weights[l], biases[l], relu=(l < n - 1), out=out, ldy=weights[l].shape[0], want_split=True)
         ctx.act_splits = splits if any(ctx.needs_input_grad) else None
         ctx.E, ctx.W1e = (E, W1e) if any(ctx.needs_input_grad) else (None, None)
+        ctx.gate_planes = gate_planes
         ctx.save_for_backward(x, A, P, dPdA, *weights, *acts)
         ctx.gate, ctx.hot, ctx.n = gate, hot, n
         if n == 1:
@@ -708,12 +734,14 @@ class DagMlpFn(torch.autograd.Function):
         g = gate.c_struct()
         dW1 = torch.empty_like(W1)
         E, W1e = ctx.E, ctx.W1e
+        DXp, DPp = ctx.gate_planes
         ctx.E = ctx.W1e = None
+        ctx.gate_planes = (None, None)
         if E is not None and not _dag_l1_plane(M, N1, d, "bwd"):
             E = None
         elif E is None and _dag_l1_plane(M, N1, d, "bwd"):        # forward ran on the loader kernels: regenerate the plane (same Philox counters)
             E = _rows(M, d, x)
-            _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), E.stride(0), B, d, st)
+            _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), None, None, E.stride(0), B, d, st)
             W1e = W1[:, :d]
         if E is not None:
             linear_wgrad(delta, delta.stride(0), E, E.stride(0), M, N1, d, out=dW1, lddw=dW1.stride(0))
@@ -730,8 +758,8 @@ class DagMlpFn(torch.autograd.Function):
             dP = torch.empty_like(A)
             if E is not None:
                 dE = linear_dgrad(delta, delta.stride(0), W1e, None, M)
-                _call("gnf_dag_embed_bwd", ptr(dE), dE.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx), ptr(dP), B, d, st)
-                del dE
+                _call("gnf_dag_embed_bwd", ptr(dE), dE.stride(0), ptr(x), ptr(P), C.byref(g), ptr(DXp), ptr(DPp), ptr(dx), ptr(dP), B, d, st)
+                del dE, DXp, DPp
             else:
                 _call("gnf_dag_l1_dgrad", ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx),
                                              ptr(dP), B, d, N1, st)

@@ -198,13 +198,16 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
 /* Wide flows on the tensor-core GEMM engine (d > 64, cfg5): the masked embedding of DAGConditioner.forward
  * (DAGConditioner.py:126-153: x.unsqueeze(1).expand(-1,d,-1) * gate) written once as a plane
  *   E[b*d+i, j] = x[b,j] G[b,i,j]   ([B*d, lde], lde % 4 == 0, padding columns zero)
- * so that layer 1's forward / weight-gradient / input-cotangent GEMMs run on gnf_linear_*_tc against it ... */
-int gnf_dag_embed_fwd(const float* x, const float* P, const gnf_gate_t* gate, float* E, int lde, int B, int d,
-                      gnf_stream_t stream);
-/* ... and the reduction of the cotangent plane dE = dY W1[:, :d] those GEMMs leave (autograd through the same lines):
- *   dx[b,j] = sum_i dE[b*d+i,j] de/dx(b,i,j);  dP[i,j] = sum_b dE[b*d+i,j] de/dP(b,i,j).  dx is zero-filled by the call. */
-int gnf_dag_embed_bwd(const float* dE, int lde, const float* x, const float* P, const gnf_gate_t* gate, float* dx,
-                      float* dP, int B, int d, gnf_stream_t stream);
+ * so that layer 1's forward / weight-gradient / input-cotangent GEMMs run on gnf_linear_*_tc against it.  DX / DP (nullable,
+ * both or neither; same shape as E): training also keeps the gate's partial derivatives de/dx and de/dP ... */
+int gnf_dag_embed_fwd(const float* x, const float* P, const gnf_gate_t* gate, float* E, float* DX, float* DP, int lde, int B,
+                      int d, gnf_stream_t stream);
+/* ... for the reduction of the cotangent plane dE = dY W1[:, :d] those GEMMs leave (autograd through the same lines):
+ *   dx[b,j] = sum_i dE[b*d+i,j] de/dx(b,i,j);  dP[i,j] = sum_b dE[b*d+i,j] de/dP(b,i,j).  dx is zero-filled by the call.
+ * With DX / DP the pass streams the three planes; without them (NULL) the gate is regenerated from x, P and the same Philox
+ * counters. */
+int gnf_dag_embed_bwd(const float* dE, int lde, const float* x, const float* P, const gnf_gate_t* gate, const float* DX,
+                      const float* DP, float* dx, float* dP, int B, int d, gnf_stream_t stream);
 /* dA[i,j] (+)= dP[i,j]*dPdA[i,j]. */
 int gnf_dag_finish_dA(const float* dP, const float* dPdA, float* dA, int d, int accumulate, gnf_stream_t stream);
 /* Debug / parity hook: materialise the in-kernel Philox draws for (seed, offset) as [B,d,d] tensors. */

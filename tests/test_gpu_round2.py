@@ -117,8 +117,8 @@ def test_bench_eval_mode_cfg5_vs_oracle(engine_reset):
 
 @pytest.mark.parametrize("mode,imp", [("GATE_GUMBEL", "IMP_SOFT"), ("GATE_TABLE", "IMP_HARD_SOFT"), ("GATE_NOISER", "IMP_SOFT")])
 @pytest.mark.parametrize("B,d,N1,hot", [(40, 96, 160, True), (7, 130, 136, False)])
-@pytest.mark.parametrize("layers", [1, 2])
-def test_dag_layer1_embedding_plane_matches_the_loader_kernels(engine_reset, mode, imp, B, d, N1, hot, layers):
+@pytest.mark.parametrize("layers,keep", [(1, True), (1, False), (2, True)])
+def test_dag_layer1_embedding_plane_matches_the_loader_kernels(engine_reset, mode, imp, B, d, N1, hot, layers, keep):
     """Wide-flow layer 1 (d > 64) on the tensor-core engine: embedding plane + 3xTF32 GEMMs + cotangent reduction
     (gnf_dag_embed_fwd / gnf_dag_embed_bwd) against the FFMA kernels that generate the gate in their operand loaders --
     same Philox counters, so the two paths see the same gates: h, dx, dA and every weight gradient agree to fp32 accuracy
@@ -136,6 +136,7 @@ def test_dag_layer1_embedding_plane_matches_the_loader_kernels(engine_reset, mod
     G.ops.set_gemm_mode("tf32x3")
     for plane in (True, False):
         G.ops.DAG_L1_PLANE = plane
+        G.ops.DAG_L1_PLANE_KEEP_DERIVATIVES = keep     # the backward reduction streams the kept de/dx, de/dP planes / regenerates the gates
         try:
             x, A = x0.clone().requires_grad_(), A0.clone().requires_grad_()
             params = [t.clone().requires_grad_() for pair in zip(W, b) for t in pair]
@@ -146,6 +147,7 @@ def test_dag_layer1_embedding_plane_matches_the_loader_kernels(engine_reset, mod
             G.ops.enable_kernel_timing(False)
         finally:
             G.ops.DAG_L1_PLANE = True
+            G.ops.DAG_L1_PLANE_KEEP_DERIVATIVES = True
         assert ("gnf_dag_embed_fwd" in called) == plane and ("gnf_dag_embed_bwd" in called) == plane
         outs[plane] = [h.detach(), x.grad, A.grad] + [p.grad for p in params]
     for name, a, r in zip(["h", "dx", "dA", "dW1", "db1", "dW2", "db2"], outs[True], outs[False]):
