@@ -252,8 +252,10 @@ def main():
     ap.add_argument("--random-steps", action="store_true",
                     help="train: S = nb_steps + U{0..9} per step as the reference's UCI driver does (UCIExperiments.py:131-133); one "
                          "captured graph per S")
-    ap.add_argument("--allreduce", default="single", choices=["overlap", "single", "none"],
-                    help="N > 1: one flat bucket all-reduced after the backward (default); sub-buckets overlapped with the rest of the backward (measured slower: the NCCL CTAs displace CTAs of the 148-CTA persistent GEMMs); none = measurement only")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "overlap", "single", "none"],
+                    help="N > 1, gradient average of the flat bucket after the backward: peer = ONE libgnf kernel over NVLink peer memory (default; falls back "
+                         "to single when CUDA IPC is unavailable); single = one NCCL all-reduce; overlap = NCCL sub-buckets overlapped with the rest of "
+                         "the backward (measured slower: the NCCL CTAs displace CTAs of the 148-CTA persistent GEMMs); none = measurement only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="train mode: skip the additional log-lik eval measurement")
     ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
@@ -308,7 +310,9 @@ def main():
     G.dist.decorrelate_gate_noise(model, rank)
     d = spec["d"]
     lr, wd = ADAM[cfg]
-    bucket = G.dist.GradBucket(model.parameters(), overlap=(args.allreduce == "overlap"))
+    bucket = G.dist.GradBucket(model.parameters(), overlap=(args.allreduce == "overlap"), peer=(args.allreduce == "peer"))
+    if args.allreduce == "peer":
+        config["allreduce"] = "peer" if bucket.peer is not None else ("single" if world > 1 else "peer")
     # the reference's optimizer (torch.optim.Adam(lr, weight_decay), UCIExperiments.py:100) as one multi-tensor launch per step
     opt = G.FusedAdam(model.parameters(), lr=lr, weight_decay=wd)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)

@@ -79,6 +79,13 @@ _PROTOS = {
     "gnf_dag_l1_fwd": ([_P, _P, C.POINTER(GateT), _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_dag_l1_wgrad": ([_P, _I, _P, _P, C.POINTER(GateT), _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_dag_l1_dgrad": ([_P, _I, _P, _I, _P, _P, C.POINTER(GateT), _P, _P, _I, _I, _I, _P], C.c_int),
+    "gnf_peer_alloc": ([_SZ, C.POINTER(C.c_void_p)], C.c_int),
+    "gnf_peer_free": ([_P], C.c_int),
+    "gnf_peer_export": ([_P, C.c_char_p], C.c_int),
+    "gnf_peer_import": ([C.c_char_p, C.POINTER(C.c_void_p)], C.c_int),
+    "gnf_peer_close": ([_P], C.c_int),
+    "gnf_peer_flag_bytes": ([], _SZ),
+    "gnf_peer_allreduce_avg": ([C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I, _I, C.c_longlong, _P], C.c_int),
     "gnf_dag_embed_fwd": ([_P, _P, C.POINTER(GateT), _P, _P, _P, _I, _I, _I, _P], C.c_int),
     "gnf_dag_embed_bwd": ([_P, _I, _P, _P, C.POINTER(GateT), _P, _P, _P, _P, _I, _I, _P], C.c_int),
     "gnf_dag_finish_dA": ([_P, _P, _P, _I, _I, _P], C.c_int),

@@ -23,6 +23,76 @@ def broadcast_parameters(model, src=0):
             dist.broadcast(t.data, src)
 
 
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device allocation (torch.as_tensor wraps it without copying)."""
+
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerGroup:
+    """NVLink peer-memory exchange group of the ranks of one node (csrc/peer.cu): every rank owns a cudaMalloc'ed fp32 bucket and
+    a flag block, opened by all other ranks through CUDA IPC handles (exchanged once with all_gather_object).  `flat` is this
+    rank's bucket as a torch tensor; `allreduce_avg()` enqueues ONE kernel that averages it over the ranks in place.
+    Raises RuntimeError when peer memory cannot be set up (the caller falls back to NCCL)."""
+
+    def __init__(self, numel, device):
+        import ctypes as C
+        from . import _lib as L
+        lib = L.lib()
+        self._lib, self._C = lib, C
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.numel = (int(numel) + 3) // 4 * 4
+        self.device = torch.device(device)
+        self._own, self._opened = [], []
+        with torch.cuda.device(self.device):
+            buf, flag = C.c_void_p(), C.c_void_p()
+            ok = lib.gnf_peer_alloc(self.numel * 4, C.byref(buf)) == 0 and lib.gnf_peer_alloc(lib.gnf_peer_flag_bytes(), C.byref(flag)) == 0
+            self._own = [buf, flag]
+            hb, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+            ok = ok and lib.gnf_peer_export(buf, hb) == 0 and lib.gnf_peer_export(flag, hf) == 0
+            mine = (bytes(hb.raw), bytes(hf.raw)) if ok else None
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)
+            if any(h is None for h in everyone):
+                self.close()
+                raise RuntimeError("peer memory: an export failed on some rank: " + lib.gnf_last_error().decode())
+            bufs, flags = (C.c_void_p * self.world)(), (C.c_void_p * self.world)()
+            fail = None
+            for r, (b, f) in enumerate(everyone):
+                if r == self.rank:
+                    bufs[r], flags[r] = buf.value, flag.value
+                    continue
+                pb, pf = C.c_void_p(), C.c_void_p()
+                if lib.gnf_peer_import(b, C.byref(pb)) != 0 or lib.gnf_peer_import(f, C.byref(pf)) != 0:
+                    fail = lib.gnf_last_error().decode()
+                    break
+                self._opened += [pb, pf]
+                bufs[r], flags[r] = pb.value, pf.value
+            status = [None] * self.world
+            dist.all_gather_object(status, fail)
+            if any(st is not None for st in status):
+                self.close()
+                raise RuntimeError("peer memory: " + "; ".join(st for st in status if st))
+            self._bufs, self._flags = bufs, flags
+            self.flat = torch.as_tensor(_DevArray(buf.value, self.numel), device=self.device)
+        dist.barrier()
+
+    def allreduce_avg(self):
+        from . import _lib as L
+        from . import ops
+        ops._call("gnf_peer_allreduce_avg", self._bufs, self._flags, self.rank, self.world, self.numel, L.stream_ptr())
+        ops._count()
+
+    def close(self):
+        for p in self._opened:
+            self._lib.gnf_peer_close(p)
+        for p in self._own:
+            if p and p.value:
+                self._lib.gnf_peer_free(p)
+        self._opened, self._own = [], []
+
+
 class GradBucket:
     """Flat gradient buffer; every ``p.grad`` aliases a slice of it after the all-reduce.
 
@@ -34,13 +104,24 @@ class GradBucket:
     backward.  Only the last, small sub-bucket (first layer + A) is exposed.  Works inside CUDA-graph capture (the side stream
     is forked from and joined to the capturing stream)."""
 
-    def __init__(self, params, bucket_bytes=1 << 21, overlap=True):
+    def __init__(self, params, bucket_bytes=1 << 21, overlap=True, peer=False):
+        """peer=True (CUDA, world_size > 1, all ranks on one node): the bucket lives in NVLink peer memory and the average is ONE
+        kernel of libgnf (PeerGroup / gnf_peer_allreduce_avg) instead of a NCCL all-reduce; silently falls back to NCCL when
+        CUDA IPC is not available.  `self.peer` tells which one is active."""
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        self.peer = None
+        if peer and is_dist() and dev.type == "cuda" and dt == torch.float32:
+            try:
+                self.peer = PeerGroup(self.numel, dev)
+                overlap = False
+            except RuntimeError as err:
+                import warnings
+                warnings.warn(f"GradBucket: {err}; using the NCCL all-reduce")
+        self.flat = self.peer.flat[:self.numel] if self.peer is not None else torch.zeros(self.numel, device=dev, dtype=dt)
         off = 0
         self._offsets = {}
         for p in self.params:
@@ -144,7 +225,9 @@ class GradBucket:
         itself)."""
         if not is_dist():
             return
-        if self.flat.is_cuda:
+        if self.peer is not None:
+            self.peer.allreduce_avg()
+        elif self.flat.is_cuda:
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
         else:                                                     # gloo (CPU tests) has no AVG
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)

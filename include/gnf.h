@@ -32,6 +32,7 @@ typedef void* gnf_stream_t; /* cudaStream_t */
 #define GNF_ERR_INVALID 1001     /* bad argument */
 #define GNF_ERR_UNSUPPORTED 1002 /* shape or mode outside what the kernels cover */
 #define GNF_ERR_WORKSPACE 1003   /* workspace too small */
+#define GNF_ERR_PEER 1004        /* peer memory (CUDA IPC between the ranks of one node) unavailable */
 
 #define GNF_MAX_LAYERS 8
 
@@ -311,6 +312,25 @@ typedef struct {
 } gnf_adam_tensor_t;
 int gnf_adam_step(const gnf_adam_tensor_t* tensors, int n_tensors, const int64_t* step_dev, float lr, float beta1, float beta2,
                   float eps, float weight_decay, gnf_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory (one process per GPU; replaces the gradient gather of the
+ * reference's nn.DataParallel, ImageExperiments.py:168, and the NCCL all-reduce of the flat bucket): every rank allocates its
+ * bucket and a flag block with gnf_peer_alloc (the one place where the library allocates device memory: cudaIpc needs a
+ * cudaMalloc base), exports 64-byte handles, imports its peers' and passes the pointer tables to gnf_peer_allreduce_avg:
+ * ONE kernel = barrier, reduce-scatter by peer loads, all-gather by peer stores, barrier; in place, bit-identical on every
+ * rank, replayable inside a CUDA graph (the barrier epoch lives in the flag block).
+ * -------------------------------------------------------------------------------------------- */
+int gnf_peer_alloc(size_t bytes, void** out);                    /* zero-filled */
+int gnf_peer_free(void* p);
+int gnf_peer_export(const void* p, unsigned char* handle64);     /* cudaIpcGetMemHandle */
+int gnf_peer_import(const unsigned char* handle64, void** out);  /* cudaIpcOpenMemHandle with lazy peer access */
+int gnf_peer_close(void* p);
+size_t gnf_peer_flag_bytes(void);
+/* bufs / flags: [world] device pointers (entry `rank` = this rank's own allocations), numel % 4 == 0, world <= 16.
+ * Every rank of the group must make the call once per step; bufs[rank][0..numel) becomes the mean over ranks. */
+int gnf_peer_allreduce_avg(float* const* bufs, unsigned* const* flags, int rank, int world, long long numel,
+                           gnf_stream_t stream);
 
 /* Backward of the integral with the dgrad chain fused on the tensor cores (UMNN NeuralIntegral.backward; same
  * cotangents, outputs and gradient conventions as gnf_umnn_bwd / gnf_umnn_bwd_lw; 3xTF32): the cotangent of the pre-ELU output is
