@@ -3,6 +3,7 @@
 // the small pack / reduce helpers around them.  See include/gnf.h for the reference lines each
 // entry point replaces.
 #include "gemm.cuh"
+#include "thin.cuh"
 
 namespace gnf {
 
@@ -521,6 +522,28 @@ __global__ void __launch_bounds__(256) dag_embed_bwd_kernel(GateCtx g, const flo
     if (i0 + k < g.d) dP[(size_t)(i0 + k) * g.d + j] = acc[k];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny layers: launchers of thin.cuh (return false when the shape does not fit: the tile GEMM takes over)
+// ------------------------------------------------------------------------------------------------
+static int g_thin = 1;                     // measurement switch (gnf_linear_set_thin, dev build)
+constexpr int kThinMinRows = 512;
+
+static bool thin_launch_red(const float* in, int ldin, const float* Wp, long long s_t, long long s_w, const float* bias, int relu, const float* act,
+                            int ldact, float* out, int ldout, int M, int T, int Wd, cudaStream_t s) {
+  const size_t smem = thin_red_smem(T, Wd);
+  if (T > kThinT || smem > 200 * 1024) return false;
+#ifndef GNF_EMU
+  cudaFuncSetAttribute(thin_red_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  // every CTA loads the weight image before it can start: no more CTAs than one resident wave (each warp streams its share of the rows)
+  const long long warps = ((long long)M + kThinRows - 1) / kThinRows;
+  long long grid = (warps + kThinThreads / 32 - 1) / (kThinThreads / 32);
+  const int per_sm = thin_per_sm(smem, 4);
+  if (grid > (long long)per_sm * kNumSMs) grid = (long long)per_sm * kNumSMs;
+  GNF_LAUNCH(thin_red_kernel, (int)grid, kThinThreads, smem, s, in, ldin, Wp, s_t, s_w, bias, relu, act, ldact, out, ldout, M, T, Wd);
+  return true;
+}
+
 static int g_dag_l1_resident = 1;   // measurement switch (gnf_dag_l1_set_resident): 0 = functor-loader tile GEMM for every d
 
 static int make_gate(GateCtx* out, const float* x, const float* P, const gnf_gate_t* gate, int d) {
@@ -677,6 +700,10 @@ int gnf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float
   if (!X || !W || !Y || M < 0 || N <= 0 || K <= 0 || ldx < K || ldw < K || ldy < N) return fail(GNF_ERR_INVALID, "gnf_linear_fwd: bad arguments");
   if (M == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (g_thin && bias_period <= 1 && M >= kThinMinRows) {
+    // a reduction of a few terms (thin.cuh): Y[m, n] = sum_k X[m, k] W[n, k]
+    if (K <= kThinT && N <= kThinMaxWide && thin_launch_red(X, ldx, W, 1, ldw, bias, relu, nullptr, 0, Y, ldy, M, K, N, s)) return check_launch("gnf_linear_fwd");
+  }
   LoadRowMajorA al{X, ldx};
   LoadWeightT bl{W, ldw};
   EpiBiasAct epi{Y, ldy, bias, N, bias_period < 1 ? 1 : bias_period, relu};
@@ -689,6 +716,10 @@ int gnf_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const f
   if (!dY || !W || !dX || M < 0 || N <= 0 || K <= 0 || lddy < N || ldw < K || lddx < K) return fail(GNF_ERR_INVALID, "gnf_linear_dgrad: bad arguments");
   if (M == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (g_thin && M >= kThinMinRows) {
+    // a reduction of a few terms (thin.cuh): dX[m, k] = sum_n dY[m, n] W[n, k]
+    if (N <= kThinT && K <= kThinMaxWide && thin_launch_red(dY, lddy, W, ldw, 1, nullptr, 0, act, ldact, dX, lddx, M, N, K, s)) return check_launch("gnf_linear_dgrad");
+  }
   LoadRowMajorA al{dY, lddy};        // A(m, n) reduction over n
   LoadRowMajorB bl{W, ldw};          // B(n, k) = W[n, k]
   EpiMaskStore epi{dX, lddx, act, ldact};
@@ -867,6 +898,13 @@ int gnf_dag_embed_bwd(const float* dE, int lde, const float* x, const float* P, 
   }
   return check_launch("gnf_dag_embed_bwd");
 }
+
+#ifdef GNF_DEVTOOLS
+int gnf_linear_set_thin(int enable) {
+  g_thin = enable != 0;
+  return 0;
+}
+#endif
 
 #ifdef GNF_DEVTOOLS
 int gnf_dag_l1_set_resident(int enable) {

@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     float* stage = epi_stage + warp * kG2EpiStageFloats;
     const int sub = lane >> 3, piece = lane & 7;
-    const bool mask = p.epi == TCG_EPI_MASK;
+    const bool mask = p.epi == TCG_EPI_MASK && p.act != nullptr;          // a dgrad without a ReLU behind it (act == NULL) stores the plain product
     const bool table = !mask && p.bias != nullptr && p.bias_period > 1;   // periodic bias table (DAG layer 1: one row per variable): added on the coalesced side
     const int ngroups = (nchunks + fold - 1) / fold;
     int gcount = 0;
@@ -922,10 +922,10 @@ static bool g2_eligible(const TcGemmParams& p) {
   if (p.passes != 3 || !p.B_lo || p.A_lo || p.a_src != TCG_SRC_K || p.epi == TCG_EPI_ATOMIC || p.bits_out || p.mask_bits) return false;
   if (p.epi == TCG_EPI_BIAS_ACT && p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0) return false;
   if (p.epi == TCG_EPI_BIAS_ACT && p.bias && p.bias_period > 1 && ((p.N % 4) != 0 || (p.bias_ld % 4) != 0)) return false;
-  if (p.epi == TCG_EPI_MASK && (!p.act || (reinterpret_cast<uintptr_t>(p.act) & 15) != 0 || (p.ldact % 4) != 0)) return false;
+  if (p.epi == TCG_EPI_MASK && p.act && ((reinterpret_cast<uintptr_t>(p.act) & 15) != 0 || (p.ldact % 4) != 0)) return false;
   const int N4 = (p.N + 3) / 4 * 4;                        // 16-byte pieces: a row's last piece may reach into its padding columns
   if (p.ldc < N4 || (p.ldc % 4) != 0 || (reinterpret_cast<uintptr_t>(p.C) & 15) != 0) return false;
-  if (p.epi == TCG_EPI_MASK && p.ldact < N4) return false;
+  if (p.epi == TCG_EPI_MASK && p.act && p.ldact < N4) return false;
   return p.M >= 1024 && p.N >= 256 && p.K >= 128;          // small problems: the planned tiling of the engine above
 }
 

@@ -58,6 +58,8 @@ int gnf_tc_gemm_set_v2(int enable);
 /* Fused strict UMNN forward (tc_umnn3.cu): CTA 0 records SM-clock stamps into buf[4][256] (rows: issuer, epilogue warp 0,
  * producer, epilogue warp of the last column block); NULL disables. */
 int gnf_umnn_tc3_set_trace(long long* buf);
+/* 0: skinny layers (one weight dimension <= 32) run on the register-tiled GEMM instead of the kernels of csrc/thin.cuh. */
+int gnf_linear_set_thin(int enable);
 /* Ablation: bit0 skip the global stores of the saved planes, bit1 skip their staging too, bit2 skip masks / pre-ELU outputs. */
 int gnf_umnn_tc3_set_debug(int bits);
 

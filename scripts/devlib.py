@@ -25,6 +25,7 @@ DEV_PROTOS = {
     "gnf_tc_gemm_set_v2": ([_I], C.c_int),
     "gnf_umnn_tc3_set_trace": ([_P], C.c_int),
     "gnf_umnn_tc3_set_debug": ([_I], C.c_int),
+    "gnf_linear_set_thin": ([_I], C.c_int),
 }
 
 

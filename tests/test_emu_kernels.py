@@ -82,3 +82,17 @@ def test_fused_bisection_inverse_in_simulator(emu):
     res = 40. / 2 ** 20
     assert float((x_fused - x_loop).abs().max()) <= res * 1.01
     assert float((x_fused - x).abs().max()) < 2 * res
+
+
+@pytest.mark.parametrize("M_,N,K", [(520, 5, 70), (515, 70, 5), (600, 32, 33)])
+def test_skinny_layer_kernels_in_simulator(emu, M_, N, K):
+    """csrc/thin.cuh (one weight dimension <= 32): forward with bias + ReLU and the masked input cotangent, both weight layouts,
+    against torch."""
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(M_ + N + K)
+    X, W, b = torch.randn(M_, K, generator=g), torch.randn(N, K, generator=g) / K ** .5, torch.randn(N, generator=g)
+    dY = torch.randn(M_, N, generator=g)
+    Y = G.ops.linear_fwd(X, W, b, relu=True)
+    assert torch.allclose(Y, torch.relu(X @ W.t() + b), rtol=1e-4, atol=1e-5)
+    dX = G.ops.linear_dgrad(dY, N, W, X, M_)
+    assert torch.allclose(dX, (dY @ W) * (X > 0), rtol=1e-4, atol=1e-5)

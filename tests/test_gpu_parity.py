@@ -70,7 +70,10 @@ def test_compute_ll_api_matches_forward():
 
 
 # ---------------- kernel-level checks through the C-ABI wrappers ----------------
-@pytest.mark.parametrize("M_,N,K", [(1, 1, 1), (127, 33, 65), (300, 630, 126), (1000, 30, 630), (64, 2, 1024), (513, 210, 21)])
+@pytest.mark.parametrize("M_,N,K", [(1, 1, 1), (127, 33, 65), (300, 630, 126), (1000, 30, 630), (64, 2, 1024), (513, 210, 21),
+                                    # skinny layers (csrc/thin.cuh: one weight dimension <= 32, >= 512 rows): thin output / thin reduction
+                                    (6300, 30, 630), (6300, 150, 30), (6301, 31, 1), (777, 32, 1536), (2049, 5, 33), (4096, 1, 700), (900, 700, 7),
+                                    (6300, 630, 30), (513, 32, 32)])
 def test_linear_engine_vs_torch(M_, N, K):
     g = torch.Generator(device="cuda").manual_seed(M_ + N + K)
     X = torch.randn(M_, K, device="cuda", generator=g)
