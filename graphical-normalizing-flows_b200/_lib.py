@@ -64,6 +64,7 @@ _PROTOS = {
     "gnf_linear_fwd_tc": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_dgrad_tc": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_wgrad_tc": ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "gnf_linear_wgrad_bias_tc": ([_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P], C.c_int),
     "gnf_split_tf32": ([_P, _I, _P, _P, _I, _I, _I, _P], C.c_int),
     "gnf_linear_tc_ps2": ([_I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_linear_fwd_tc_ps": ([_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
@@ -79,6 +80,9 @@ _PROTOS = {
     "gnf_dag_l1_fwd": ([_P, _P, C.POINTER(GateT), _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gnf_dag_l1_wgrad": ([_P, _I, _P, _P, C.POINTER(GateT), _P, _I, _I, _I, _I, _P], C.c_int),
     "gnf_dag_l1_dgrad": ([_P, _I, _P, _I, _P, _P, C.POINTER(GateT), _P, _P, _I, _I, _I, _P], C.c_int),
+    "gnf_nll_loss_work_floats": ([_I], _SZ),
+    "gnf_nll_loss_fwd": ([_P, _P, _P, _P, _P, _I, _I, _P], C.c_int),
+    "gnf_nll_loss_bwd": ([_P, _P, _P, _P, _I, _I, _P], C.c_int),
     "gnf_peer_alloc": ([_SZ, C.POINTER(C.c_void_p)], C.c_int),
     "gnf_peer_free": ([_P], C.c_int),
     "gnf_peer_export": ([_P, C.c_char_p], C.c_int),

@@ -141,6 +141,8 @@ inline float atomicAdd(float* addr, float val) {
     if (a->compare_exchange_weak(old, nw)) { float r; memcpy(&r, &old, 4); return r; }
   }
 }
+inline unsigned atomicAdd(unsigned* addr, unsigned val) { return reinterpret_cast<std::atomic<uint32_t>*>(addr)->fetch_add(val); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }

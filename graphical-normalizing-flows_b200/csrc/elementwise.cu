@@ -92,6 +92,53 @@ __global__ void normal_ll_bwd_kernel(const float* __restrict__ z, const float* _
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) gz[i] = -z[i] * gout[i / d];
 }
 
+// Training loss in one launch (NormalizingFlow.py:144-146 + NormalizingFlowFactories.py:15-16): out = constraint - mean_b(ll_b),
+// ll_b = logdet_b - 0.5 sum_i (log 2pi + z_bi^2).  Every block writes the sum of its rows to work[block]; the last block to finish
+// (a self-resetting counter behind the partial sums) adds them in block order: deterministic, no memset, graph-replayable.
+__global__ void __launch_bounds__(256) nll_loss_fwd_kernel(const float* __restrict__ z, const float* __restrict__ logdet, const float* __restrict__ constraint,
+                                                           float* __restrict__ out, float* __restrict__ work, int B, int d) {
+  GNF_SMEM(float, s_part);                    // kRowsPerBlock partial sums + the "last block" flag
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float log2pi = 1.8378770664093453f;
+  float rows = 0.f;
+  for (int b = blockIdx.x * kRowsPerBlock + warp; b < B; b += gridDim.x * kRowsPerBlock) {
+    float acc = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float v = z[(size_t)b * d + i];
+      acc += log2pi + v * v;
+    }
+    acc = warp_sum(acc);
+    rows += (logdet ? logdet[b] : 0.f) + (-.5f) * acc;
+  }
+  if (lane == 0) s_part[warp] = rows;
+  __syncthreads();
+  unsigned* counter = reinterpret_cast<unsigned*>(work + gridDim.x);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kRowsPerBlock; ++w) t += s_part[w];
+    work[blockIdx.x] = t;
+    __threadfence();
+    s_part[kRowsPerBlock] = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1.f : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_part[kRowsPerBlock] != 0.f) {
+    __threadfence();
+    float t = 0.f;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += reinterpret_cast<volatile float*>(work)[k];
+    *out = (constraint ? *constraint : 0.f) - t / (float)B;
+    *counter = 0u;
+  }
+}
+
+// gz[b,i] = z[b,i] * g / B, glogdet[b] = -g / B  (g = the loss cotangent, a device scalar; NULL = 1)
+__global__ void nll_loss_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, float* __restrict__ gz, float* __restrict__ glogdet, int B, int d) {
+  const float s = (g ? *g : 1.f) / (float)B;
+  const size_t n = (size_t)B * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) gz[i] = z[i] * s;
+  if (glogdet)
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < (size_t)B; b += (size_t)gridDim.x * blockDim.x) glogdet[b] = -s;
+}
+
 __global__ void __launch_bounds__(256) logdet_fwd_kernel(const float* __restrict__ jac, float* __restrict__ logdet, int B, int d) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b = blockIdx.x * kRowsPerBlock + warp; b < B; b += gridDim.x * kRowsPerBlock) {
@@ -206,6 +253,20 @@ int gnf_normal_ll_bwd(const float* z, const float* gout, float* gz, int B, int d
   if (B == 0) return 0;
   GNF_LAUNCH(normal_ll_bwd_kernel, flat_blocks((size_t)B * d), 256, 0, (cudaStream_t)stream, z, gout, gz, B, d);
   return check_launch("gnf_normal_ll_bwd");
+}
+
+size_t gnf_nll_loss_work_floats(int B) { return (size_t)(B > 0 ? row_blocks(B) : 1) + 1; }
+
+int gnf_nll_loss_fwd(const float* z, const float* logdet, const float* constraint, float* out, float* work, int B, int d, gnf_stream_t stream) {
+  if (!z || !out || !work || B <= 0 || d <= 0) return fail(GNF_ERR_INVALID, "gnf_nll_loss_fwd: bad arguments (B >= 1; work = gnf_nll_loss_work_floats(B) floats whose last word is zero)");
+  GNF_LAUNCH(nll_loss_fwd_kernel, row_blocks(B), 256, (kRowsPerBlock + 1) * sizeof(float), (cudaStream_t)stream, z, logdet, constraint, out, work, B, d);
+  return check_launch("gnf_nll_loss_fwd");
+}
+
+int gnf_nll_loss_bwd(const float* z, const float* g, float* gz, float* glogdet, int B, int d, gnf_stream_t stream) {
+  if (!z || !gz || B <= 0 || d <= 0) return fail(GNF_ERR_INVALID, "gnf_nll_loss_bwd: bad arguments");
+  GNF_LAUNCH(nll_loss_bwd_kernel, flat_blocks((size_t)B * d), 256, 0, (cudaStream_t)stream, z, g, gz, glogdet, B, d);
+  return check_launch("gnf_nll_loss_bwd");
 }
 
 int gnf_logdet_fwd(const float* jac, float* logdet, int B, int d, gnf_stream_t stream) {

@@ -840,6 +840,30 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
       const int tm = w % tiles_m, tn = w / tiles_m;
       const int n0 = tn * kG2BN + ch, m0 = tm * kGemmBM + quarter * 32;
       float run[64];
+      // dgrad: the ReLU mask of this thread's output pieces (coalesced side: rows 4 i + sub, columns 4 piece .. + 3 of both 32-column
+      // blocks), fetched before the tile's first MMA group is awaited (the running sum is not live yet) and kept as 2 x 32 bits.  Loading it inside the output pass put one
+      // exposed global-load latency in front of every store (dgrad 508 us against 318 us for the plain product at 64512 x 632 x 632,
+      // profiles/r02ab_dgrad_probe.txt).  Clamped addresses: the loads are unconditional, out-of-range pieces are never stored.
+      uint32_t mbits[2] = {0u, 0u};
+      {
+        if (mask) {
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            const int n = n0 + 32 * cb + 4 * piece, nc = n < p.N ? n : 0;
+            float4 av[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = m0 + 4 * i + sub, mc = m < p.M ? m : p.M - 1;
+              av[i] = __ldg(reinterpret_cast<const float4*>(p.act + (long long)mc * p.ldact + nc));
+            }
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              bits |= ((av[i].x > 0.f ? 1u : 0u) | (av[i].y > 0.f ? 2u : 0u) | (av[i].z > 0.f ? 4u : 0u) | (av[i].w > 0.f ? 8u : 0u)) << (4 * i);
+            mbits[cb] = bits;
+          }
+        }
+      }
       for (int g = 0; g < ngroups; ++g, ++gcount) {
         const int acc = gcount % kParts;
         mbar_wait(&tfull[acc], (uint32_t)((gcount / kParts) & 1));
@@ -897,8 +921,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
             uint4 o = *reinterpret_cast<const uint4*>(stage + R * 32 + 4 * (piece ^ (R & 7)));
             if (m < p.M && n < p.N) {                    // pieces straddling N end in the row's padding (ldc >= round_up(N, 4)): zeros
               if (mask) {
-                const float4 av = __ldg(reinterpret_cast<const float4*>(p.act + (long long)m * p.ldact + n));
-                o.x = av.x > 0.f ? o.x : 0u; o.y = av.y > 0.f ? o.y : 0u; o.z = av.z > 0.f ? o.z : 0u; o.w = av.w > 0.f ? o.w : 0u;
+                const uint32_t mb = mbits[c >> 5] >> (4 * i);
+                o.x = (mb & 1u) ? o.x : 0u; o.y = (mb & 2u) ? o.y : 0u; o.z = (mb & 4u) ? o.z : 0u; o.w = (mb & 8u) ? o.w : 0u;
               } else if (table) {                        // N % 4 == 0 here (g2_eligible): the piece is inside the table row
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)(m % p.bias_period) * p.bias_ld + n));
                 float v0 = __uint_as_float(o.x) + b4.x, v1 = __uint_as_float(o.y) + b4.y, v2 = __uint_as_float(o.z) + b4.z, v3 = __uint_as_float(o.w) + b4.w;
@@ -1070,6 +1094,11 @@ __global__ void __launch_bounds__(kW2Threads, 1) tc_wgrad2_kernel(TcGemmParams p
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int nch = item_chunks(w);
+      // bias gradient for free: this thread sees every dY[m, n] of its output row n; the work items of the first tile column add
+      // their share of db[n] = sum_m dY[m, n] (rows beyond the batch are TMA zero fill)
+      const int t = w % tiles;
+      const bool want_sum = p.rowsum != nullptr && t / tiles_m == 0;
+      float bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
       for (int c = 0; c < nch; ++c, ++it) {
         const int s = it % kG2Stages, b = it % kW2Ring;
         mbar_wait(&landed[s], (uint32_t)((it / kG2Stages) & 1));
@@ -1082,6 +1111,10 @@ __global__ void __launch_bounds__(kW2Threads, 1) tc_wgrad2_kernel(TcGemmParams p
           const uint32_t h = (e + 0x1000u) & 0xffffe000u;
           hi[kk] = h;
           lo[kk] = __float_as_uint(__uint_as_float(e) - __uint_as_float(h)) + 0x1000u;   // the tensor core drops the low bits
+          if ((kk & 3) == 0) bs0 += __uint_as_float(e);
+          else if ((kk & 3) == 1) bs1 += __uint_as_float(e);
+          else if ((kk & 3) == 2) bs2 += __uint_as_float(e);
+          else bs3 += __uint_as_float(e);
         }
         mbar_wait(&a_empty[b], (uint32_t)(((it / kW2Ring) & 1) ^ 1));
         fence_after_sync();
@@ -1093,6 +1126,10 @@ __global__ void __launch_bounds__(kW2Threads, 1) tc_wgrad2_kernel(TcGemmParams p
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[b]);
         if (tid == 256) trace_stamp(p.trace, 2, it);
+      }
+      if (want_sum) {
+        const int n = (t % tiles_m) * kGemmBM + q * 32 + lane;
+        if (n < p.M) atomicAdd(p.rowsum + n, (bs0 + bs1) + (bs2 + bs3));
       }
     }
   } else {
@@ -1236,6 +1273,10 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
     cudaFuncSetAttribute(tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     GNF_LAUNCH(tc_wgrad2_kernel, (int)(total2 < kNumSMs ? total2 : kNumSMs), kW2Threads, smem2, s, p, tmA, tmB);
     return 0;
+  }
+  if (p.rowsum) {      // only the kernel above sums the rows of A on its way: shapes of the first engine take the column-sum kernel (overwrites)
+    if (int e = gnf_colsum(p.A, (int)p.lda, p.rowsum, p.K, p.M, 1, (gnf_stream_t)s)) return e;
+    p.rowsum = nullptr;
   }
   if (g_tc_gemm_v2 && p.use_tma && g2_eligible(p)) {
     // engine v2: BN = 128, A through registers into TMEM (the maps of A and of the pre-split B built above already have the
@@ -1477,6 +1518,31 @@ int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, floa
   p.epi = TCG_EPI_ATOMIC; p.C = dW; p.ldc = lddw;
   if (int e = launch_tc_gemm(p, s)) return e;
   return check_launch("gnf_linear_wgrad_tc");
+#endif
+}
+
+int gnf_linear_wgrad_bias_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K,
+                             gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!dY || !X || !dW || !db || M < 0 || N <= 0 || K <= 0 || lddy < N || ldx < K || lddw < K) return fail(GNF_ERR_INVALID, "gnf_linear_wgrad_bias_tc: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  TcGemmParams p = {};
+  p.A = dY; p.lda = lddy; p.a_src = TCG_SRC_MN;
+  p.B = X; p.ldb = ldx; p.b_src = TCG_SRC_MN;
+  p.M = N; p.N = K; p.K = M; p.passes = 3;
+  p.epi = TCG_EPI_ATOMIC; p.C = dW; p.ldc = lddw;
+  if (M == 0) {
+    if (int e = gnf_colsum(dY, lddy, db, M, N, 1, stream)) return e;
+    return gnf_linear_wgrad_tc(dY, lddy, X, ldx, dW, lddw, M, N, K, 3, stream);
+  }
+  if (lddw == K) cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s);
+  else cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)N, s);
+  cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), s);
+  p.rowsum = db;
+  if (int e = launch_tc_gemm(p, s)) return e;
+  return check_launch("gnf_linear_wgrad_bias_tc");
 #endif
 }
 

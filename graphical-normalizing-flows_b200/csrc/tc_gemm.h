@@ -24,6 +24,7 @@ struct TcGemmParams {
   const float* act; long long ldact;                    // TCG_EPI_MASK: keep dX where act > 0 ...
   const uint32_t* mask_bits; long long mask_ld;         // ... or where bit n of row m is set ([M][mask_ld] words; wins over act)
   uint32_t* bits_out; long long bits_ld;                // TCG_EPI_BIAS_ACT: also emit the bit mask (Y > 0), same layout
+  float* rowsum;                                        // engine v2 wgrad only, nullable: rowsum[m] += sum_k A(m, k) (= the bias gradient, atomics)
   int use_tma, c_vec, act_vec, bias_vec;                          // set by launch_tc_gemm
   long long* trace;                                     // measurement: SM-clock stamps of CTA 0 (gnf_tc_gemm_set_trace)
 };

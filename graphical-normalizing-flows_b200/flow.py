@@ -132,10 +132,14 @@ class FCNormalizingFlow(NormalizingFlow):
         return self.z_log_density(z) + jac, z
 
     def constraintsLoss(self):
-        loss = 0.
+        loss = None
         for step in self.steps:
-            loss += step.constraintsLoss()
-        return loss
+            l = step.constraintsLoss()
+            if torch.is_tensor(l):
+                loss = l if loss is None else loss + l      # no `0. + tensor` launch for the first term
+            elif l != 0.:
+                loss = l if loss is None else loss + l
+        return 0. if loss is None else loss
 
     def DAGness(self):
         dagness = []
@@ -148,11 +152,14 @@ class FCNormalizingFlow(NormalizingFlow):
             step.step(epoch_number, loss_avg)
 
     def loss(self, z, jac):
-        if isinstance(self.z_log_density, NormalLogDensity):
-            log_p_x = ops.NormalLLFn.apply(z.contiguous(), jac.contiguous())     # jac + z_log_density(z), one kernel
-        else:
-            log_p_x = jac + self.z_log_density(z)
-        return self.constraintsLoss() - log_p_x.mean()
+        c = self.constraintsLoss()
+        if isinstance(self.z_log_density, NormalLogDensity) and z.dim() == 2 and z.shape[0] > 0:
+            # constraint - mean(jac + z_log_density(z)) as one kernel per direction
+            tensor_c = torch.is_tensor(c) and c.dim() == 0 and c.dtype == z.dtype and c.device == z.device
+            out = ops.NllLossFn.apply(z.contiguous(), jac.contiguous(), c if tensor_c else None)
+            return out if tensor_c else c + out
+        log_p_x = jac + self.z_log_density(z)
+        return c - log_p_x.mean()
 
     def getNormalizers(self):
         normalizers = []

@@ -176,6 +176,44 @@ class NormalLLFn(torch.autograd.Function):
         return gz, (gout if ctx.has_logdet else None)
 
 
+_NLL_WORK = {}
+
+
+class NllLossFn(torch.autograd.Function):
+    """FCNormalizingFlow.loss (NormalizingFlow.py:144-146) with the standard-normal base density: constraint - mean_b(logdet_b +
+    log N(z_b)) as ONE kernel per direction instead of the density kernel + mean / neg / add (and their autograd nodes).
+    forward(z [B,d], logdet [B], constraint: 0-dim tensor or None) -> 0-dim loss."""
+
+    @staticmethod
+    def forward(ctx, z, logdet, constraint):
+        require(z, "z"), require(logdet, "logdet")
+        B, d = z.shape
+        if constraint is not None:
+            require(constraint, "constraint")
+        key = z.device                 # one persistent buffer per device (made by the eager warm-up steps before any graph capture)
+        n = lib().gnf_nll_loss_work_floats(B)
+        work = _NLL_WORK.get(key)
+        if work is None or work.numel() < n or L._SIMULATOR:
+            work = torch.zeros(max(n, 256), device=z.device, dtype=torch.float32)      # the trailing block counter starts at zero and is left at zero
+            _NLL_WORK[key] = work
+        out = torch.empty((), device=z.device, dtype=z.dtype)
+        _call("gnf_nll_loss_fwd", ptr(z), ptr(logdet), ptr(constraint), ptr(out), ptr(work[work.numel() - n:]), B, d, stream_ptr())
+        _count()
+        ctx.save_for_backward(z)
+        ctx.has_constraint = constraint is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (z,) = ctx.saved_tensors
+        g = _contig(g)
+        gz = torch.empty_like(z)
+        glogdet = torch.empty(z.shape[0], device=z.device, dtype=z.dtype)
+        _call("gnf_nll_loss_bwd", ptr(z), ptr(g), ptr(gz), ptr(glogdet), z.shape[0], z.shape[1], stream_ptr())
+        _count()
+        return gz, glogdet, (g if ctx.has_constraint else None)
+
+
 def reverse_cols(z):
     require(z, "z")
     out = torch.empty_like(z)
@@ -465,6 +503,20 @@ def linear_wgrad(dY, lddy, X, ldx, M, N, K, dy_split=None, x_split=None, out=Non
     return dW
 
 
+def linear_wgrad_bias(dY, lddy, X, ldx, M, N, K):
+    """(dW, db) of one Linear layer; in 3xTF32 the weight-gradient engine takes db from the dY tiles it streams (one launch)."""
+    if _gemm_passes(M, N, K, "wgrad") == 3 and M > 0 and not PRESPLIT_ACTS:
+        dW = torch.empty(N, K, device=dY.device, dtype=dY.dtype)
+        db = torch.empty(N, device=dY.device, dtype=dY.dtype)
+        _note_flops("gnf_linear_wgrad_tc", 2. * M * N * K, (M, N, K))
+        _TIMES_ALIAS["gnf_linear_wgrad_bias_tc"] = "gnf_linear_wgrad_tc"
+        _call("gnf_linear_wgrad_bias_tc", ptr(dY), lddy, ptr(X), ldx, ptr(dW), K, ptr(db), M, N, K, stream_ptr())
+        _count()
+        return dW, db
+    db = colsum(dY, lddy, M, N).view(N)
+    return linear_wgrad(dY, lddy, X, ldx, M, N, K), db
+
+
 def colsum(Y, ldy, M, N, period=1):
     out = torch.empty(period, N, device=Y.device, dtype=Y.dtype)
     _call("gnf_colsum", ptr(Y), ldy, ptr(out), M, N, period, stream_ptr())
@@ -487,6 +539,12 @@ def _mlp_backward(gout, ldg, acts, x_in, ldx, K0, weights, need_dx, first_layer_
         N, K = W.shape
         if l == 0 and first_layer_done:
             break
+        if l > 0 and not PRESPLIT_ACTS:
+            a_prev = acts[l - 1]
+            dWs[l], dbs[l] = linear_wgrad_bias(delta, ldd, a_prev, a_prev.stride(0), M, N, K)
+            delta = linear_dgrad(delta, ldd, W, a_prev, M)
+            ldd = delta.stride(0)
+            continue
         dbs[l] = colsum(delta, ldd, M, N).view(N)
         if l > 0:
             a_prev = acts[l - 1]

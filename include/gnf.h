@@ -67,6 +67,16 @@ int gnf_normal_ll_fwd(const float* z, const float* logdet, float* out, int B, in
 /* gz[b,i] = -z[b,i]*gout[b]. */
 int gnf_normal_ll_bwd(const float* z, const float* gout, float* gz, int B, int d, gnf_stream_t stream);
 
+/* The training loss in one launch (FCNormalizingFlow.loss, NormalizingFlow.py:144-146: constraintsLoss() - log_p_x.mean() with
+ * log_p_x = jac + z_log_density(z)): *out = (constraint ? *constraint : 0) - mean_b ll_b.  work: gnf_nll_loss_work_floats(B) floats,
+ * caller-owned and reusable across calls; its LAST word is a block counter that must be zero before the first call (the kernel
+ * leaves it zero).  Deterministic (block-ordered sum). */
+size_t gnf_nll_loss_work_floats(int B);
+int gnf_nll_loss_fwd(const float* z, const float* logdet, const float* constraint, float* out, float* work, int B, int d,
+                     gnf_stream_t stream);
+/* gz[b,i] = z[b,i] g / B, glogdet[b] = -g / B (nullable); g: device scalar cotangent of the loss (NULL = 1). */
+int gnf_nll_loss_bwd(const float* z, const float* g, float* gz, float* glogdet, int B, int d, gnf_stream_t stream);
+
 /* log(jac).sum(1) for a jac [B,d] produced elsewhere (NormalizingFlow.py:70). */
 int gnf_logdet_fwd(const float* jac, float* logdet, int B, int d, gnf_stream_t stream);
 
@@ -119,6 +129,11 @@ int gnf_linear_dgrad_tc(const float* dY, int lddy, const float* W, int ldw, cons
                         int lddx, int M, int N, int K, int passes, gnf_stream_t stream);
 int gnf_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
                         int passes, gnf_stream_t stream);
+/* Weight AND bias gradient of one nn.Linear in 3xTF32 (autograd of DAGConditioner.py:7-20): dW as gnf_linear_wgrad_tc, and
+ * db[n] = sum_m dY[m, n] taken by the weight-gradient engine from the dY tiles it streams anyway (no separate column-sum pass;
+ * shapes the engine does not take fall back to gnf_colsum + gnf_linear_wgrad_tc inside).  db: [N], overwritten. */
+int gnf_linear_wgrad_bias_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K,
+                             gnf_stream_t stream);
 /* DAGMLP / MADE / CouplingMLP hidden layers (DAGConditioner.py:7-20, AutoregressiveConditioner.py:24-25, CouplingConditioner.py:6-18)
  * in 3xTF32 with the weights split ONCE per call instead of per tile in shared memory: gnf_split_tf32 writes W_hi = rn_tf32(W) and
  * W_lo = rn_tf32(W - W_hi) as [N][ld] (ld a multiple of 4 floats, 16-byte aligned: both are TMA-loaded); the _ps flavours of

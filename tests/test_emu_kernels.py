@@ -96,3 +96,30 @@ def test_skinny_layer_kernels_in_simulator(emu, M_, N, K):
     assert torch.allclose(Y, torch.relu(X @ W.t() + b), rtol=1e-4, atol=1e-5)
     dX = G.ops.linear_dgrad(dY, N, W, X, M_)
     assert torch.allclose(dX, (dY @ W) * (X > 0), rtol=1e-4, atol=1e-5)
+
+
+def _nll_loss_case(device, B, d, with_constraint):
+    g = torch.Generator().manual_seed(B * 131 + d)
+    z = torch.randn(B, d, generator=g).to(device).requires_grad_(True)
+    logdet = torch.randn(B, generator=g).to(device).requires_grad_(True)
+    c = (torch.randn((), generator=g).abs()).to(device).requires_grad_(True) if with_constraint else None
+    out = G.ops.NllLossFn.apply(z, logdet, c)
+    out.backward()
+    z64, l64 = z.detach().double().cpu().requires_grad_(True), logdet.detach().double().cpu().requires_grad_(True)
+    ll = l64 - .5 * (torch.log(torch.tensor(2 * torch.pi, dtype=torch.float64)) + z64 ** 2).sum(1)
+    want = (c.detach().double().cpu() if with_constraint else 0.) - ll.mean()
+    want.backward()
+    assert abs(float(out.detach()) - float(want)) <= 1e-5 * max(1., abs(float(want)))
+    assert torch.allclose(z.grad.cpu().double(), z64.grad, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(logdet.grad.cpu().double(), l64.grad, rtol=1e-6, atol=1e-9)
+    if with_constraint:
+        assert float(c.grad) == 1.
+
+
+@pytest.mark.parametrize("B,d,with_constraint", [(1, 1, False), (100, 63, True), (37, 6, True), (300, 5, False)])
+def test_fused_training_loss_in_simulator(emu, B, d, with_constraint):
+    """gnf_nll_loss_{fwd,bwd} (FCNormalizingFlow.loss with the standard-normal base density, NormalizingFlow.py:144-146) against
+    float64 torch; called twice through the same work buffer (the block counter must be left at zero)."""
+    torch.set_num_threads(1)
+    _nll_loss_case("cpu", B, d, with_constraint)
+    _nll_loss_case("cpu", B, d, with_constraint)

@@ -471,3 +471,39 @@ def test_mnist_and_cifar_factories_build_the_reference_structure():
     assert G.buildMNISTNormalizingFlow([1, 1], G.AffineNormalizer, {}) is None
     c = G.buildCIFAR10NormalizingFlow([1], G.AffineNormalizer, {})
     assert isinstance(c, G.FCNormalizingFlow) and c.steps[0].conditioner.in_size == 3072
+
+
+@pytest.mark.parametrize("B,d,with_constraint", [(1, 1, False), (100, 63, True), (6400, 784, True), (100000, 6, False)])
+def test_fused_training_loss_vs_float64(B, d, with_constraint):
+    """gnf_nll_loss_{fwd,bwd}: constraintsLoss() - mean(jac + log N(z)) (NormalizingFlow.py:144-146) as one kernel per direction,
+    against float64 torch, repeatedly through the same work buffer (self-resetting block counter)."""
+    from test_emu_kernels import _nll_loss_case
+    for _ in range(3):
+        _nll_loss_case("cuda", B, d, with_constraint)
+
+
+@pytest.mark.parametrize("M_,N,K", [(6300, 632, 632), (2100, 300, 260), (5000, 1024, 520), (3000, 30, 630), (100, 64, 64)])
+def test_weight_and_bias_gradient_in_one_launch(M_, N, K):
+    """gnf_linear_wgrad_bias_tc: the weight-gradient engine sums the dY columns it streams (db); shapes it does not take fall back
+    to the column-sum kernel inside the call.  Against float64."""
+    g = torch.Generator().manual_seed(M_ + N)
+    dY = _rows_pad(torch.randn(M_, N, generator=g).cuda())
+    X = _rows_pad(torch.randn(M_, K, generator=g).cuda())
+    G.ops.set_gemm_mode("tf32x3")
+    try:
+        for _ in range(2):
+            dW, db = G.ops.linear_wgrad_bias(dY, dY.stride(0), X, X.stride(0), M_, N, K)
+    finally:
+        G.ops.set_gemm_mode("ffma")
+    dY64, X64 = dY[:, :N].double(), X[:, :K].double()
+    assert float((dW.double() - dY64.t() @ X64).norm() / (dY64.t() @ X64).norm()) < 2e-6
+    want = dY64.sum(0)
+    assert float((db.double() - want).abs().max()) < 1e-5 * float(dY64.abs().sum(0).max())
+
+
+def _rows_pad(t):
+    """[M, N] view of a buffer whose rows are padded to a multiple of 4 floats (what the engine's TMA maps need)."""
+    M_, N = t.shape
+    buf = torch.zeros(M_, (N + 3) // 4 * 4, device=t.device, dtype=t.dtype)
+    buf[:, :N] = t
+    return buf
