@@ -376,6 +376,10 @@ def main():
             G.ops.enable_kernel_timing(True)
             n_eager = min(steps, 10)
             for i in range(n_eager):
+                # keep the launch queue full: a spin kernel (~4 ms) ahead of the step lets the host enqueue every launch of the step
+                # before the first one starts, so that an event pair brackets its kernel(s) and not the host's launch gaps
+                # (idle-queue pairs read 10-14 us for a 3-us kernel)
+                torch.cuda._sleep(8_000_000)
                 step(pool[i % n_pool])
             eager_ktimes = G.ops.collect_kernel_timing()
             eager_kflops = G.ops.collect_call_flops()

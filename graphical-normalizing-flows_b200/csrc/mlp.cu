@@ -157,7 +157,13 @@ constexpr int kDagLDK = kDagKP + 4;
 constexpr int kDagFwdWPer = kDagFwdBN * kDagKP / kDagFwdThreads;       // 32 prefetch registers
 constexpr size_t kDagFwdSmem = (size_t)(kDagFwdBM + kDagFwdBN) * kDagLDK * sizeof(float);
 
-__global__ void __launch_bounds__(kDagFwdThreads, 2) dag_l1_fwd_kernel(GateCtx g, const float* __restrict__ W1, int ldw, const float* __restrict__ T,
+// Training with a stochastic gate (round 2): the forward also leaves e, de/dx and de/dP as [M][kDagKP] planes (3 x 1.6 MB at cfg4)
+// and the two backward kernels read them instead of drawing and evaluating every gate again -- the gate math (Philox4x32-10 + six
+// transcendentals + divisions, ~300 instructions) was most of each of the three kernels (see above), now it runs once per step.
+struct GatePlanes { float* E; float* DX; float* DP; };
+
+template <bool kSave>
+__global__ void __launch_bounds__(kDagFwdThreads, 2) dag_l1_fwd_kernel(GateCtx g, GatePlanes sv, const float* __restrict__ W1, int ldw, const float* __restrict__ T,
                                                                     int bias_ld, int period, int relu, float* __restrict__ Y, int ldy, int M, int N) {
   GNF_SMEM(float, smem);
   float* Es = smem;                              // [BM][LDK]   Es[m][j]
@@ -181,7 +187,15 @@ __global__ void __launch_bounds__(kDagFwdThreads, 2) dag_l1_fwd_kernel(GateCtx g
   for (int idx = t; idx < kDagFwdBM * kDagKP; idx += kDagFwdThreads) {
     const int j = idx % kDagKP, mm = idx / kDagKP, m = m0 + mm;
     float v = 0.f;
-    if (m < M && j < d) v = gate_e<false, true>(g, m / d, m % d, j, nullptr, nullptr);
+    if (kSave) {
+      float ddx = 0.f, ddp = 0.f;
+      if (m < M && j < d) v = gate_e<true, true>(g, m / d, m % d, j, &ddx, &ddp);
+      if (m < M) {
+        sv.E[(size_t)m * kDagKP + j] = v;
+        sv.DX[(size_t)m * kDagKP + j] = ddx;
+        sv.DP[(size_t)m * kDagKP + j] = ddp;
+      }
+    } else if (m < M && j < d) v = gate_e<false, true>(g, m / d, m % d, j, nullptr, nullptr);
     Es[mm * kDagLDK + j] = v;
   }
   const int tx = t % 32, ty = t / 32;            // lane = column residue, warp = group of 4 rows
@@ -248,6 +262,7 @@ constexpr int kDagWgLDN = kDagWgBN + 4;
 constexpr int kDagWgPer = kDagWgBK * kDagWgBN / kDagWgThreads;         // 32 prefetch registers
 constexpr size_t kDagWgSmem = (size_t)kDagWgBK * (kDagLDK + kDagWgLDN) * sizeof(float);
 
+template <bool kSaved>     // kSaved: e comes from the forward's plane (g.x = the plane, [M][kDagKP])
 __global__ void __launch_bounds__(kDagWgThreads, 2) dag_l1_wgrad_kernel(GateCtx g, const float* __restrict__ dY, int lddy, EpiAtomicAdd epi, int M, int N) {
   GNF_SMEM(float, smem);
   float* Em = smem;                              // [BK][LDK]   Em[m][j]
@@ -272,7 +287,8 @@ __global__ void __launch_bounds__(kDagWgThreads, 2) dag_l1_wgrad_kernel(GateCtx 
   for (int idx = t; idx < kDagWgBK * kDagKP; idx += kDagWgThreads) {   // four independent gate chains in flight (see the forward)
     const int j = idx % kDagKP, mm = idx / kDagKP, m = m0 + mm;
     float v = 0.f;
-    if (m < M && j < d) v = gate_e<false, true>(g, m / d, m % d, j, nullptr, nullptr);
+    if (kSaved) { if (m < M) v = __ldg(g.x + (size_t)m * kDagKP + j); }
+    else if (m < M && j < d) v = gate_e<false, true>(g, m / d, m % d, j, nullptr, nullptr);
     Em[mm * kDagLDK + j] = v;
   }
   const int tx = t % 16, ty = t / 16;            // 16 j quads x 16 groups of 8 output rows n
@@ -322,6 +338,7 @@ constexpr int kDagDgLDA = kDagDgBK + 4;
 constexpr int kDagDgAPer = kDagDgBM * kDagDgBK / kDagDgThreads, kDagDgBPer = kDagDgBK * kDagKP / kDagDgThreads;   // 8 + 16
 constexpr size_t kDagDgSmem = (size_t)(kDagDgBM * kDagDgLDA + kDagDgBK * kDagLDK) * sizeof(float);
 
+template <bool kSaved>     // kSaved: de/dx and de/dP come from the forward's planes (g.x = DX, g.P = DP, both [M][kDagKP])
 __global__ void __launch_bounds__(kDagDgThreads, 4) dag_l1_dgrad_kernel(GateCtx g, const float* __restrict__ dY, int lddy, const float* __restrict__ W1, int ldw,
                                                                      float* __restrict__ dx, float* __restrict__ dP, int M, int N) {
   GNF_SMEM(float, smem);
@@ -397,10 +414,17 @@ __global__ void __launch_bounds__(kDagDgThreads, 4) dag_l1_dgrad_kernel(GateCtx 
       float av[4], ddx[4], ddp[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) av[jj] = i == 0 ? acc[0][jj] : (i == 1 ? acc[1][jj] : (i == 2 ? acc[2][jj] : acc[3][jj]));
+      if (kSaved) {
+        const float4 vx = __ldg(reinterpret_cast<const float4*>(g.x + (size_t)m * kDagKP + j));
+        const float4 vp = __ldg(reinterpret_cast<const float4*>(g.P + (size_t)m * kDagKP + j));
+        ddx[0] = vx.x; ddx[1] = vx.y; ddx[2] = vx.z; ddx[3] = vx.w;
+        ddp[0] = vp.x; ddp[1] = vp.y; ddp[2] = vp.z; ddp[3] = vp.w;
+      } else {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        ddx[jj] = ddp[jj] = 0.f;
-        if (j + jj < d) gate_e<true, true>(g, b, iv, j + jj, &ddx[jj], &ddp[jj]);
+        for (int jj = 0; jj < 4; ++jj) {
+          ddx[jj] = ddp[jj] = 0.f;
+          if (j + jj < d) gate_e<true, true>(g, b, iv, j + jj, &ddx[jj], &ddp[jj]);
+        }
       }
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -809,7 +833,8 @@ int gnf_dag_l1_fwd(const float* x, const float* P, const gnf_gate_t* gate, const
   EpiBiasAct epi{Y, ldy, T, N, bias_period < 1 ? 1 : bias_period, relu};
   const int M = B * d;
   if (d <= kDagMaxD && g_dag_l1_resident) {
-    GNF_LAUNCH(dag_l1_fwd_kernel, ceil_div(M, kDagFwdBM), kDagFwdThreads, kDagFwdSmem, s, g, W1, ldw, T, N, bias_period < 1 ? 1 : bias_period, relu, Y, ldy, M, N);
+    GNF_LAUNCH(dag_l1_fwd_kernel<false>, ceil_div(M, kDagFwdBM), kDagFwdThreads, kDagFwdSmem, s, g, GatePlanes{nullptr, nullptr, nullptr}, W1, ldw, T, N,
+               bias_period < 1 ? 1 : bias_period, relu, Y, ldy, M, N);
     return check_launch("gnf_dag_l1_fwd");
   }
   if (d >= kGateInlineMinD) launch_gemm_auto(LoadDagA<true>{g}, bl, epi, M, N, d, false, s);
@@ -830,9 +855,9 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
   EpiAtomicAdd epi{dW1, ldw};
   if (d <= kDagMaxD && g_dag_l1_resident) {
 #ifndef GNF_EMU
-    cudaFuncSetAttribute(dag_l1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDagWgSmem);   // per device: set per launch
+    cudaFuncSetAttribute(dag_l1_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDagWgSmem);   // per device: set per launch
 #endif
-    GNF_LAUNCH(dag_l1_wgrad_kernel, ceil_div(M, kDagWgBK), kDagWgThreads, kDagWgSmem, s, g, dY, lddy, epi, M, N);
+    GNF_LAUNCH(dag_l1_wgrad_kernel<false>, ceil_div(M, kDagWgBK), kDagWgThreads, kDagWgSmem, s, g, dY, lddy, epi, M, N);
     return check_launch("gnf_dag_l1_wgrad");
   }
   if (d >= kGateInlineMinD) launch_gemm_auto(al, LoadDagB<true>{g}, epi, N, d, M, true, s);    // B(m, j) = e[m, j]
@@ -853,7 +878,7 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   LoadRowMajorA al{dY, lddy};   // A(m, n)
   LoadRowMajorB bl{W1, ldw};    // B(n, j) = W1[n, j]
   if (d <= kDagMaxD && g_dag_l1_resident) {
-    GNF_LAUNCH(dag_l1_dgrad_kernel, ceil_div(M, kDagDgBM), kDagDgThreads, kDagDgSmem, s, g, dY, lddy, W1, ldw, dx, dP, M, N);
+    GNF_LAUNCH(dag_l1_dgrad_kernel<false>, ceil_div(M, kDagDgBM), kDagDgThreads, kDagDgSmem, s, g, dY, lddy, W1, ldw, dx, dP, M, N);
     return check_launch("gnf_dag_l1_dgrad");
   }
   // wide flows: N = d gives few tile columns: split the reduction over the layer width.  The epilogue is
@@ -861,6 +886,119 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   if (d >= kGateInlineMinD) launch_gemm_auto(al, bl, EpiDagDgrad<true>{g, dx, dP}, M, d, N, true, s);
   else launch_gemm_auto(al, bl, EpiDagDgrad<false>{g, dx, dP}, M, d, N, true, s);
   return check_launch("gnf_dag_l1_dgrad");
+}
+
+// dx[b, j] = sum_i dE[(b,i), j] DX[(b,i), j]  (owned by the CTA of batch entry b),  dP[i, j] += sum_b dE[(b,i), j] DP[(b,i), j]  (atomics;
+// every CTA sums kNarrowRedB batch entries in registers first).  Planes [B d][64]; thread = (j quad, i residue mod 16).  grid = ceil(B / kNarrowRedB).
+constexpr int kNarrowRedB = 2;
+__global__ void __launch_bounds__(256) dag_l1_reduce_narrow_kernel(const float* __restrict__ dE, const float* __restrict__ DX, const float* __restrict__ DP,
+                                                                   float* __restrict__ dx, float* __restrict__ dP, int B, int d) {
+  GNF_SMEM(float, red);                           // [16 i residues][64 j]
+  const int jq = threadIdx.x & 15, ig = threadIdx.x >> 4, j = jq * 4;
+  const int b0 = blockIdx.x * kNarrowRedB;
+  float4 accp[4];                                 // dP partial sums of rows i = ig + 16 r (d <= 64: r < 4)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) accp[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int bb = 0; bb < kNarrowRedB; ++bb) {
+    const int b = b0 + bb;
+    float4 sx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < B) {
+      float4 e[4], vx[4], vp[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {               // unconditional loads from clamped rows, masked at use
+        const int i = ig + 16 * r, ic = i < d ? i : d - 1;
+        const size_t o = ((size_t)b * d + ic) * kDagKP + j;
+        e[r] = __ldg(reinterpret_cast<const float4*>(dE + o));
+        vx[r] = __ldg(reinterpret_cast<const float4*>(DX + o));
+        vp[r] = __ldg(reinterpret_cast<const float4*>(DP + o));
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (ig + 16 * r < d) {
+          sx.x = fmaf(e[r].x, vx[r].x, sx.x); sx.y = fmaf(e[r].y, vx[r].y, sx.y); sx.z = fmaf(e[r].z, vx[r].z, sx.z); sx.w = fmaf(e[r].w, vx[r].w, sx.w);
+          accp[r].x = fmaf(e[r].x, vp[r].x, accp[r].x); accp[r].y = fmaf(e[r].y, vp[r].y, accp[r].y);
+          accp[r].z = fmaf(e[r].z, vp[r].z, accp[r].z); accp[r].w = fmaf(e[r].w, vp[r].w, accp[r].w);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(red + ig * kDagKP + j) = sx;
+    __syncthreads();
+    if (threadIdx.x < kDagKP && b < B && (int)threadIdx.x < d) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) t += red[g * kDagKP + threadIdx.x];
+      dx[(size_t)b * d + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = ig + 16 * r;
+    if (i < d) {
+      float* dst = dP + (size_t)i * d + j;
+      if (j < d) atomicAdd(dst, accp[r].x);
+      if (j + 1 < d) atomicAdd(dst + 1, accp[r].y);
+      if (j + 2 < d) atomicAdd(dst + 2, accp[r].z);
+      if (j + 3 < d) atomicAdd(dst + 3, accp[r].w);
+    }
+  }
+}
+
+// Narrow flows (d <= GNF_DAG_L1_MAX_D), training: the forward keeps the gate planes, the backward kernels read them
+int gnf_dag_l1_fwd_save(const float* x, const float* P, const gnf_gate_t* gate, const float* W1, int ldw, const float* T, int bias_period,
+                        float* Y, int ldy, float* E, float* DX, float* DP, int B, int d, int N, int relu, gnf_stream_t stream) {
+  if (!x || !P || !W1 || !Y || !E || !DX || !DP || B < 0 || d <= 0 || N <= 0 || ldw < d || ldy < N) return fail(GNF_ERR_INVALID, "gnf_dag_l1_fwd_save: bad arguments");
+  if (d > kDagMaxD) return fail(GNF_ERR_UNSUPPORTED, "gnf_dag_l1_fwd_save: d <= 64 only (wide flows: gnf_dag_embed_fwd + the GEMM engine)");
+  if (((reinterpret_cast<uintptr_t>(DX) | reinterpret_cast<uintptr_t>(DP)) & 15) != 0) return fail(GNF_ERR_INVALID, "gnf_dag_l1_fwd_save: planes must be 16-byte aligned");
+  GateCtx g;
+  if (int e = make_gate(&g, x, P, gate, d)) return e;
+  if (B == 0) return 0;
+  const int M = B * d;
+  GNF_LAUNCH(dag_l1_fwd_kernel<true>, ceil_div(M, kDagFwdBM), kDagFwdThreads, kDagFwdSmem, (cudaStream_t)stream, g, GatePlanes{E, DX, DP}, W1, ldw, T, N,
+             bias_period < 1 ? 1 : bias_period, relu, Y, ldy, M, N);
+  return check_launch("gnf_dag_l1_fwd_save");
+}
+
+int gnf_dag_l1_wgrad_saved(const float* dY, int lddy, const float* E, float* dW1, int ldw, int B, int d, int N, gnf_stream_t stream) {
+  if (!dY || !E || !dW1 || B < 0 || d <= 0 || d > kDagMaxD || N <= 0 || ldw < d || lddy < N) return fail(GNF_ERR_INVALID, "gnf_dag_l1_wgrad_saved: bad arguments (d <= 64)");
+  cudaStream_t s = (cudaStream_t)stream;
+  zero2d(dW1, ldw, N, d, s);
+  if (B == 0) return check_launch("gnf_dag_l1_wgrad_saved");
+  GateCtx g = {};
+  g.x = E; g.d = d;
+  const int M = B * d;
+#ifndef GNF_EMU
+  cudaFuncSetAttribute(dag_l1_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDagWgSmem);
+#endif
+  GNF_LAUNCH(dag_l1_wgrad_kernel<true>, ceil_div(M, kDagWgBK), kDagWgThreads, kDagWgSmem, s, g, dY, lddy, EpiAtomicAdd{dW1, ldw}, M, N);
+  return check_launch("gnf_dag_l1_wgrad_saved");
+}
+
+int gnf_dag_l1_dgrad_saved(const float* dY, int lddy, const float* W1, int ldw, const float* DX, const float* DP, float* dx, float* dP,
+                           int B, int d, int N, gnf_stream_t stream) {
+  if (!dY || !W1 || !DX || !DP || !dx || !dP || B < 0 || d <= 0 || d > kDagMaxD || N <= 0 || ldw < d || lddy < N ||
+      ((reinterpret_cast<uintptr_t>(DX) | reinterpret_cast<uintptr_t>(DP)) & 15) != 0)
+    return fail(GNF_ERR_INVALID, "gnf_dag_l1_dgrad_saved: bad arguments (d <= 64, 16-byte aligned planes)");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(dx, 0, (size_t)B * d * sizeof(float), s);
+  cudaMemsetAsync(dP, 0, (size_t)d * d * sizeof(float), s);
+  if (B == 0) return check_launch("gnf_dag_l1_dgrad_saved");
+  GateCtx g = {};
+  g.x = DX; g.P = DP; g.d = d;
+  const int M = B * d;
+  GNF_LAUNCH(dag_l1_dgrad_kernel<true>, ceil_div(M, kDagDgBM), kDagDgThreads, kDagDgSmem, s, g, dY, lddy, W1, ldw, dx, dP, M, N);
+  return check_launch("gnf_dag_l1_dgrad_saved");
+}
+
+int gnf_dag_l1_reduce_saved(const float* dE, const float* DX, const float* DP, float* dx, float* dP, int B, int d, gnf_stream_t stream) {
+  if (!dE || !DX || !DP || !dx || !dP || B < 0 || d <= 0 || d > kDagMaxD ||
+      ((reinterpret_cast<uintptr_t>(dE) | reinterpret_cast<uintptr_t>(DX) | reinterpret_cast<uintptr_t>(DP)) & 15) != 0)
+    return fail(GNF_ERR_INVALID, "gnf_dag_l1_reduce_saved: bad arguments (d <= 64, 16-byte aligned [B d, 64] planes)");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(dP, 0, (size_t)d * d * sizeof(float), s);
+  if (B == 0) return check_launch("gnf_dag_l1_reduce_saved");
+  GNF_LAUNCH(dag_l1_reduce_narrow_kernel, ceil_div(B, kNarrowRedB), 256, 16 * kDagKP * sizeof(float), s, dE, DX, DP, dx, dP, B, d);
+  return check_launch("gnf_dag_l1_reduce_saved");
 }
 
 int gnf_dag_embed_fwd(const float* x, const float* P, const gnf_gate_t* gate, float* E, float* DX, float* DP, int lde, int B, int d,

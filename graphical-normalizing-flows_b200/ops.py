@@ -706,6 +706,21 @@ DAG_L1_PLANE_MIN_D = 65
 DAG_L1_PLANE_KEEP_DERIVATIVES = True      # training keeps the de/dx and de/dP planes (2 x 246 MB at cfg5) instead of regenerating the gates
 
 
+# Narrow DAG flows (d <= 64) with a stochastic gate, training: the forward kernel also leaves e, de/dx and de/dP as [B d, 64] planes
+# and the two backward kernels read them instead of drawing and evaluating every gate again (the gate math was most of each kernel)
+DAG_L1_KEEP_GATES = True
+
+
+def _narrow_l1_tc(M, N1, delta):
+    """Backward GEMMs of a narrow flow's layer 1 against the saved planes on the tensor-core engine (3xTF32)?  cfg4 (6300 x 630 x 64):
+    weight gradient 42 -> 23 us, input cotangent 49 -> 26 + 5 us (profiles/r02ag_*)."""
+    return (DAG_L1_NARROW_TC and _GEMM_MODE in ("auto", "tf32x3") and not L._SIMULATOR and M >= 2048 and N1 >= 128
+            and _tma_ok(delta, delta.stride(0)))
+
+
+DAG_L1_NARROW_TC = True
+
+
 def _dag_l1_plane(M, N1, d, direction):
     """direction 'fwd' / 'bwd'; DAG_L1_PLANE may also be the string 'fwd' or 'bwd' (measurement: one direction only)."""
     on = DAG_L1_PLANE is True or DAG_L1_PLANE == direction
@@ -743,7 +758,7 @@ class DagMlpFn(torch.autograd.Function):
         _call("gnf_dag_bias_table", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st)
         g = gate.c_struct()
         y = _rows(B * d, N1, x) if n > 1 else torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
-        E = W1e = None
+        E = W1e = narrow = None
         gate_planes = (None, None)
         if _dag_l1_plane(B * d, N1, d, "fwd"):
             E = _rows(B * d, d, x)
@@ -753,6 +768,13 @@ class DagMlpFn(torch.autograd.Function):
             W1e = weights[0][:, :d]                 # the masked-input half of layer 1; the one-hot half is the bias table T
             linear_fwd(E, W1e, T, relu=(n > 1), bias_period=(d if hot else 1), out=y, ldy=y.stride(0), K=d, ldx=E.stride(0))
             _count(2)
+        elif (DAG_L1_KEEP_GATES and d <= 64 and gate.mode != L.GATE_TABLE and B > 0 and any(ctx.needs_input_grad)):
+            # narrow flow, stochastic gate, training: the forward leaves e, de/dx, de/dP ([B d, 64] each) for the two backward kernels
+            narrow = tuple(torch.empty(B * d, 64, device=x.device, dtype=x.dtype) for _ in range(3))
+            _TIMES_ALIAS["gnf_dag_l1_fwd_save"] = "gnf_dag_l1_fwd"
+            _call("gnf_dag_l1_fwd_save", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
+                  ptr(y), y.stride(0), ptr(narrow[0]), ptr(narrow[1]), ptr(narrow[2]), B, d, N1, int(n > 1), st)
+            _count(3)
         else:
             _call("gnf_dag_l1_fwd", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
                                        ptr(y), y.stride(0), B, d, N1, int(n > 1), st)
@@ -769,6 +791,7 @@ class DagMlpFn(torch.autograd.Function):
         ctx.act_splits = splits if any(ctx.needs_input_grad) else None
         ctx.E, ctx.W1e = (E, W1e) if any(ctx.needs_input_grad) else (None, None)
         ctx.gate_planes = gate_planes
+        ctx.narrow = narrow
         ctx.save_for_backward(x, A, P, dPdA, *weights, *acts)
         ctx.gate, ctx.hot, ctx.n = gate, hot, n
         if n == 1:
@@ -803,8 +826,17 @@ class DagMlpFn(torch.autograd.Function):
             E = _rows(M, d, x)
             _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), None, None, E.stride(0), B, d, st)
             W1e = W1[:, :d]
+        narrow, ctx.narrow = ctx.narrow, None
         if E is not None:
             linear_wgrad(delta, delta.stride(0), E, E.stride(0), M, N1, d, out=dW1, lddw=dW1.stride(0))
+        elif narrow is not None and _narrow_l1_tc(M, N1, delta):
+            # dW1[:, :d] = delta^T E on the tensor-core engine (3xTF32) against the saved plane
+            _TIMES_ALIAS["gnf_linear_wgrad_tc"] = "gnf_dag_l1_wgrad"
+            _call("gnf_linear_wgrad_tc", ptr(delta), delta.stride(0), ptr(narrow[0]), 64, ptr(dW1), W1.stride(0), M, N1, d, 3, st)
+            _TIMES_ALIAS.pop("gnf_linear_wgrad_tc")
+        elif narrow is not None:
+            _TIMES_ALIAS["gnf_dag_l1_wgrad_saved"] = "gnf_dag_l1_wgrad"
+            _call("gnf_dag_l1_wgrad_saved", ptr(delta), delta.stride(0), ptr(narrow[0]), ptr(dW1), W1.stride(0), B, d, N1, st)
         else:
             _call("gnf_dag_l1_wgrad", ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st)
         dT = colsum(delta, delta.stride(0), M, N1, period=(d if hot else 1))
@@ -820,6 +852,20 @@ class DagMlpFn(torch.autograd.Function):
                 dE = linear_dgrad(delta, delta.stride(0), W1e, None, M)
                 _call("gnf_dag_embed_bwd", ptr(dE), dE.stride(0), ptr(x), ptr(P), C.byref(g), ptr(DXp), ptr(DPp), ptr(dx), ptr(dP), B, d, st)
                 del dE, DXp, DPp
+            elif narrow is not None and _narrow_l1_tc(M, N1, delta):
+                # ebar = delta W1[:, :d] on the tensor-core engine, then the two reductions against the saved derivative planes
+                hi, lo = _split_weight(W1[:, :d])
+                dE = torch.empty(M, 64, device=x.device, dtype=x.dtype)
+                _TIMES_ALIAS["gnf_linear_dgrad_tc_ps"] = "gnf_dag_l1_dgrad"
+                _call("gnf_linear_dgrad_tc_ps", ptr(delta), delta.stride(0), ptr(hi), ptr(lo), hi.stride(0), None, 0, ptr(dE), 64, M, N1, d, st)
+                _TIMES_ALIAS["gnf_linear_dgrad_tc_ps"] = "gnf_linear_dgrad_tc"
+                _TIMES_ALIAS["gnf_dag_l1_reduce_saved"] = "gnf_dag_l1_dgrad"
+                _call("gnf_dag_l1_reduce_saved", ptr(dE), ptr(narrow[1]), ptr(narrow[2]), ptr(dx), ptr(dP), B, d, st)
+                _count(2)
+            elif narrow is not None:
+                _TIMES_ALIAS["gnf_dag_l1_dgrad_saved"] = "gnf_dag_l1_dgrad"
+                _call("gnf_dag_l1_dgrad_saved", ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(narrow[1]), ptr(narrow[2]), ptr(dx),
+                      ptr(dP), B, d, N1, st)
             else:
                 _call("gnf_dag_l1_dgrad", ptr(delta), delta.stride(0), ptr(W1), W1.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dx),
                                              ptr(dP), B, d, N1, st)

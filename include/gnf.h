@@ -211,6 +211,19 @@ int gnf_dag_l1_wgrad(const float* dY, int lddy, const float* x, const float* P, 
  * dx [B,d] and dP [d,d] are zero-filled by the call. */
 int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const float* x, const float* P,
                      const gnf_gate_t* gate, float* dx, float* dP, int B, int d, int N, gnf_stream_t stream);
+/* Narrow flows (d <= 64), training with a stochastic gate: gnf_dag_l1_fwd that also leaves e[b,i,j], de/dx and de/dP as planes
+ * E / DX / DP ([B*d, 64] floats each, 16-byte aligned, columns >= d zero), and the two backward entry points that read them instead
+ * of drawing and evaluating every gate again (autograd of DAGConditioner.py:94-169; same results as the regenerating flavours:
+ * the planes hold exactly the values those would recompute). */
+int gnf_dag_l1_fwd_save(const float* x, const float* P, const gnf_gate_t* gate, const float* W1, int ldw, const float* T,
+                        int bias_period, float* Y, int ldy, float* E, float* DX, float* DP, int B, int d, int N, int relu,
+                        gnf_stream_t stream);
+int gnf_dag_l1_wgrad_saved(const float* dY, int lddy, const float* E, float* dW1, int ldw, int B, int d, int N, gnf_stream_t stream);
+int gnf_dag_l1_dgrad_saved(const float* dY, int lddy, const float* W1, int ldw, const float* DX, const float* DP, float* dx,
+                           float* dP, int B, int d, int N, gnf_stream_t stream);
+/* ... or, with the input-cotangent GEMM dE = dY W1[:, :d] run elsewhere (gnf_linear_dgrad_tc into a [B*d, 64] plane whose columns
+ * >= d are zero or finite), only the reductions: dx[b,j] = sum_i dE DX (overwritten), dP[i,j] = sum_b dE DP (zero-filled, atomics). */
+int gnf_dag_l1_reduce_saved(const float* dE, const float* DX, const float* DP, float* dx, float* dP, int B, int d, gnf_stream_t stream);
 /* Wide flows on the tensor-core GEMM engine (d > 64, cfg5): the masked embedding of DAGConditioner.forward
  * (DAGConditioner.py:126-153: x.unsqueeze(1).expand(-1,d,-1) * gate) written once as a plane
  *   E[b*d+i, j] = x[b,j] G[b,i,j]   ([B*d, lde], lde % 4 == 0, padding columns zero)

@@ -123,3 +123,25 @@ def test_fused_training_loss_in_simulator(emu, B, d, with_constraint):
     torch.set_num_threads(1)
     _nll_loss_case("cpu", B, d, with_constraint)
     _nll_loss_case("cpu", B, d, with_constraint)
+
+
+def _narrow_reduce_case(device, B, d):
+    import ctypes as C
+    from gnf_b200.ops import _call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(B * 7 + d)
+    dE, DX, DP = (torch.randn(B * d, 64, generator=g).to(device) for _ in range(3))
+    DX[:, d:] = 0
+    DP[:, d:] = 0
+    dx = torch.full((B, d), float("nan"), device=device)
+    dP = torch.full((d, d), float("nan"), device=device)
+    _call("gnf_dag_l1_reduce_saved", ptr(dE), ptr(DX), ptr(DP), ptr(dx), ptr(dP), B, d, stream_ptr())
+    e, vx, vp = (t.double().cpu().view(B, d, 64)[:, :, :d] for t in (dE, DX, DP))
+    assert torch.allclose(dx.double().cpu(), (e * vx).sum(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(dP.double().cpu(), (e * vp).sum(0), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,d", [(1, 1), (5, 6), (7, 63), (4, 64)])
+def test_narrow_layer1_plane_reduction_in_simulator(emu, B, d):
+    """gnf_dag_l1_reduce_saved: dx[b,j] = sum_i dE de/dx, dP[i,j] = sum_b dE de/dP over the planes the training forward kept."""
+    torch.set_num_threads(1)
+    _narrow_reduce_case("cpu", B, d)

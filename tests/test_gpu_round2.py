@@ -507,3 +507,36 @@ def _rows_pad(t):
     buf = torch.zeros(M_, (N + 3) // 4 * 4, device=t.device, dtype=t.dtype)
     buf[:, :N] = t
     return buf
+
+
+@pytest.mark.parametrize("B,d", [(1, 1), (100, 63), (101, 64), (1000, 21)])
+def test_narrow_layer1_plane_reduction(B, d):
+    from test_emu_kernels import _narrow_reduce_case
+    _narrow_reduce_case("cuda", B, d)
+
+
+def test_narrow_layer1_backward_on_tensor_cores_matches_resident_kernels():
+    """cfg4-shaped DAG conditioner, stochastic gate: the backward through the saved gate planes on the tensor-core engine
+    (gnf_linear_wgrad_tc / gnf_linear_dgrad_tc_ps + gnf_dag_l1_reduce_saved) against the FFMA kernels that regenerate every gate."""
+    torch.manual_seed(3)
+    cond = G.DAGConditioner(63, [630, 630], 30, gumble_T=.5, hot_encoding=True, l1=0.).cuda()
+    x = torch.randn(100, 63, device="cuda", requires_grad=True)
+    w = torch.randn(100, 63, 30, device="cuda")
+    grads = {}
+    from gnf_b200.conditioners import _stack_params
+    gate = cond._gate_spec(x)            # one Philox (seed, offset) for the three variants
+    for tag, keep, tc, mode in (("regen", False, False, "auto"), ("saved", True, False, "auto"), ("tc", True, True, "auto")):   # same forward in all three
+        G.ops.DAG_L1_KEEP_GATES, G.ops.DAG_L1_NARROW_TC = keep, tc
+        G.ops.set_gemm_mode(mode)
+        try:
+            cond.zero_grad()
+            x.grad = None
+            h = G.ops.DagMlpFn.apply(x, cond.A, gate, True, *_stack_params(cond.embedding_net.net))
+            (h * w).sum().backward()
+            grads[tag] = [x.grad.clone(), cond.A.grad.clone()] + [p.grad.clone() for p in cond.embedding_net.parameters()]
+        finally:
+            G.ops.DAG_L1_KEEP_GATES = G.ops.DAG_L1_NARROW_TC = True
+            G.ops.set_gemm_mode("ffma")
+    for tag in ("saved", "tc"):
+        for a, b in zip(grads["regen"], grads[tag]):
+            assert float((a - b).norm() / b.norm()) < (2e-6 if tag == "saved" else 2e-5), tag
