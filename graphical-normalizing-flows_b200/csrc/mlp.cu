@@ -888,6 +888,20 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
   return check_launch("gnf_dag_l1_dgrad");
 }
 
+// The three planes alone (layer 1's forward GEMM then runs on the tensor-core engine against E): one gate per thread, grid-stride.
+__global__ void __launch_bounds__(256) dag_gate_planes_kernel(GateCtx g, GatePlanes sv, int M) {
+  const int d = g.d;
+  const size_t total = (size_t)M * kDagKP;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % kDagKP), m = (int)(idx / kDagKP);
+    float v = 0.f, ddx = 0.f, ddp = 0.f;
+    if (j < d) v = gate_e<true, true>(g, m / d, m % d, j, &ddx, &ddp);
+    sv.E[idx] = v;
+    sv.DX[idx] = ddx;
+    sv.DP[idx] = ddp;
+  }
+}
+
 // dx[b, j] = sum_i dE[(b,i), j] DX[(b,i), j]  (owned by the CTA of batch entry b),  dP[i, j] += sum_b dE[(b,i), j] DP[(b,i), j]  (atomics;
 // every CTA sums kNarrowRedB batch entries in registers first).  Planes [B d][64]; thread = (j quad, i residue mod 16).  grid = ceil(B / kNarrowRedB).
 constexpr int kNarrowRedB = 2;
@@ -957,6 +971,16 @@ int gnf_dag_l1_fwd_save(const float* x, const float* P, const gnf_gate_t* gate, 
   GNF_LAUNCH(dag_l1_fwd_kernel<true>, ceil_div(M, kDagFwdBM), kDagFwdThreads, kDagFwdSmem, (cudaStream_t)stream, g, GatePlanes{E, DX, DP}, W1, ldw, T, N,
              bias_period < 1 ? 1 : bias_period, relu, Y, ldy, M, N);
   return check_launch("gnf_dag_l1_fwd_save");
+}
+
+int gnf_dag_gate_planes(const float* x, const float* P, const gnf_gate_t* gate, float* E, float* DX, float* DP, int B, int d, gnf_stream_t stream) {
+  if (!x || !P || !E || !DX || !DP || B < 0 || d <= 0 || d > kDagMaxD) return fail(GNF_ERR_INVALID, "gnf_dag_gate_planes: bad arguments (d <= 64)");
+  GateCtx g;
+  if (int e = make_gate(&g, x, P, gate, d)) return e;
+  if (B == 0) return 0;
+  const int M = B * d;
+  GNF_LAUNCH(dag_gate_planes_kernel, ew_blocks((size_t)M * kDagKP), 256, 0, (cudaStream_t)stream, g, GatePlanes{E, DX, DP}, M);
+  return check_launch("gnf_dag_gate_planes");
 }
 
 int gnf_dag_l1_wgrad_saved(const float* dY, int lddy, const float* E, float* dW1, int ldw, int B, int d, int N, gnf_stream_t stream) {

@@ -719,6 +719,9 @@ def _narrow_l1_tc(M, N1, delta):
 
 
 DAG_L1_NARROW_TC = True
+# ... and the forward GEMM too (gnf_dag_gate_planes + gnf_linear_fwd_tc_ps with the periodic bias table)?  Measured slower at cfg4: 5 + 40 us
+# (the planned-tile engine at K = 64) against 46 us for the resident-gate kernel, step 1.049 vs 1.011 ms (profiles/r02ah_*): off.
+DAG_L1_NARROW_TC_FWD = False
 
 
 def _dag_l1_plane(M, N1, d, direction):
@@ -771,10 +774,21 @@ class DagMlpFn(torch.autograd.Function):
         elif (DAG_L1_KEEP_GATES and d <= 64 and gate.mode != L.GATE_TABLE and B > 0 and any(ctx.needs_input_grad)):
             # narrow flow, stochastic gate, training: the forward leaves e, de/dx, de/dP ([B d, 64] each) for the two backward kernels
             narrow = tuple(torch.empty(B * d, 64, device=x.device, dtype=x.dtype) for _ in range(3))
-            _TIMES_ALIAS["gnf_dag_l1_fwd_save"] = "gnf_dag_l1_fwd"
-            _call("gnf_dag_l1_fwd_save", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
-                  ptr(y), y.stride(0), ptr(narrow[0]), ptr(narrow[1]), ptr(narrow[2]), B, d, N1, int(n > 1), st)
-            _count(3)
+            if DAG_L1_NARROW_TC_FWD and _narrow_l1_tc(B * d, N1, y) and n > 1:
+                # gates once (one per thread), then the forward GEMM on the tensor-core engine with the bias table as a periodic bias
+                _TIMES_ALIAS["gnf_dag_gate_planes"] = "gnf_dag_l1_fwd"
+                _call("gnf_dag_gate_planes", ptr(x), ptr(P), C.byref(g), ptr(narrow[0]), ptr(narrow[1]), ptr(narrow[2]), B, d, st)
+                hi, lo = _split_weight(weights[0][:, :d])
+                _TIMES_ALIAS["gnf_linear_fwd_tc_ps"] = "gnf_dag_l1_fwd"
+                _call("gnf_linear_fwd_tc_ps", ptr(narrow[0]), 64, ptr(hi), ptr(lo), hi.stride(0), ptr(T), (d if hot else 1), ptr(y), y.stride(0),
+                      B * d, N1, d, 1, st)
+                _TIMES_ALIAS["gnf_linear_fwd_tc_ps"] = "gnf_linear_fwd_tc"
+                _count(4)
+            else:
+                _TIMES_ALIAS["gnf_dag_l1_fwd_save"] = "gnf_dag_l1_fwd"
+                _call("gnf_dag_l1_fwd_save", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
+                      ptr(y), y.stride(0), ptr(narrow[0]), ptr(narrow[1]), ptr(narrow[2]), B, d, N1, int(n > 1), st)
+                _count(3)
         else:
             _call("gnf_dag_l1_fwd", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
                                        ptr(y), y.stride(0), B, d, N1, int(n > 1), st)

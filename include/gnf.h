@@ -218,6 +218,9 @@ int gnf_dag_l1_dgrad(const float* dY, int lddy, const float* W1, int ldw, const 
 int gnf_dag_l1_fwd_save(const float* x, const float* P, const gnf_gate_t* gate, const float* W1, int ldw, const float* T,
                         int bias_period, float* Y, int ldy, float* E, float* DX, float* DP, int B, int d, int N, int relu,
                         gnf_stream_t stream);
+/* ... the three planes alone (layer 1's forward then is gnf_linear_fwd_tc_ps against E with the bias table as a periodic bias). */
+int gnf_dag_gate_planes(const float* x, const float* P, const gnf_gate_t* gate, float* E, float* DX, float* DP, int B, int d,
+                        gnf_stream_t stream);
 int gnf_dag_l1_wgrad_saved(const float* dY, int lddy, const float* E, float* dW1, int ldw, int B, int d, int N, gnf_stream_t stream);
 int gnf_dag_l1_dgrad_saved(const float* dY, int lddy, const float* W1, int ldw, const float* DX, const float* DP, float* dx,
                            float* dP, int B, int d, int N, gnf_stream_t stream);
