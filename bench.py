@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--random-steps", action="store_true",
                     help="train: S = nb_steps + U{0..9} per step as the reference's UCI driver does (UCIExperiments.py:131-133); one "
                          "captured graph per S")
+    ap.add_argument("--no-side-branch", action="store_true", help="measurement: keep the DAG penalty chain in line with the forward inside the captured step")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "overlap", "single", "none"],
                     help="N > 1, gradient average of the flat bucket after the backward: peer = ONE libgnf kernel over NVLink peer memory (default; falls back "
                          "to single when CUDA IPC is unavailable); single = one NCCL all-reduce; overlap = NCCL sub-buckets overlapped with the rest of "
@@ -399,15 +400,15 @@ def main():
                         if hasattr(n, "nb_steps"):
                             n.nb_steps = Sx
                     if Sx not in graphs:
-                        graphs[Sx] = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=2)
+                        graphs[Sx] = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=2, side_branch=not args.no_side_branch)
                     return graphs[Sx](x)
                 for Sx in range(S_, S_ + 10):             # capture outside the timed region
                     for n in model.getNormalizers():
                         if hasattr(n, "nb_steps"):
                             n.nb_steps = Sx
-                    graphs[Sx] = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=2)
+                    graphs[Sx] = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=2, side_branch=not args.no_side_branch)
             elif mode == "train":
-                step = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=3)
+                step = G.GraphedTrainStep(model, opt, bucket, pool[0], allreduce=args.allreduce != "none", warmup=3, side_branch=not args.no_side_branch)
             else:
                 graphed_eval = G.GraphedEvalStep(model, pool[0], warmup=3)
                 step = lambda x: graphed_eval(x)[0].mean()

@@ -151,8 +151,10 @@ class FCNormalizingFlow(NormalizingFlow):
         for step in self.steps:
             step.step(epoch_number, loss_avg)
 
-    def loss(self, z, jac):
-        c = self.constraintsLoss()
+    def loss(self, z, jac, constraint=None):
+        """NormalizingFlow.py:144-146.  constraint: a constraintsLoss() value the caller already has (GraphedTrainStep computes it on a
+        side branch of the captured step, next to the forward); None = compute it here, as the reference does."""
+        c = self.constraintsLoss() if constraint is None else constraint
         if isinstance(self.z_log_density, NormalLogDensity) and z.dim() == 2 and z.shape[0] > 0:
             # constraint - mean(jac + z_log_density(z)) as one kernel per direction
             tensor_c = torch.is_tensor(c) and c.dim() == 0 and c.dtype == z.dtype and c.device == z.device

@@ -93,8 +93,10 @@ class GraphedTrainStep:
     differs (`recaptures` counts them).  Note the reference's own quirk: when update_dual_param re-creates A as a new
     Parameter, an optimizer built earlier no longer owns it -- here as there."""
 
-    def __init__(self, model, optimizer, bucket, example_x, allreduce=True, warmup=3, stream=None):
+    def __init__(self, model, optimizer, bucket, example_x, allreduce=True, warmup=3, stream=None, side_branch=True):
         self.model, self.opt, self.bucket = model, optimizer, bucket
+        has_penalty = any(hasattr(c, "get_power_trace") for c in model.getConditioners())
+        self.side = torch.cuda.Stream() if (side_branch and has_penalty and example_x.is_cuda) else None
         self.static_x = example_x.clone()
         self.allreduce, self.warmup, self.stream = allreduce, warmup, stream
         self.recaptures = 0
@@ -108,8 +110,19 @@ class GraphedTrainStep:
             for cnt in self.counters:
                 ops.counter_add(cnt, 1)
             bucket.begin_step()
-            z, jac = model(self.static_x)
-            loss = model.loss(z, jac)
+            if self.side is not None:
+                # the acyclicity / sparsity penalty depends on A only (a ~40-us chain of one-CTA kernels at d = 63: power trace, loss
+                # formula, and their backward): it runs as a parallel branch of the captured step, next to the forward
+                cur = torch.cuda.current_stream()
+                self.side.wait_stream(cur)
+                with torch.cuda.stream(self.side):
+                    c = model.constraintsLoss()
+                z, jac = model(self.static_x)
+                cur.wait_stream(self.side)
+                loss = model.loss(z, jac, constraint=c)
+            else:
+                z, jac = model(self.static_x)
+                loss = model.loss(z, jac)
             loss.backward()
             if allreduce:
                 bucket.finish_step()
