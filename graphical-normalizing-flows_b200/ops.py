@@ -96,6 +96,40 @@ def launch_count():
     return _LAUNCHES
 
 
+# Independent pieces of one backward (a layer's weight gradient, bias-table gradient and input cotangent; the wgrad and dgrad of a
+# skinny layer) are enqueued on side streams between a fork and a join: inside a captured step they become parallel branches of the
+# graph, and kernels that fill a fraction of the SMs run next to each other.  Discipline (caching allocator): a fork always waits for
+# the forking stream, every tensor a branch reads or writes stays referenced until the join.
+PARALLEL_BRANCHES = True
+_SIDE_STREAMS = {}
+
+
+class _Fork:
+    def __init__(self, k, like):
+        self.on = PARALLEL_BRANCHES and like.is_cuda and not L._SIMULATOR
+        if self.on:
+            key = (like.device.index, k)
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=like.device)
+            self.side = _SIDE_STREAMS[key]
+
+    def __enter__(self):
+        if self.on:
+            self.cur = torch.cuda.current_stream()
+            self.side.wait_stream(self.cur)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.ctx.__exit__(*a)
+
+    def join(self):
+        if self.on:
+            self.cur.wait_stream(self.side)
+
+
 def _contig(t):
     return t if t.is_contiguous() else t.contiguous()
 
@@ -541,8 +575,17 @@ def _mlp_backward(gout, ldg, acts, x_in, ldx, K0, weights, need_dx, first_layer_
             break
         if l > 0 and not PRESPLIT_ACTS:
             a_prev = acts[l - 1]
-            dWs[l], dbs[l] = linear_wgrad_bias(delta, ldd, a_prev, a_prev.stride(0), M, N, K)
-            delta = linear_dgrad(delta, ldd, W, a_prev, M)
+            if _gemm_passes(M, N, K, "wgrad") == 0 and M > 0:
+                # a skinny layer on the FFMA engine (cfg4's 630 -> 30 output layer: ~20 us each, a fraction of the SMs): the weight / bias
+                # gradient and the input cotangent run side by side
+                with _Fork(0, delta) as f:
+                    dWs[l], dbs[l] = linear_wgrad_bias(delta, ldd, a_prev, a_prev.stride(0), M, N, K)
+                delta_in, delta = delta, linear_dgrad(delta, ldd, W, a_prev, M)
+                f.join()
+                del delta_in
+            else:
+                dWs[l], dbs[l] = linear_wgrad_bias(delta, ldd, a_prev, a_prev.stride(0), M, N, K)
+                delta = linear_dgrad(delta, ldd, W, a_prev, M)
             ldd = delta.stride(0)
             continue
         dbs[l] = colsum(delta, ldd, M, N).view(N)
@@ -760,6 +803,14 @@ class DagMlpFn(torch.autograd.Function):
         T = torch.empty(d if hot else 1, N1, device=x.device, dtype=x.dtype)
         _call("gnf_dag_bias_table", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st)
         g = gate.c_struct()
+        # the weight splits of the hidden layers depend on nothing of this step: a side branch next to layer 1
+        f_split = None
+        if PRESPLIT_WEIGHTS and not PRESPLIT_ACTS and B > 0:
+            todo = [weights[l] for l in range(1, n) if _gemm_passes(B * d, weights[l].shape[0], weights[l].shape[1]) == 3]
+            if todo:
+                with _Fork(0, x) as f_split:
+                    for W in todo:
+                        _split_weight(W)
         y = _rows(B * d, N1, x) if n > 1 else torch.empty(B * d, N1, device=x.device, dtype=x.dtype)
         E = W1e = narrow = None
         gate_planes = (None, None)
@@ -793,6 +844,8 @@ class DagMlpFn(torch.autograd.Function):
             _call("gnf_dag_l1_fwd", ptr(x), ptr(P), C.byref(g), ptr(weights[0]), weights[0].stride(0), ptr(T), (d if hot else 1),
                                        ptr(y), y.stride(0), B, d, N1, int(n > 1), st)
             _count(3)
+        if f_split is not None:
+            f_split.join()
         acts = []
         splits = [None] * n       # splits[l] = TF32 (hi, lo) of layer l's input, when its forward GEMM ran pre-split: reused by its wgrad
         cur = y
@@ -841,32 +894,37 @@ class DagMlpFn(torch.autograd.Function):
             _call("gnf_dag_embed_fwd", ptr(x), ptr(P), C.byref(g), ptr(E), None, None, E.stride(0), B, d, st)
             W1e = W1[:, :d]
         narrow, ctx.narrow = ctx.narrow, None
-        if E is not None:
-            linear_wgrad(delta, delta.stride(0), E, E.stride(0), M, N1, d, out=dW1, lddw=dW1.stride(0))
-        elif narrow is not None and _narrow_l1_tc(M, N1, delta):
-            # dW1[:, :d] = delta^T E on the tensor-core engine (3xTF32) against the saved plane
-            _TIMES_ALIAS["gnf_linear_wgrad_tc"] = "gnf_dag_l1_wgrad"
-            _call("gnf_linear_wgrad_tc", ptr(delta), delta.stride(0), ptr(narrow[0]), 64, ptr(dW1), W1.stride(0), M, N1, d, 3, st)
-            _TIMES_ALIAS.pop("gnf_linear_wgrad_tc")
-        elif narrow is not None:
-            _TIMES_ALIAS["gnf_dag_l1_wgrad_saved"] = "gnf_dag_l1_wgrad"
-            _call("gnf_dag_l1_wgrad_saved", ptr(delta), delta.stride(0), ptr(narrow[0]), ptr(dW1), W1.stride(0), B, d, N1, st)
-        else:
-            _call("gnf_dag_l1_wgrad", ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st)
-        dT = colsum(delta, delta.stride(0), M, N1, period=(d if hot else 1))
-        db1 = torch.empty(N1, device=x.device, dtype=x.dtype)
-        _call("gnf_dag_bias_table_bwd", ptr(dT), ptr(dW1), W1.stride(0), ptr(db1), d, N1, int(hot), st)
+        narrow_tc = narrow is not None and _narrow_l1_tc(M, N1, delta)
+        # three independent pieces: [weight gradient of the masked half] | [bias table -> one-hot half of dW1, db1] | [input cotangent]
+        with _Fork(0, x) as f_w:
+            st = stream_ptr()
+            if E is not None:
+                linear_wgrad(delta, delta.stride(0), E, E.stride(0), M, N1, d, out=dW1, lddw=dW1.stride(0))
+            elif narrow_tc:
+                # dW1[:, :d] = delta^T E on the tensor-core engine (3xTF32) against the saved plane
+                _TIMES_ALIAS["gnf_linear_wgrad_tc"] = "gnf_dag_l1_wgrad"
+                _call("gnf_linear_wgrad_tc", ptr(delta), delta.stride(0), ptr(narrow[0]), 64, ptr(dW1), W1.stride(0), M, N1, d, 3, st)
+                _TIMES_ALIAS.pop("gnf_linear_wgrad_tc")
+            elif narrow is not None:
+                _TIMES_ALIAS["gnf_dag_l1_wgrad_saved"] = "gnf_dag_l1_wgrad"
+                _call("gnf_dag_l1_wgrad_saved", ptr(delta), delta.stride(0), ptr(narrow[0]), ptr(dW1), W1.stride(0), B, d, N1, st)
+            else:
+                _call("gnf_dag_l1_wgrad", ptr(delta), delta.stride(0), ptr(x), ptr(P), C.byref(g), ptr(dW1), W1.stride(0), B, d, N1, st)
+        with _Fork(1, x) as f_b:
+            dT = colsum(delta, delta.stride(0), M, N1, period=(d if hot else 1))
+            db1 = torch.empty(N1, device=x.device, dtype=x.dtype)
+            _call("gnf_dag_bias_table_bwd", ptr(dT), ptr(dW1), W1.stride(0), ptr(db1), d, N1, int(hot), stream_ptr())
         _count(2)
         dWs[0], dbs[0] = dW1, db1
-        dx = dA = None
+        st = stream_ptr()
+        dx = dA = dE = dP = hi = lo = None
         if needs[0] or needs[1]:
             dx = torch.empty_like(x)
             dP = torch.empty_like(A)
             if E is not None:
                 dE = linear_dgrad(delta, delta.stride(0), W1e, None, M)
                 _call("gnf_dag_embed_bwd", ptr(dE), dE.stride(0), ptr(x), ptr(P), C.byref(g), ptr(DXp), ptr(DPp), ptr(dx), ptr(dP), B, d, st)
-                del dE, DXp, DPp
-            elif narrow is not None and _narrow_l1_tc(M, N1, delta):
+            elif narrow_tc:
                 # ebar = delta W1[:, :d] on the tensor-core engine, then the two reductions against the saved derivative planes
                 hi, lo = _split_weight(W1[:, :d])
                 dE = torch.empty(M, 64, device=x.device, dtype=x.dtype)
@@ -886,6 +944,9 @@ class DagMlpFn(torch.autograd.Function):
             dA = torch.empty_like(A)
             _call("gnf_dag_finish_dA", ptr(dP), ptr(dPdA), ptr(dA), d, 0, st)
             _count(2)
+        f_w.join()
+        f_b.join()
+        del dE, DXp, DPp, narrow, E, dT, hi, lo          # (everything the branches touched stayed referenced until the joins)
         out = [dx if needs[0] else None, dA if needs[1] else None, None, None]
         for l in range(n):
             out += [dWs[l], dbs[l]]
