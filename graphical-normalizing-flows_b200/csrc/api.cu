@@ -31,6 +31,29 @@ int check_launch(const char* what) {
   return 0;
 }
 
+#ifndef GNF_EMU
+const Branches& branches() {
+  constexpr int kMaxDev = 16;
+  static Branches pool[kMaxDev];
+  static bool made[kMaxDev] = {};
+  static Branches none = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return none;
+  if (!made[dev]) {
+    Branches& b = pool[dev];
+    b.ok = true;
+    for (int k = 0; k < Branches::kSide; ++k) {
+      b.ok = b.ok && cudaStreamCreateWithFlags(&b.side[k], cudaStreamNonBlocking) == cudaSuccess;
+      b.ok = b.ok && cudaEventCreateWithFlags(&b.fork_ev[k], cudaEventDisableTiming) == cudaSuccess;
+      b.ok = b.ok && cudaEventCreateWithFlags(&b.join_ev[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!b.ok) cudaGetLastError();
+    made[dev] = true;
+  }
+  return pool[dev];
+}
+#endif
+
 }  // namespace gnf
 
 extern "C" {

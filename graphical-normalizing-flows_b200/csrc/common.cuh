@@ -26,6 +26,31 @@ int fail(int code, const char* fmt, ...);
 // Check the launch status of the kernels enqueued by an entry point.
 int check_launch(const char* what);
 
+#ifndef GNF_EMU
+// Fork / join inside one entry point: independent groups of small kernels are enqueued on library-owned side streams between an
+// event fork from, and an event join back into, the caller's stream -- inside a stream capture they become parallel branches of the
+// graph.  Streams and events are created per device on first use (the warm-up call before a capture); when that is impossible the
+// calls degrade to the caller's stream.
+struct Branches {
+  static constexpr int kSide = 2;
+  cudaStream_t side[kSide];
+  cudaEvent_t fork_ev[kSide], join_ev[kSide];
+  bool ok;
+  cudaStream_t begin(cudaStream_t main, int k) const {        // side stream k now follows everything enqueued on `main` so far
+    if (!ok) return main;
+    cudaEventRecord(fork_ev[k], main);
+    cudaStreamWaitEvent(side[k], fork_ev[k], 0);
+    return side[k];
+  }
+  void end(cudaStream_t main, int k) const {                  // `main` now follows everything enqueued on side stream k
+    if (!ok) return;
+    cudaEventRecord(join_ev[k], side[k]);
+    cudaStreamWaitEvent(main, join_ev[k], 0);
+  }
+};
+const Branches& branches();
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

@@ -34,7 +34,7 @@ int launch_rw_gemm(const RwGemmParams& p, cudaStream_t s);
 bool rw_wgrad_supported(int N, int K);
 size_t rw_wgrad_partial_floats(int K);
 int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long ldx, float* dW, long long lddw, int Q, int N, int K, int passes,
-                    float* partial, cudaStream_t s);
+                    float* partial, cudaStream_t s, const Branches* br = nullptr, int side = 0);
 
 }  // namespace gnf
 #endif

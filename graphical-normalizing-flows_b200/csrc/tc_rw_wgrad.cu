@@ -322,7 +322,7 @@ bool rw_wgrad_supported(int N, int K) {
 }
 
 int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long ldx, float* dW, long long lddw, int Q, int N, int K, int passes,
-                    float* partial, cudaStream_t s) {
+                    float* partial, cudaStream_t s, const Branches* br, int side) {
   if (passes != 1 && passes != 3) return fail(GNF_ERR_INVALID, "resident wgrad: passes must be 1 or 3");
   const int NP = (K + 31) / 32 * 32;
   if (!rw_wgrad_supported(N, K) || ldx != NP || lddy < N || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(partial) & 15))
@@ -344,6 +344,7 @@ int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long l
 #undef WG_CASE
   int rb = (N * K * 8 + 255) / 256;
   if (rb > 8 * kNumSMs) rb = 8 * kNumSMs;
+  if (br) s = br->begin(s, side);       // the second stage as a branch: it overlaps whatever the caller enqueues next (the caller joins: br->end)
   GNF_LAUNCH(rw_wgrad_reduce_kernel, rb, 256, 0, s, partial, grid, NP, dW, lddw, N, K);
   return 0;
 }

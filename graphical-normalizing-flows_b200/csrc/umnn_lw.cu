@@ -613,7 +613,7 @@ size_t gnf_umnn_bwd_tc3_workspace_bytes(const gnf_mlp_t* net, int R, int S) {
   if (img == 0) return 0;
   if (!pl.rw) { set_error("umnn tc3 backward: the hidden layers do not fit the resident weight-gradient kernel"); return 0; }
   const size_t plane = (size_t)pl.Q * pl.NP;
-  return ((size_t)R * pl.NP + (size_t)(pl.L - 1) * plane + rw_wgrad_partial_floats(pl.NP) + img + 8) * sizeof(float);
+  return ((size_t)R * pl.NP + (size_t)(pl.L - 1) * plane + 2 * (rw_wgrad_partial_floats(pl.NP) + 4) + img + 8) * sizeof(float);
 #endif
 }
 
@@ -643,7 +643,8 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   float* D = ws;
   float* dplanes = ws + (((size_t)R * NP + 3) / 4) * 4;            // plane 0: delta_L, planes 1..L-2: delta_{L-1} .. delta_2
   float* part = dplanes + (size_t)(L - 1) * plane;
-  float* image = part + ((rw_wgrad_partial_floats(NP) + 3) / 4) * 4;
+  const size_t part_floats = ((rw_wgrad_partial_floats(NP) + 3) / 4) * 4;     // two buffers: the reduction of one layer overlaps the next layer's kernel
+  float* image = part + 2 * part_floats;
   LwGeom g;
   g.R = R; g.d = d; g.E = E; g.S = S; g.nodes = pl.nodes; g.NP = NP; g.L = L; g.Q = pl.Q;
   const int red_threads = (NP / 4) * kLwRL;
@@ -657,17 +658,29 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   cudaMemsetAsync(D, 0, (size_t)R * NP * sizeof(float), s);
   cudaMemsetAsync(dx, 0, (size_t)R * sizeof(float), s);
   if (int e = launch_u3_bwd_chain(x, net, S, ccw, ccn, jac, gz, gzrev, gjac, glogdet, saved, image, dplanes + plane, D, dx, grads, R, d, s)) return e;
-  // weight gradients of the hidden GEMM layers: dW_l = delta_{l+1}^T a_l
-  for (int l = L - 1; l >= 1; --l) {
+  // Branch 0 (small per-row kernels, a fraction of the SMs each; they fill in around the persistent kernels of the main branch):
+  // the first layer -- db0 = colsum(D), dW0[:,1:] = D^T h, dh = D W0[:,1:] (+ gz on the first conditioning feature)
+  const Branches& br = branches();
+  {
+    cudaStream_t s0 = br.begin(s, 0);
+    gnf_stream_t st0 = (gnf_stream_t)s0;
+    if (int e = gnf_colsum(D, NP, grads->db[0], R, net->dims[1], 1, st0)) return e;
+    if (int e = gnf_linear_wgrad(D, NP, h, E, grads->dW[0] + 1, 1 + E, R, net->dims[1], E, st0)) return e;
+    if (int e = gnf_linear_dgrad(D, NP, net->W[0] + 1, 1 + E, nullptr, 0, dh, E, R, net->dims[1], E, st0)) return e;
+    GNF_LAUNCH(lw_finish_dh_kernel, lw_blocks(R, 256, 4), 256, 0, s0, dh, E, gz, gzrev, R, d);
+  }
+  // Main branch: weight gradients of the hidden GEMM layers, dW_l = delta_{l+1}^T a_l; the second stage (sum of the per-CTA partial
+  // tiles) of each layer is branch 1 and overlaps the next layer's kernel
+  int k = 0;
+  for (int l = L - 1; l >= 1; --l, ++k) {
     const float* dnext = dplanes + (size_t)(L - 1 - l) * plane;    // delta_{l+1}
     const float* a_l = saved + (size_t)(l - 1) * plane;
-    if (int e = launch_rw_wgrad(dnext, NP, a_l, NP, grads->dW[l], net->dims[l], (int)pl.Q, net->dims[l + 1], net->dims[l], 3, part, s)) return e;
+    if (k >= 2) br.end(s, 1);                                      // the partial buffer about to be reused has been summed
+    if (int e = launch_rw_wgrad(dnext, NP, a_l, NP, grads->dW[l], net->dims[l], (int)pl.Q, net->dims[l + 1], net->dims[l], 3,
+                                part + (size_t)(k & 1) * part_floats, s, &br, 1)) return e;
   }
-  // first layer: db0 = colsum(D), dW0[:,1:] = D^T h, dh = D W0[:,1:] (+ gz on the first conditioning feature)
-  if (int e = gnf_colsum(D, NP, grads->db[0], R, net->dims[1], 1, stream)) return e;
-  if (int e = gnf_linear_wgrad(D, NP, h, E, grads->dW[0] + 1, 1 + E, R, net->dims[1], E, stream)) return e;
-  if (int e = gnf_linear_dgrad(D, NP, net->W[0] + 1, 1 + E, nullptr, 0, dh, E, R, net->dims[1], E, stream)) return e;
-  GNF_LAUNCH(lw_finish_dh_kernel, lw_blocks(R, 256, 4), 256, 0, s, dh, E, gz, gzrev, R, d);
+  br.end(s, 1);
+  br.end(s, 0);
   return check_launch("gnf_umnn_bwd_tc3");
 #endif
 }
