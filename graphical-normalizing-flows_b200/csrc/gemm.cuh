@@ -205,6 +205,13 @@ struct EpiAtomicAdd {  // C += acc   (split-K)
     for (int j = 0; j < nv; ++j) atomicAdd(C + (size_t)m * ld + n + j, v[j]);
   }
 };
+struct EpiStoreSplit {  // P[split][m, n] = acc   (split-K partial tiles, summed in fixed order by a second kernel: deterministic)
+  float* P; int ld; size_t split_stride;
+  __device__ __forceinline__ void operator()(int m, int n, const float* v, int nv) const {
+    float* dst = P + (size_t)blockIdx.z * split_stride + (size_t)m * ld + n;
+    for (int j = 0; j < nv; ++j) dst[j] = v[j];
+  }
+};
 struct EpiStore {  // C = acc
   float* C; int ld;
   __device__ __forceinline__ void operator()(int m, int n, const float* v, int nv) const {

@@ -735,6 +735,48 @@ int gnf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float
   return check_launch("gnf_linear_fwd");
 }
 
+// Skinny output layer with a long reduction (cfg4: 6300 x 30 <- 630): 50 row tiles cannot fill the chip and one CTA per tile is a chain
+// of ten global round trips (35 us).  Split-K over kSkSplits slices into partial tiles + a fixed-order sum with bias / ReLU.
+constexpr int kSkSplits = 6, kSkLD = 32;
+static int sk_splits(int K) { return K / kSkSplits >= 64 ? kSkSplits : (K >= 128 ? K / 64 : 1); }
+
+__global__ void __launch_bounds__(256) splitk_sum_kernel(const float* __restrict__ P, size_t split_stride, int splits, const float* __restrict__ bias,
+                                                         int relu, float* __restrict__ Y, int ldy, int M, int N) {
+  const size_t total = (size_t)M * kSkLD;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % kSkLD);
+    const size_t m = idx / kSkLD;
+    if (n >= N) continue;
+    float v = bias ? __ldg(bias + n) : 0.f;
+    for (int z = 0; z < splits; ++z) v += __ldg(P + (size_t)z * split_stride + idx);
+    Y[m * ldy + n] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+size_t gnf_linear_fwd_splitk_workspace_bytes(int M, int N, int K) {
+  if (M < 1024 || N > kSkLD || sk_splits(K) < 2) return 0;
+  return (size_t)sk_splits(K) * M * kSkLD * sizeof(float);
+}
+
+int gnf_linear_fwd_splitk(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int M, int N, int K, int relu,
+                          void* work, size_t work_bytes, gnf_stream_t stream) {
+  if (!X || !W || !Y || M < 0 || N <= 0 || K <= 0 || ldx < K || ldw < K || ldy < N) return fail(GNF_ERR_INVALID, "gnf_linear_fwd_splitk: bad arguments");
+  const size_t need = gnf_linear_fwd_splitk_workspace_bytes(M, N, K);
+  if (need == 0) return fail(GNF_ERR_UNSUPPORTED, "gnf_linear_fwd_splitk: N <= 32, M >= 1024, K >= 128 only (else gnf_linear_fwd)");
+  if (!work || work_bytes < need) return fail(GNF_ERR_WORKSPACE, "gnf_linear_fwd_splitk: workspace too small (%zu < %zu)", work_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int splits = sk_splits(K);
+  const size_t stride = (size_t)M * kSkLD;
+  LoadRowMajorA al{X, ldx};
+  LoadWeightT bl{W, ldw};
+  EpiStoreSplit epi{(float*)work, kSkLD, stride};
+  launch_gemm<TileSkinny>(al, bl, epi, M, N, K, splits, s);
+  // launch_gemm rounds the slice to whole k tiles: the number of slices it really made
+  const int ktiles = ceil_div(K, TileSkinny::BK), per = ceil_div(ktiles, splits) * TileSkinny::BK, made = ceil_div(K, per);
+  GNF_LAUNCH(splitk_sum_kernel, ew_blocks(stride), 256, 0, s, (const float*)work, stride, made, bias, relu, Y, ldy, M, N);
+  return check_launch("gnf_linear_fwd_splitk");
+}
+
 int gnf_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const float* act, int ldact, float* dX,
                      int lddx, int M, int N, int K, gnf_stream_t stream) {
   if (!dY || !W || !dX || M < 0 || N <= 0 || K <= 0 || lddy < N || ldw < K || lddx < K) return fail(GNF_ERR_INVALID, "gnf_linear_dgrad: bad arguments");

@@ -406,6 +406,7 @@ def _tma_weight(W):
     return Wp
 
 
+SPLITK_SKINNY = True         # skinny layers with a long reduction (630 -> 30) on the FFMA engine: deterministic split-K (gnf_linear_fwd_splitk)
 PRESPLIT_WEIGHTS = True      # 3xTF32: split the weights once per call (gnf_split_tf32) instead of per tile in shared memory
 
 
@@ -488,8 +489,16 @@ def linear_fwd(X, W, bias, relu, bias_period=1, out=None, ldy=None, K=None, ldx=
         _call("gnf_linear_fwd_tc", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
               passes, stream_ptr())
     else:
-        _call("gnf_linear_fwd", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
-              stream_ptr())
+        nbytes = lib().gnf_linear_fwd_splitk_workspace_bytes(M, N, K) if (SPLITK_SKINNY and bias_period <= 1 and (X.is_cuda or L._SIMULATOR)) else 0
+        if nbytes:
+            work = torch.empty(nbytes // 4, device=X.device, dtype=torch.float32)
+            _TIMES_ALIAS["gnf_linear_fwd_splitk"] = "gnf_linear_fwd"
+            _call("gnf_linear_fwd_splitk", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), ptr(out), ldy, M, N, K, int(relu), ptr(work), nbytes,
+                  stream_ptr())
+            _count()
+        else:
+            _call("gnf_linear_fwd", ptr(X), ldx, ptr(W), W.stride(0), ptr(bias), bias_period, ptr(out), ldy, M, N, K, int(relu),
+                  stream_ptr())
     _count()
     return (out, used) if want_split else out
 

@@ -114,6 +114,12 @@ int gnf_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const f
 /* dW[n,k] = sum_m dY[m,n] X[m,k]  (overwrites dW). */
 int gnf_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int N, int K,
                      gnf_stream_t stream);
+/* gnf_linear_fwd for a skinny layer with a long reduction (N <= 32, M >= 1024, K >= 128: the conditioner's output layer,
+ * DAGConditioner.py:7-20 with out_size = 30): split-K into partial tiles in `work` + a fixed-order sum with bias / ReLU
+ * (deterministic).  gnf_linear_fwd_splitk_workspace_bytes returns 0 for shapes it does not take. */
+size_t gnf_linear_fwd_splitk_workspace_bytes(int M, int N, int K);
+int gnf_linear_fwd_splitk(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int M, int N, int K,
+                          int relu, void* work, size_t work_bytes, gnf_stream_t stream);
 /* out[p,n] = sum_{m % period == p} Y[m,n]  (bias gradients; one-hot column gradients). */
 int gnf_colsum(const float* Y, int ldy, float* out, int M, int N, int period, gnf_stream_t stream);
 /* dY[m,n] *= (act[m,n] > 0)  — ReLU backward for a cotangent produced outside the engine. */

@@ -145,3 +145,23 @@ def test_narrow_layer1_plane_reduction_in_simulator(emu, B, d):
     """gnf_dag_l1_reduce_saved: dx[b,j] = sum_i dE de/dx, dP[i,j] = sum_b dE de/dP over the planes the training forward kept."""
     torch.set_num_threads(1)
     _narrow_reduce_case("cpu", B, d)
+
+
+def _splitk_case(device, M_, N, K, relu):
+    g = torch.Generator().manual_seed(M_ + N + K)
+    X = torch.randn(M_, K, generator=g).to(device)
+    W = (torch.randn(N, K, generator=g) / K ** .5).to(device)
+    b = torch.randn(N, generator=g).to(device)
+    assert G._lib.lib().gnf_linear_fwd_splitk_workspace_bytes(M_, N, K) > 0
+    Y = G.ops.linear_fwd(X, W, b, relu=relu)
+    Y2 = G.ops.linear_fwd(X, W, b, relu=relu)
+    assert torch.equal(Y, Y2)                                      # fixed-order sum of the partial tiles: deterministic
+    ref = X.double() @ W.double().t() + b.double()
+    ref = torch.relu(ref) if relu else ref
+    assert torch.allclose(Y.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_skinny_split_k_forward_in_simulator(emu):
+    """gnf_linear_fwd_splitk (the conditioner's 630 -> 30 output layer): partial tiles + fixed-order sum, against float64."""
+    torch.set_num_threads(1)
+    _splitk_case("cpu", 1024, 5, 130, False)

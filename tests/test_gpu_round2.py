@@ -540,3 +540,9 @@ def test_narrow_layer1_backward_on_tensor_cores_matches_resident_kernels():
     for tag in ("saved", "tc"):
         for a, b in zip(grads["regen"], grads[tag]):
             assert float((a - b).norm() / b.norm()) < (2e-6 if tag == "saved" else 2e-5), tag
+
+
+@pytest.mark.parametrize("M_,N,K,relu", [(6300, 30, 630, False), (1024, 32, 128, True), (5000, 1, 1000, False)])
+def test_skinny_split_k_forward(M_, N, K, relu):
+    from test_emu_kernels import _splitk_case
+    _splitk_case("cuda", M_, N, K, relu)
