@@ -51,6 +51,17 @@ struct Branches {
 const Branches& branches();
 #endif
 
+// Zero-fill of several small buffers in ONE launch (inside a captured step every cudaMemsetAsync is a graph node of its own, ~1.5 us
+// each on the critical path; the fused UMNN backward alone had ten).
+struct ZeroList {
+  static constexpr int kMax = 24;       // 2 GNF_MAX_LAYERS gradient tensors + a few work buffers
+  float* p[kMax];
+  long long n[kMax];      // floats
+  int count = 0;
+  void add(float* ptr, size_t floats) { if (ptr && floats && count < kMax) { p[count] = ptr; n[count] = (long long)floats; ++count; } }
+};
+void zero_many(const ZeroList& z, cudaStream_t s);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

@@ -219,6 +219,23 @@ __global__ void dag_loss_bwd_kernel(const float* __restrict__ A, int n, const fl
   if (blockIdx.x == 0 && threadIdx.x == 0) *dt = gv * *dag_const * (*lambd + *c * *t);
 }
 
+__global__ void __launch_bounds__(256) zero_many_kernel(ZeroList z) {
+  for (int k = 0; k < z.count; ++k) {
+    float* __restrict__ p = z.p[k];
+    const long long n = z.n[k];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.f;
+  }
+}
+
+void zero_many(const ZeroList& z, cudaStream_t s) {
+  if (z.count == 0) return;
+  long long most = 0;
+  for (int k = 0; k < z.count; ++k) most = z.n[k] > most ? z.n[k] : most;
+  long long blocks = (most + 255) / 256;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  GNF_LAUNCH(zero_many_kernel, (int)blocks, 256, 0, s, z);
+}
+
 }  // namespace gnf
 
 using namespace gnf;

@@ -1537,9 +1537,15 @@ int gnf_linear_wgrad_bias_tc(const float* dY, int lddy, const float* X, int ldx,
     if (int e = gnf_colsum(dY, lddy, db, M, N, 1, stream)) return e;
     return gnf_linear_wgrad_tc(dY, lddy, X, ldx, dW, lddw, M, N, K, 3, stream);
   }
-  if (lddw == K) cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s);
-  else cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)N, s);
-  cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), s);
+  if (lddw == K) {
+    ZeroList zl;
+    zl.add(dW, (size_t)N * K);
+    zl.add(db, (size_t)N);
+    zero_many(zl, s);
+  } else {
+    cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)N, s);
+    cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), s);
+  }
   p.rowsum = db;
   if (int e = launch_tc_gemm(p, s)) return e;
   return check_launch("gnf_linear_wgrad_bias_tc");

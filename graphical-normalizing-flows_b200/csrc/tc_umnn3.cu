@@ -961,9 +961,11 @@ int gnf_umnn_fwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   // P = h W0[:,1:]^T + b0, once per row (strict fp32 on the FFMA engine: R x N1 x E is tiny)
   float* P = ws + pl.off_P;
   if (int e = gnf_linear_fwd(h, E, net->W[0] + 1, 1 + E, net->b[0], 1, P, NP, R, net->dims[1], E, 0, stream)) return e;
-  cudaMemsetAsync(z, 0, (size_t)R * sizeof(float), s);
-  if (zrev) cudaMemsetAsync(zrev, 0, (size_t)R * sizeof(float), s);
-  if (logdet) cudaMemsetAsync(logdet, 0, (size_t)(R / d) * sizeof(float), s);
+  ZeroList zl;
+  zl.add(z, (size_t)R);
+  zl.add(zrev, (size_t)R);
+  zl.add(logdet, (size_t)(R / d));
+  zero_many(zl, s);
   U3Params p;
   p.x = x; p.h = h; p.ccw = ccw; p.ccn = ccn; p.P = P; p.image = ws; p.blast = net->b[L];
   p.z = z; p.zrev = zrev; p.jac = jac; p.logdet = logdet; p.saved = saved;

@@ -632,12 +632,13 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   if ((reinterpret_cast<uintptr_t>(work) & 15) != 0) return fail(GNF_ERR_INVALID, "gnf_umnn_bwd_tc3: workspace must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const int NP = pl.NP, L = pl.L, E = pl.E;
+  ZeroList zl;
   for (int l = 0; l < net->n_layers; ++l) {
     if (!grads->dW[l] || !grads->db[l]) return fail(GNF_ERR_INVALID, "gnf_umnn_bwd_tc3: gradient pointer %d is NULL", l);
-    cudaMemsetAsync(grads->dW[l], 0, (size_t)net->dims[l] * net->dims[l + 1] * sizeof(float), s);
-    cudaMemsetAsync(grads->db[l], 0, (size_t)net->dims[l + 1] * sizeof(float), s);
+    zl.add(grads->dW[l], (size_t)net->dims[l] * net->dims[l + 1]);
+    zl.add(grads->db[l], (size_t)net->dims[l + 1]);
   }
-  if (R == 0) return check_launch("gnf_umnn_bwd_tc3");
+  if (R == 0) { zero_many(zl, s); return check_launch("gnf_umnn_bwd_tc3"); }
   float* ws = (float*)work;
   const size_t plane = (size_t)pl.Q * NP;
   float* D = ws;
@@ -650,13 +651,14 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   const int red_threads = (NP / 4) * kLwRL;
   const size_t red_smem = ((size_t)kLwRL * NP + kLwRL + 4) * sizeof(float);
   const float* ysave = saved + (size_t)L * plane;
+  zl.add(D, (size_t)R * NP);
+  zl.add(dx, (size_t)R);
+  zero_many(zl, s);                    // every gradient tensor, D and dx: one launch (GNF_MAX_LAYERS = 6: at most 14 entries)
   // output layer: delta_L (plane for the weight gradient of W_{L-1}), dW_L, db_L, db_{L-1}
   const int out_bwd_per_sm = 65536 / (64 * red_threads) < 1 ? 1 : (65536 / (64 * red_threads) > 4 ? 4 : 65536 / (64 * red_threads));
   GNF_LAUNCH(lw_out_bwd_kernel, lw_blocks(pl.Q, 64, out_bwd_per_sm), red_threads, red_smem, s, saved + (size_t)(L - 1) * plane, ysave, net->W[L],
              net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dplanes, grads->dW[L], grads->db[L], grads->db[L - 1], g);
   // the dgrad chain on the tensor cores: delta_{L-1} .. delta_2 planes, hidden db, dW0[:,0], D, dx
-  cudaMemsetAsync(D, 0, (size_t)R * NP * sizeof(float), s);
-  cudaMemsetAsync(dx, 0, (size_t)R * sizeof(float), s);
   if (int e = launch_u3_bwd_chain(x, net, S, ccw, ccn, jac, gz, gzrev, gjac, glogdet, saved, image, dplanes + plane, D, dx, grads, R, d, s)) return e;
   // Branch 0 (small per-row kernels, a fraction of the SMs each; they fill in around the persistent kernels of the main branch):
   // the first layer -- db0 = colsum(D), dW0[:,1:] = D^T h, dh = D W0[:,1:] (+ gz on the first conditioning feature)
