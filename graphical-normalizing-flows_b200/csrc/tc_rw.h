@@ -33,8 +33,11 @@ int launch_rw_gemm(const RwGemmParams& p, cudaStream_t s);
 // (rw_wgrad_partial_floats(K) floats), summed by a second kernel.
 bool rw_wgrad_supported(int N, int K);
 size_t rw_wgrad_partial_floats(int K);
+// dY given as a masked rank-one product instead of a plane: dY[q][n] = g[q] w[n] if bit (n % 32) of bits[q * bits_ld + n / 32] else 0
+// (the top of the UMNN backward: delta_L = (g_q w_L) o relu'(a_L))
+struct RwRankOne { const float* g; const float* w; const uint32_t* bits; int bits_ld; };
 int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long ldx, float* dW, long long lddw, int Q, int N, int K, int passes,
-                    float* partial, cudaStream_t s, const Branches* br = nullptr, int side = 0);
+                    float* partial, cudaStream_t s, const Branches* br = nullptr, int side = 0, const RwRankOne* rank_one = nullptr);
 
 }  // namespace gnf
 #endif

@@ -47,6 +47,7 @@ static long long* g_wg_trace = nullptr;
 struct RwWgradParams {
   long long* trace;
   const float* dY; long long lddy;     // [Q][lddy], N columns used
+  RwRankOne r1;                        // r1.g != NULL: dY is the masked rank-one product instead (dY unused)
   const float* X;                      // [Q][NP] dense (row stride NP), padding columns finite
   float* partial;                      // [gridDim.x][kWgPartRows][NP]
   int Q, N, chunks_per_cta, passes;
@@ -204,8 +205,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
     float va[kWgQC], vb[kWgQC];                                            // two chunks in flight
     const int nc = n < p.N ? n : 0;
     const bool row_ok = n < p.N;
-    auto load = [&](int j, float (&v)[kWgQC]) {
+    // Rank-one mode (p.r1.g): dY[q][n] = g_q w_n where bit n of the row's ReLU mask is set.  g_q and the mask word of this warp's
+    // 32 columns are warp-uniform: lanes 0-15 fetch g of the chunk's 16 node-rows, lanes 16-31 their mask words (ONE load per lane
+    // and chunk, prefetched two chunks ahead like the plane loads), and the values are handed round by shuffles when the chunk is split.
+    const bool r1 = p.r1.g != nullptr;
+    const float w_n = r1 ? __ldg(p.r1.w + nc) : 0.f;
+    const int wword = (tile ? 128 : warp * 32) >> 5;
+    uint32_t ra = 0u, rb = 0u;
+    auto load = [&](int j, float (&v)[kWgQC], uint32_t& raw) {
       const long long q0 = (long long)(c0 + (j < nloc ? j : 0)) * kWgQC;
+      if (r1) {
+        const long long qq = q0 + (lane & 15);
+        const long long q = qq < p.Q ? qq : (long long)p.Q - 1;
+        raw = lane < 16 ? __float_as_uint(__ldg(p.r1.g + q)) : __ldg(p.r1.bits + q * p.r1.bits_ld + wword);
+        return;
+      }
 #pragma unroll
       for (int c = 0; c < kWgQC; ++c) {
         const long long q = (q0 + c < p.Q) ? q0 + c : (long long)p.Q - 1;
@@ -213,11 +227,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
       }
     };
     WgTrace tr = {(p.trace && blockIdx.x == 0 && tid == 0) ? p.trace + 512 : nullptr, 0};
-    auto step = [&](int j, float (&v)[kWgQC]) {
+    auto step = [&](int j, float (&v)[kWgQC], uint32_t& raw) {
       const int b = j & 1;
       const long long q0 = (long long)(c0 + j) * kWgQC;
       tr.stamp();                                                          // per chunk: start, split + A free, handed over, next loads issued
       uint32_t hi[kWgQC], lo[kWgQC];
+      if (r1) {                                                            // all 32 shuffles first (independent), then the selects
+        uint32_t gs[kWgQC], ms[kWgQC];
+#pragma unroll
+        for (int c = 0; c < kWgQC; ++c) { gs[c] = __shfl_sync(0xffffffffu, raw, c); ms[c] = __shfl_sync(0xffffffffu, raw, 16 + c); }
+#pragma unroll
+        for (int c = 0; c < kWgQC; ++c) v[c] = ((ms[c] >> lane) & 1u) ? __uint_as_float(gs[c]) * w_n : 0.f;
+      }
 #pragma unroll
       for (int c = 0; c < kWgQC; ++c) {
         const float x = (row_ok && q0 + c < p.Q) ? v[c] : 0.f;
@@ -225,7 +246,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
         hi[c] = h;
         lo[c] = wg_rn_tf32(__float_as_uint(x - __uint_as_float(h)));
       }
-      load(j + 2, v);                                                      // this buffer's next chunk: in flight for two chunk periods
+      load(j + 2, v, raw);                                                 // this buffer's next chunk: in flight for two chunk periods
       if (j >= 2) {                                                        // the MMAs of chunk j-2 must be done with this A buffer
         mbar_wait(&a_empty[b], (uint32_t)(((j >> 1) - 1) & 1));
         fence_after_sync();
@@ -240,11 +261,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
       if (lane == 0) wg_mbar_arrive(&a_full[b]);
       tr.stamp();
     };
-    load(0, va);
-    load(1, vb);
+    load(0, va, ra);
+    load(1, vb, rb);
     for (int j = 0; j < nloc; j += 2) {
-      step(j, va);
-      if (j + 1 < nloc) step(j + 1, vb);
+      step(j, va, ra);
+      if (j + 1 < nloc) step(j + 1, vb, rb);
     }
     // ---- epilogue: partial tile of this CTA, row-owner -> coalesced through a swizzled 32 x 32 block (the rings are idle now)
     mbar_wait(d_full, 0);
@@ -322,7 +343,7 @@ bool rw_wgrad_supported(int N, int K) {
 }
 
 int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long ldx, float* dW, long long lddw, int Q, int N, int K, int passes,
-                    float* partial, cudaStream_t s, const Branches* br, int side) {
+                    float* partial, cudaStream_t s, const Branches* br, int side, const RwRankOne* rank_one) {
   if (passes != 1 && passes != 3) return fail(GNF_ERR_INVALID, "resident wgrad: passes must be 1 or 3");
   const int NP = (K + 31) / 32 * 32;
   if (!rw_wgrad_supported(N, K) || ldx != NP || lddy < N || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(partial) & 15))
@@ -333,6 +354,7 @@ int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long l
   const int grid = (nchunks + cpc - 1) / cpc;
   RwWgradParams p;
   p.trace = g_wg_trace;
+  p.r1 = rank_one ? *rank_one : RwRankOne{nullptr, nullptr, nullptr, 0};
   p.dY = dY; p.lddy = lddy; p.X = X; p.partial = partial; p.Q = Q; p.N = N; p.chunks_per_cta = cpc; p.passes = passes;
   const size_t smem = wg_smem_bytes(NP);
 #define WG_CASE(nb)                                                                                                      \

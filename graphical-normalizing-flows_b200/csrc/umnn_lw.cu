@@ -161,7 +161,7 @@ __device__ __forceinline__ float lw_gz_total(const float* __restrict__ gz, const
 __global__ void lw_out_bwd_kernel(const float* __restrict__ aL, const float* __restrict__ ysave, const float* __restrict__ wl, int NL,
                                   const float* __restrict__ x, const float* __restrict__ ccw, const float* __restrict__ jac,
                                   const float* __restrict__ gz, const float* __restrict__ gzrev, const float* __restrict__ gjac,
-                                  const float* __restrict__ glogdet, float* __restrict__ dL, float* __restrict__ dWl,
+                                  const float* __restrict__ glogdet, float* __restrict__ dL, float* __restrict__ gq_out, float* __restrict__ dWl,
                                   float* __restrict__ dbl, float* __restrict__ dbprev, LwGeom g) {
   GNF_SMEM(float, red);                       // [kLwRL][NP] + [kLwRL]
   const int C4 = g.NP / 4;
@@ -214,7 +214,10 @@ __global__ void lw_out_bwd_kernel(const float* __restrict__ aL, const float* __r
         o[e] = a[e] > 0.f ? gq * w[e] : 0.f;
         sB[e] += o[e];
       }
-      *reinterpret_cast<float4*>(dL + (size_t)(q + u * kLwRL) * g.NP + c) = make_float4(o[0], o[1], o[2], o[3]);
+      // gq_out: the caller's weight-gradient kernel rebuilds delta_L = (g_q w_L) o relu'(a_L) from g_q and the saved ReLU bit mask --
+      // one float per node-row leaves instead of a [Q][NP] plane (89 MB at cfg4, written here and read back there)
+      if (gq_out) { if (c4 == 0) gq_out[q + u * kLwRL] = gq; }
+      else *reinterpret_cast<float4*>(dL + (size_t)(q + u * kLwRL) * g.NP + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (c4 == 0) sy += gq;
     }
   }
@@ -570,7 +573,7 @@ int gnf_umnn_bwd_lw(const float* x, const float* h, const gnf_mlp_t* net, int S,
   // SM ran as 1.33 waves)
   const int out_bwd_per_sm = 65536 / (64 * red_threads) < 1 ? 1 : (65536 / (64 * red_threads) > 4 ? 4 : 65536 / (64 * red_threads));
   GNF_LAUNCH(lw_out_bwd_kernel, lw_blocks(pl.Q, 64, out_bwd_per_sm), red_threads, red_smem, s, saved + (size_t)(L - 1) * plane, ysave, net->W[L],
-             net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dcur, grads->dW[L], grads->db[L], grads->db[L - 1], g);
+             net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dcur, (float*)nullptr, grads->dW[L], grads->db[L], grads->db[L - 1], g);
   // hidden layers, top down: dW_l = delta_{l+1}^T a_l;  delta_l = (delta_{l+1} W_l) o relu'(a_l);  db_{l-1} = colsum delta_l
   for (int l = L - 1; l >= 1; --l) {
     const float* a_l = saved + (size_t)(l - 1) * plane;
@@ -654,10 +657,13 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   zl.add(D, (size_t)R * NP);
   zl.add(dx, (size_t)R);
   zero_many(zl, s);                    // every gradient tensor, D and dx: one launch (GNF_MAX_LAYERS = 6: at most 14 entries)
-  // output layer: delta_L (plane for the weight gradient of W_{L-1}), dW_L, db_L, db_{L-1}
+  // output layer: g_q per node-row (the weight-gradient kernel of W_{L-1} rebuilds delta_L from it and the saved ReLU mask of a_L: no
+  // delta_L plane), dW_L, db_L, db_{L-1}.  g_q lives in the first Q floats of what used to be that plane.
+  float* gq = dplanes;
+  const uint32_t* bits_top = reinterpret_cast<const uint32_t*>(saved + (size_t)L * plane + pl.Q) + (size_t)(L - 1) * pl.Q * (NP / 32);
   const int out_bwd_per_sm = 65536 / (64 * red_threads) < 1 ? 1 : (65536 / (64 * red_threads) > 4 ? 4 : 65536 / (64 * red_threads));
   GNF_LAUNCH(lw_out_bwd_kernel, lw_blocks(pl.Q, 64, out_bwd_per_sm), red_threads, red_smem, s, saved + (size_t)(L - 1) * plane, ysave, net->W[L],
-             net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dplanes, grads->dW[L], grads->db[L], grads->db[L - 1], g);
+             net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dplanes, gq, grads->dW[L], grads->db[L], grads->db[L - 1], g);
   // the dgrad chain on the tensor cores: delta_{L-1} .. delta_2 planes, hidden db, dW0[:,0], D, dx
   if (int e = launch_u3_bwd_chain(x, net, S, ccw, ccn, jac, gz, gzrev, gjac, glogdet, saved, image, dplanes + plane, D, dx, grads, R, d, s)) return e;
   // Branch 0 (small per-row kernels, a fraction of the SMs each; they fill in around the persistent kernels of the main branch):
@@ -678,8 +684,9 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
     const float* dnext = dplanes + (size_t)(L - 1 - l) * plane;    // delta_{l+1}
     const float* a_l = saved + (size_t)(l - 1) * plane;
     if (k >= 2) br.end(s, 1);                                      // the partial buffer about to be reused has been summed
+    const RwRankOne top = {gq, net->W[L], bits_top, NP / 32};
     if (int e = launch_rw_wgrad(dnext, NP, a_l, NP, grads->dW[l], net->dims[l], (int)pl.Q, net->dims[l + 1], net->dims[l], 3,
-                                part + (size_t)(k & 1) * part_floats, s, &br, 1)) return e;
+                                part + (size_t)(k & 1) * part_floats, s, &br, 1, l == L - 1 ? &top : nullptr)) return e;
   }
   br.end(s, 1);
   br.end(s, 0);
