@@ -23,7 +23,8 @@ namespace gnf {
 
 constexpr int kWgQC = 16;                 // reduction rows (q) per chunk: two 8-q MMA k-steps
 constexpr int kWgThreads = 15 * 32;       // warps 0-3 loaders of rows 0..127 (+ epilogue), 4 loader of rows 128..159, 5-12 stagers, 13 issuer, 14 producer
-constexpr int kWgRawStages = 4, kWgImgStages = 3;
+constexpr int kWgRawStages = 6, kWgImgStages = 3;
+constexpr int kWgDyStages = 6, kWgDyFloats = kWgQC * 160;   // dY chunks by bulk copy (dense planes): six in flight, no registers
 constexpr int kWgColD0 = 0, kWgColD1 = 160, kWgColA = 320;   // A buffer b at 320 + 64 b: A0hi, A0lo, A1hi, A1lo (16 columns each)
 constexpr int kWgPartRows = 160;
 
@@ -48,6 +49,7 @@ struct RwWgradParams {
   long long* trace;
   const float* dY; long long lddy;     // [Q][lddy], N columns used
   RwRankOne r1;                        // r1.g != NULL: dY is the masked rank-one product instead (dY unused)
+  int bulk_dy;                         // dY rows are 16-byte aligned and at most 160 floats: its chunks arrive by bulk copies
   const float* X;                      // [Q][NP] dense (row stride NP), padding columns finite
   float* partial;                      // [gridDim.x][kWgPartRows][NP]
   int Q, N, chunks_per_cta, passes;
@@ -69,7 +71,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
   uint64_t* a_full = img_empty + kWgImgStages;      // [2] loaders -> issuer (one arrive per loader warp)
   uint64_t* a_empty = a_full + 2;                   // [2] issuer -> loaders (tcgen05.commit)
   uint64_t* d_full = a_empty + 2;                   // issuer -> epilogue (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+  uint64_t* dy_full = d_full + 1;                   // [kWgDyStages] dY chunk landed (transaction bytes)
+  uint64_t* dy_empty = dy_full + kWgDyStages;       // [kWgDyStages] loaders have the chunk in registers (one arrive per loader warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dy_empty + kWgDyStages);
+  float* dyraw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);   // [kWgDyStages][16][lddy], bulk-copy target
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int nchunks_all = (p.Q + kWgQC - 1) / kWgQC;
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
     for (int s = 0; s < kWgImgStages; ++s) { mbar_init(&img_full[s], 8); mbar_init(&img_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], two ? 5 : 4); mbar_init(&a_empty[b], 1); }
     mbar_init(d_full, 1);
+    for (int s = 0; s < kWgDyStages; ++s) { mbar_init(&dy_full[s], 1); mbar_init(&dy_empty[s], two ? 5 : 4); }
     fence_mbar_init();
   }
   fence_before_sync();
@@ -102,6 +108,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
         const uint32_t bytes = (uint32_t)rows * NP * 4u;
         mbar_expect_tx(&raw_full[s], bytes);
         bulk_g2s(raw + s * kRawFloats, p.X + (size_t)q0 * NP, bytes, &raw_full[s]);
+        if (p.bulk_dy) {
+          const int sd = j % kWgDyStages;
+          mbar_wait(&dy_empty[sd], (uint32_t)(((j / kWgDyStages) & 1) ^ 1));
+          const uint32_t dbytes = (uint32_t)rows * (uint32_t)p.lddy * 4u;
+          mbar_expect_tx(&dy_full[sd], dbytes);
+          bulk_g2s(dyraw + sd * kWgDyFloats, p.dY + (size_t)q0 * p.lddy, dbytes, &dy_full[sd]);
+        }
       }
     }
   } else if (warp == 13) {
@@ -211,8 +224,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
     const bool r1 = p.r1.g != nullptr;
     const float w_n = r1 ? __ldg(p.r1.w + nc) : 0.f;
     const int wword = (tile ? 128 : warp * 32) >> 5;
-    uint32_t ra = 0u, rb = 0u;
+    // The loaders are latency-bound (scripts/wg_trace.py: a cold dY load takes ~3.9 k clocks, two chunks of register prefetch covered
+    // 2 x 1.6 k): dense dY planes now arrive by bulk copies, six chunks in flight and no registers; the rank-one words are prefetched
+    // four chunks ahead (one register each); only dY with unaligned rows keeps the two-chunk register path.
+    const bool bulk = p.bulk_dy != 0;
+    const int dist = r1 ? 4 : 2;
+    uint32_t r0 = 0u, r1w = 0u, r2 = 0u, r3 = 0u;
     auto load = [&](int j, float (&v)[kWgQC], uint32_t& raw) {
+      if (bulk) return;
       const long long q0 = (long long)(c0 + (j < nloc ? j : 0)) * kWgQC;
       if (r1) {
         const long long qq = q0 + (lane & 15);
@@ -232,7 +251,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
       const long long q0 = (long long)(c0 + j) * kWgQC;
       tr.stamp();                                                          // per chunk: start, split + A free, handed over, next loads issued
       uint32_t hi[kWgQC], lo[kWgQC];
-      if (r1) {                                                            // all 32 shuffles first (independent), then the selects
+      if (bulk) {                                                          // column nc of the landed [16 q][lddy] chunk: conflict-free
+        const int sd = j % kWgDyStages;
+        mbar_wait(&dy_full[sd], (uint32_t)((j / kWgDyStages) & 1));
+        const float* src = dyraw + sd * kWgDyFloats + nc;
+#pragma unroll
+        for (int c = 0; c < kWgQC; ++c) v[c] = src[c * (int)p.lddy];
+        __syncwarp();
+        if (lane == 0) wg_mbar_arrive(&dy_empty[sd]);
+      } else if (r1) {                                                     // all 32 shuffles first (independent), then the selects
         uint32_t gs[kWgQC], ms[kWgQC];
 #pragma unroll
         for (int c = 0; c < kWgQC; ++c) { gs[c] = __shfl_sync(0xffffffffu, raw, c); ms[c] = __shfl_sync(0xffffffffu, raw, 16 + c); }
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
         hi[c] = h;
         lo[c] = wg_rn_tf32(__float_as_uint(x - __uint_as_float(h)));
       }
-      load(j + 2, v, raw);                                                 // this buffer's next chunk: in flight for two chunk periods
+      load(j + dist, v, raw);                                              // this buffer's next chunk
       if (j >= 2) {                                                        // the MMAs of chunk j-2 must be done with this A buffer
         mbar_wait(&a_empty[b], (uint32_t)(((j >> 1) - 1) & 1));
         fence_after_sync();
@@ -261,11 +288,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
       if (lane == 0) wg_mbar_arrive(&a_full[b]);
       tr.stamp();
     };
-    load(0, va, ra);
-    load(1, vb, rb);
-    for (int j = 0; j < nloc; j += 2) {
-      step(j, va, ra);
-      if (j + 1 < nloc) step(j + 1, vb, rb);
+    load(0, va, r0);
+    load(1, vb, r1w);
+    if (r1) { load(2, va, r2); load(3, vb, r3); }
+    for (int j = 0; j < nloc; j += 4) {
+      step(j, va, r0);
+      if (j + 1 < nloc) step(j + 1, vb, r1w);
+      if (j + 2 < nloc) step(j + 2, va, r1 ? r2 : r0);
+      if (j + 3 < nloc) step(j + 3, vb, r1 ? r3 : r1w);
     }
     // ---- epilogue: partial tile of this CTA, row-owner -> coalesced through a swizzled 32 x 32 block (the rings are idle now)
     mbar_wait(d_full, 0);
@@ -332,7 +362,7 @@ __global__ void rw_wgrad_reduce_kernel(const float* __restrict__ partial, int nb
 static size_t wg_smem_bytes(int NP) {
   size_t fl = (size_t)kWgRawStages * kWgQC * NP + (size_t)kWgImgStages * 2 * kWgQC * NP;
   if (fl < 5 * 1024) fl = 5 * 1024;                       // the epilogue's five 4 KB staging blocks reuse the rings
-  return fl * sizeof(float) + 24 * sizeof(uint64_t) + 16;
+  return fl * sizeof(float) + (24 + 2 * kWgDyStages) * sizeof(uint64_t) + 16 + 128 + (size_t)kWgDyStages * kWgDyFloats * sizeof(float);
 }
 
 size_t rw_wgrad_partial_floats(int K) { return (size_t)kNumSMs * kWgPartRows * ((K + 31) / 32 * 32); }
@@ -355,6 +385,7 @@ int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long l
   RwWgradParams p;
   p.trace = g_wg_trace;
   p.r1 = rank_one ? *rank_one : RwRankOne{nullptr, nullptr, nullptr, 0};
+  p.bulk_dy = (!rank_one && (lddy % 4) == 0 && lddy <= 160 && (reinterpret_cast<uintptr_t>(dY) & 15) == 0) ? 1 : 0;
   p.dY = dY; p.lddy = lddy; p.X = X; p.partial = partial; p.Q = Q; p.N = N; p.chunks_per_cta = cpc; p.passes = passes;
   const size_t smem = wg_smem_bytes(NP);
 #define WG_CASE(nb)                                                                                                      \
