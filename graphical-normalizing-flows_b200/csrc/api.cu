@@ -1,5 +1,6 @@
 // Error reporting and version entry points of the C-ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -32,6 +33,12 @@ int check_launch(const char* what) {
 }
 
 #ifndef GNF_EMU
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("GNF_PDL"); on = (e && e[0] == '0') ? 0 : 1; }      // GNF_PDL=0: measurement (plain launches)
+  return on == 1;
+}
+
 const Branches& branches() {
   constexpr int kMaxDev = 16;
   static Branches pool[kMaxDev];

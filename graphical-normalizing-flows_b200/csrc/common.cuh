@@ -51,6 +51,36 @@ struct Branches {
 const Branches& branches();
 #endif
 
+#ifndef GNF_EMU
+// Launch with the programmatic-stream-serialization attribute: the kernel may begin (its prologue, up to pdl_prologue_done()) while the
+// previous kernel of the stream drains.  Only for kernels that call pdl_prologue_done() before their first global access.  Used for the
+// persistent tcgen05 kernels (prologue = TMEM allocation + barrier init): cfg4 +0.9 %.  NOT for the small kernels between them: their
+// early-resident CTAs, spinning in griddepcontrol.wait, take SM slots from the kernels of the step's parallel branches (-0.5 %).
+bool pdl_enabled();
+template <class... Params, class... Args>
+static inline void launch_pdl(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  if (!pdl_enabled()) { kernel<<<grid, block, smem, s>>>(Params(args)...); return; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, Params(args)...);
+}
+#define GNF_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+// Called by every thread of such a kernel before its first global access (after the prologue, if it has one): lets the NEXT kernel of
+// the stream start on SMs this grid has left, and holds this grid until the PREVIOUS grid has completed and flushed.  A no-op for
+// launches without the attribute.
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#else
+#define GNF_LAUNCH_PDL GNF_LAUNCH
+inline void pdl_prologue_done() {}
+#endif
+
 // Zero-fill of several small buffers in ONE launch (inside a captured step every cudaMemsetAsync is a graph node of its own, ~1.5 us
 // each on the critical path; the fused UMNN backward alone had ten).
 struct ZeroList {

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(TcGemmParams p, i
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();
 
   const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM, tiles_n = (p.N + BN - 1) / BN;
   const long long total = (long long)tiles_m * tiles_n * p.splits;
@@ -715,6 +716,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();
 
   const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM, tiles_n = (p.N + kG2BN - 1) / kG2BN;
   const int total = tiles_m * tiles_n;
@@ -998,6 +1000,7 @@ __global__ void __launch_bounds__(kW2Threads, 1) tc_wgrad2_kernel(TcGemmParams p
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();
 
   // GEMM view: rows = dW rows n (p.M of them), columns = dW columns k (p.N), reduction = the batch rows m (p.K)
   const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM, tiles_n = (p.N + kG2BN - 1) / kG2BN;
@@ -1271,7 +1274,7 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
     const size_t smem2 = (size_t)kG2Stages * kG2StageBytes + 8 * kG2EpiStageFloats * sizeof(float) + (3 * kG2Stages + 2 * kW2Ring + 4) * sizeof(uint64_t) + 16;
     const long long total2 = (long long)tiles2 * p.splits;
     cudaFuncSetAttribute(tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    GNF_LAUNCH(tc_wgrad2_kernel, (int)(total2 < kNumSMs ? total2 : kNumSMs), kW2Threads, smem2, s, p, tmA, tmB);
+    GNF_LAUNCH_PDL(tc_wgrad2_kernel, (int)(total2 < kNumSMs ? total2 : kNumSMs), kW2Threads, smem2, s, p, tmA, tmB);
     return 0;
   }
   if (p.rowsum) {      // only the kernel above sums the rows of A on its way: shapes of the first engine take the column-sum kernel (overwrites)
@@ -1293,12 +1296,12 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
 #ifdef GNF_DEVTOOLS
     if (g_tc_gemm_v2 == 2) {                     // measured equal to the default below at every fold interval (profiles/r02q_gemm2_fold_variants.txt)
       cudaFuncSetAttribute(tc_gemm2_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      GNF_LAUNCH((tc_gemm2_kernel<3, 2>), grid2, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
+      GNF_LAUNCH_PDL((tc_gemm2_kernel<3, 2>), grid2, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
       return 0;
     }
 #endif
     cudaFuncSetAttribute(tc_gemm2_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    GNF_LAUNCH((tc_gemm2_kernel<2, 4>), grid2, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
+    GNF_LAUNCH_PDL((tc_gemm2_kernel<2, 4>), grid2, kG2Threads, smem2, s, p, tmA, tmB, tmBlo);
     return 0;
   }
   p.trace = g_tc_gemm_trace;
@@ -1307,7 +1310,7 @@ int launch_tc_gemm(TcGemmParams p, cudaStream_t s) {
   // per launch: the attribute is per DEVICE, a process-wide "done" flag breaks the second GPU of a process (and is racy)
   cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  GNF_LAUNCH(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB, tmBlo, tmAlo);
+  GNF_LAUNCH_PDL(tc_gemm_kernel, grid, kGemmThreads, smem, s, p, vec_width(p.A, p.lda), vec_width(p.B, p.ldb), tmA, tmB, tmBlo, tmAlo);
   return 0;
 }
 

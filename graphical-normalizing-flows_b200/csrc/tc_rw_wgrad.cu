@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rw_wgrad_kernel(RwWgradParams p
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();
 
   if (warp == 14) {
     // ===================== bulk-copy producer =====================
@@ -391,7 +392,7 @@ int launch_rw_wgrad(const float* dY, long long lddy, const float* X, long long l
 #define WG_CASE(nb)                                                                                                      \
   case nb:                                                                                                               \
     cudaFuncSetAttribute(rw_wgrad_kernel<nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
-    GNF_LAUNCH(rw_wgrad_kernel<nb>, grid, kWgThreads, smem, s, p);                                                       \
+    GNF_LAUNCH_PDL(rw_wgrad_kernel<nb>, grid, kWgThreads, smem, s, p);                                                       \
     break;
   switch (NP / 32) { WG_CASE(1) WG_CASE(2) WG_CASE(3) WG_CASE(4) default: WG_CASE(5) }
 #undef WG_CASE

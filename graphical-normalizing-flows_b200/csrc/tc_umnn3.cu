@@ -158,6 +158,7 @@ __global__ void __launch_bounds__((4 * NB + 2) * 32, 1) umnn_fwd_tc3_kernel(U3Pa
     for (int b = 0; b < 2; ++b) { mbar_init(&p_full[b], 1); mbar_init(&p_empty[b], EW); }
     fence_mbar_init();
   }
+  pdl_prologue_done();                // the weight image read next comes from the previous kernel of the stream (u3_pack_kernel)
   for (int i = tid; i < (p.L + 1) * NP; i += NT) tail[i] = __ldg(p.image + p.off_tail + i);
   for (int i = tid; i <= p.S; i += NT) { ccs[i] = __ldg(p.ccn + i); ccs[kU3MaxNodes + i] = __ldg(p.ccw + i); }
   fence_before_sync();
@@ -545,6 +546,7 @@ __global__ void __launch_bounds__((4 * NB + 2) * 32, 1) umnn_bwd_tc3_kernel(U3BP
     mbar_init(d_empty, EW);
     fence_mbar_init();
   }
+  pdl_prologue_done();
   for (int i = tid; i < 2 * NP; i += NT) tail[i] = __ldg(p.image + p.off_tail + i);
   for (int i = tid; i <= p.S; i += NT) { ccs[i] = __ldg(p.ccn + i); ccs[kU3MaxNodes + i] = __ldg(p.ccw + i); }
   fence_before_sync();
@@ -893,7 +895,7 @@ int launch_u3_bwd_chain(const float* x, const gnf_mlp_t* net, int S, const float
 #define U3B_CASE(nb)                                                                                             \
   case nb:                                                                                                       \
     cudaFuncSetAttribute(umnn_bwd_tc3_kernel<nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    GNF_LAUNCH(umnn_bwd_tc3_kernel<nb>, grid, (4 * nb + 2) * 32, smem, s, p);                                    \
+    GNF_LAUNCH_PDL(umnn_bwd_tc3_kernel<nb>, grid, (4 * nb + 2) * 32, smem, s, p);                                    \
     break;
   switch (NP / 32) { U3B_CASE(1) U3B_CASE(2) U3B_CASE(3) U3B_CASE(4) U3B_CASE(5) default: return fail(GNF_ERR_UNSUPPORTED, "umnn tc3 backward: width"); }
 #undef U3B_CASE
@@ -985,7 +987,7 @@ int gnf_umnn_fwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
 #define U3_CASE(nb)                                                                                              \
   case nb:                                                                                                       \
     cudaFuncSetAttribute(umnn_fwd_tc3_kernel<nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    GNF_LAUNCH(umnn_fwd_tc3_kernel<nb>, grid, (4 * nb + 2) * 32, smem, s, p);                                           \
+    GNF_LAUNCH_PDL(umnn_fwd_tc3_kernel<nb>, grid, (4 * nb + 2) * 32, smem, s, p);                                           \
     break;
   switch (NP / 32) { U3_CASE(1) U3_CASE(2) U3_CASE(3) U3_CASE(4) U3_CASE(5) default: return fail(GNF_ERR_UNSUPPORTED, "gnf_umnn_fwd_tc3: width"); }
 #undef U3_CASE
