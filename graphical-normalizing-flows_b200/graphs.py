@@ -97,6 +97,10 @@ class GraphedTrainStep:
         self.model, self.opt, self.bucket = model, optimizer, bucket
         has_penalty = any(hasattr(c, "get_power_trace") for c in model.getConditioners())
         self.side = torch.cuda.Stream() if (side_branch and has_penalty and example_x.is_cuda) else None
+        if self.side is not None and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # A receives one gradient from the side branch (penalty) and one from the main branch (layer 1): intended, and neither
+            # stream is the default stream
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self.static_x = example_x.clone()
         self.allreduce, self.warmup, self.stream = allreduce, warmup, stream
         self.recaptures = 0

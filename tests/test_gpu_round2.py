@@ -546,3 +546,37 @@ def test_narrow_layer1_backward_on_tensor_cores_matches_resident_kernels():
 def test_skinny_split_k_forward(M_, N, K, relu):
     from test_emu_kernels import _splitk_case
     _splitk_case("cuda", M_, N, K, relu)
+
+
+def test_branched_schedule_matches_the_in_line_schedule():
+    """The late round-2 schedule of the captured step -- penalty chain on a side branch, layer-1 backward as three branches on the
+    tensor-core engine against the saved gate planes, skinny layer wgrad next to dgrad, weight splits next to layer 1 -- against the
+    in-line schedule with every one of those switches off: same first-step loss and gradients (the gate noise is the same Philox
+    stream: counters start equal), parameters after six Adam steps equal up to summation-order noise."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import model_vs_oracle as M
+    spec = M.CONFIGS["cfg4"]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xs = [torch.randn(100, 63, device="cuda", generator=g) for _ in range(6)]
+    G.ops.set_gemm_mode("auto")
+    results = {}
+    try:
+        for tag, on in (("in-line", False), ("branched", True)):
+            G.ops.PARALLEL_BRANCHES = G.ops.DAG_L1_KEEP_GATES = G.ops.DAG_L1_NARROW_TC = G.ops.SPLITK_SKINNY = on
+            model = M.build(spec, "cuda", seed=11)
+            for c in model.getConditioners():
+                c._noise_seed = 1234                       # same Philox key in both runs
+            bucket = G.dist.GradBucket(model.parameters())
+            opt = G.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-5)
+            step = G.GraphedTrainStep(model, opt, bucket, xs[0], allreduce=False, warmup=1, side_branch=on)
+            losses = [float(step(x)) for x in xs]
+            results[tag] = (losses, [p.detach().clone() for p in model.parameters()])
+    finally:
+        G.ops.PARALLEL_BRANCHES = G.ops.DAG_L1_KEEP_GATES = G.ops.DAG_L1_NARROW_TC = G.ops.SPLITK_SKINNY = True
+        G.ops.set_gemm_mode("ffma")
+    (la, pa), (lb, pb) = results["in-line"], results["branched"]
+    assert abs(la[0] - lb[0]) <= 1e-5 * abs(la[0]), (la[0], lb[0])
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 2e-3 * abs(a), (la, lb)
+    for a, b in zip(pa, pb):
+        assert float((a - b).norm() / a.norm().clamp_min(1e-12)) < 2e-3
