@@ -866,7 +866,7 @@ size_t u3_bwd_image_floats(const gnf_mlp_t* net) {
 // image: u3_bwd_image_floats(net) floats of scratch; dplanes: (L-2) planes; D, dx and the db / dW0 targets must be zeroed by the caller.
 int launch_u3_bwd_chain(const float* x, const gnf_mlp_t* net, int S, const float* ccw, const float* ccn, const float* jac, const float* gz,
                         const float* gzrev, const float* gjac, const float* glogdet, const float* saved, float* image, float* dplanes, float* D,
-                        float* dx, const gnf_mlp_grad_t* grads, int R, int d, cudaStream_t s) {
+                        float* dx, const gnf_mlp_grad_t* grads, int R, int d, cudaStream_t s, const Branches* br, int side, cudaStream_t pack_stream) {
   U3BPlan pl;
   if (int e = u3b_plan(net, &pl)) return e;
   const int NP = pl.NP, L = pl.L;
@@ -880,7 +880,9 @@ int launch_u3_bwd_chain(const float* x, const gnf_mlp_t* net, int S, const float
   a.chunk_floats = (unsigned)pl.chunk_floats; a.off_tail = (unsigned)pl.off_tail; a.total = (unsigned)pl.image_floats; a.L = L; a.NP = NP;
   int blocks = (int)((pl.image_floats + 255) / 256);
   if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
-  GNF_LAUNCH(u3_pack_bwd_kernel, blocks, 256, 0, s, a, image);
+  // the weight images depend on nothing of this call: the caller forked `pack_stream` before its output pass, joined here
+  GNF_LAUNCH(u3_pack_bwd_kernel, blocks, 256, 0, (br && pack_stream) ? pack_stream : s, a, image);
+  if (br && pack_stream) br->end(s, side);
   U3BParams p;
   p.x = x; p.ccw = ccw; p.ccn = ccn; p.jac = jac; p.gz = gz; p.gzrev = gzrev; p.gjac = gjac; p.glogdet = glogdet; p.image = image; p.saved = saved;
   p.dplanes = dplanes; p.D = D; p.dx = dx; p.dW0 = grads->dW[0]; p.ldw0 = net->dims[0];
@@ -959,15 +961,19 @@ int gnf_umnn_fwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   a.chunk_floats = (unsigned)pl.chunk_floats; a.off_tail = (unsigned)pl.off_tail; a.total = (unsigned)pl.image_floats; a.L = L; a.NP = NP;
   int blocks = (int)((pl.image_floats + 255) / 256);
   if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
-  GNF_LAUNCH(u3_pack_kernel, blocks, 256, 0, s, a, ws);
-  // P = h W0[:,1:]^T + b0, once per row (strict fp32 on the FFMA engine: R x N1 x E is tiny)
-  float* P = ws + pl.off_P;
-  if (int e = gnf_linear_fwd(h, E, net->W[0] + 1, 1 + E, net->b[0], 1, P, NP, R, net->dims[1], E, 0, stream)) return e;
+  // branch 0: the weight images and the zero-fills (they depend on nothing of this call) next to the P GEMM
+  const Branches& br = branches();
+  cudaStream_t s0 = br.begin(s, 0);
+  GNF_LAUNCH(u3_pack_kernel, blocks, 256, 0, s0, a, ws);
   ZeroList zl;
   zl.add(z, (size_t)R);
   zl.add(zrev, (size_t)R);
   zl.add(logdet, (size_t)(R / d));
-  zero_many(zl, s);
+  zero_many(zl, s0);
+  // P = h W0[:,1:]^T + b0, once per row (strict fp32 on the FFMA engine: R x N1 x E is tiny)
+  float* P = ws + pl.off_P;
+  if (int e = gnf_linear_fwd(h, E, net->W[0] + 1, 1 + E, net->b[0], 1, P, NP, R, net->dims[1], E, 0, stream)) return e;
+  br.end(s, 0);
   U3Params p;
   p.x = x; p.h = h; p.ccw = ccw; p.ccn = ccn; p.P = P; p.image = ws; p.blast = net->b[L];
   p.z = z; p.zrev = zrev; p.jac = jac; p.logdet = logdet; p.saved = saved;

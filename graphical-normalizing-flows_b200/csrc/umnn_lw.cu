@@ -656,6 +656,8 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   const float* ysave = saved + (size_t)L * plane;
   zl.add(D, (size_t)R * NP);
   zl.add(dx, (size_t)R);
+  const Branches& br = branches();
+  cudaStream_t pack_stream = br.ok ? br.begin(s, 0) : nullptr;     // the chain's weight images: next to the zero-fill and the output pass
   zero_many(zl, s);                    // every gradient tensor, D and dx: one launch (GNF_MAX_LAYERS = 6: at most 14 entries)
   // output layer: g_q per node-row (the weight-gradient kernel of W_{L-1} rebuilds delta_L from it and the saved ReLU mask of a_L: no
   // delta_L plane), dW_L, db_L, db_{L-1}.  g_q lives in the first Q floats of what used to be that plane.
@@ -665,10 +667,9 @@ int gnf_umnn_bwd_tc3(const float* x, const float* h, const gnf_mlp_t* net, int S
   GNF_LAUNCH(lw_out_bwd_kernel, lw_blocks(pl.Q, 64, out_bwd_per_sm), red_threads, red_smem, s, saved + (size_t)(L - 1) * plane, ysave, net->W[L],
              net->dims[L], x, ccw, jac, gz, gzrev, gjac, glogdet, dplanes, gq, grads->dW[L], grads->db[L], grads->db[L - 1], g);
   // the dgrad chain on the tensor cores: delta_{L-1} .. delta_2 planes, hidden db, dW0[:,0], D, dx
-  if (int e = launch_u3_bwd_chain(x, net, S, ccw, ccn, jac, gz, gzrev, gjac, glogdet, saved, image, dplanes + plane, D, dx, grads, R, d, s)) return e;
+  if (int e = launch_u3_bwd_chain(x, net, S, ccw, ccn, jac, gz, gzrev, gjac, glogdet, saved, image, dplanes + plane, D, dx, grads, R, d, s, &br, 0, pack_stream)) return e;
   // Branch 0 (small per-row kernels, a fraction of the SMs each; they fill in around the persistent kernels of the main branch):
   // the first layer -- db0 = colsum(D), dW0[:,1:] = D^T h, dh = D W0[:,1:] (+ gz on the first conditioning feature)
-  const Branches& br = branches();
   {
     cudaStream_t s0 = br.begin(s, 0);
     gnf_stream_t st0 = (gnf_stream_t)s0;
