@@ -673,12 +673,12 @@ __global__ void dag_importance_kernel(const float* __restrict__ A, int n, int im
   }
 }
 
-__global__ void dag_bias_table_kernel(const float* __restrict__ W1, int ldw, const float* __restrict__ b1, float* __restrict__ T, int d, int N, int hot) {
+__global__ void dag_bias_table_kernel(const float* __restrict__ W1, int ldw, const float* __restrict__ b1, float* __restrict__ T, int ldt, int d, int N, int hot) {
   const int rows = hot ? d : 1;
-  const size_t n = (size_t)rows * N;
+  const size_t n = (size_t)rows * ldt;          // padding columns [N, ldt) = 0
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(idx / N), c = (int)(idx % N);
-    T[idx] = (hot ? W1[(size_t)c * ldw + d + i] : 0.f) + (b1 ? b1[c] : 0.f);
+    const int i = (int)(idx / ldt), c = (int)(idx % ldt);
+    T[idx] = c < N ? (hot ? W1[(size_t)c * ldw + d + i] : 0.f) + (b1 ? b1[c] : 0.f) : 0.f;
   }
 }
 __global__ void dag_bias_table_bwd_kernel(const float* __restrict__ dT, float* __restrict__ dW1, int ldw, float* __restrict__ db1, int d, int N, int hot) {
@@ -855,8 +855,13 @@ int gnf_dag_importance(const float* A, int d, int imp, float h_thresh, float* P,
 }
 int gnf_dag_bias_table(const float* W1, int ldw, const float* b1, float* T, int d, int N, int hot, gnf_stream_t stream) {
   if (!W1 || !T || d <= 0 || N <= 0 || ldw < (hot ? 2 * d : d)) return fail(GNF_ERR_INVALID, "gnf_dag_bias_table: bad arguments");
-  GNF_LAUNCH(dag_bias_table_kernel, ew_blocks((size_t)(hot ? d : 1) * N), 256, 0, (cudaStream_t)stream, W1, ldw, b1, T, d, N, hot);
+  GNF_LAUNCH(dag_bias_table_kernel, ew_blocks((size_t)(hot ? d : 1) * N), 256, 0, (cudaStream_t)stream, W1, ldw, b1, T, N, d, N, hot);
   return check_launch("gnf_dag_bias_table");
+}
+int gnf_dag_bias_table_ld(const float* W1, int ldw, const float* b1, float* T, int ldt, int d, int N, int hot, gnf_stream_t stream) {
+  if (!W1 || !T || d <= 0 || N <= 0 || ldt < N || ldw < (hot ? 2 * d : d)) return fail(GNF_ERR_INVALID, "gnf_dag_bias_table_ld: bad arguments");
+  GNF_LAUNCH(dag_bias_table_kernel, ew_blocks((size_t)(hot ? d : 1) * ldt), 256, 0, (cudaStream_t)stream, W1, ldw, b1, T, ldt, d, N, hot);
+  return check_launch("gnf_dag_bias_table_ld");
 }
 int gnf_dag_bias_table_bwd(const float* dT, float* dW1, int ldw, float* db1, int d, int N, int hot, gnf_stream_t stream) {
   if (!dT || (hot && !dW1) || d <= 0 || N <= 0) return fail(GNF_ERR_INVALID, "gnf_dag_bias_table_bwd: bad arguments");

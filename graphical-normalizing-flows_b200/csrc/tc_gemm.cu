@@ -947,12 +947,16 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
 static bool g2_eligible(const TcGemmParams& p) {
   if (p.passes != 3 || !p.B_lo || p.A_lo || p.a_src != TCG_SRC_K || p.epi == TCG_EPI_ATOMIC || p.bits_out || p.mask_bits) return false;
   if (p.epi == TCG_EPI_BIAS_ACT && p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0) return false;
-  if (p.epi == TCG_EPI_BIAS_ACT && p.bias && p.bias_period > 1 && ((p.N % 4) != 0 || (p.bias_ld % 4) != 0)) return false;
+  if (p.epi == TCG_EPI_BIAS_ACT && p.bias && p.bias_period > 1 && ((p.bias_ld % 4) != 0 || p.bias_ld < (p.N + 3) / 4 * 4)) return false;   // 16-byte pieces inside the (padded) table row
   if (p.epi == TCG_EPI_MASK && p.act && ((reinterpret_cast<uintptr_t>(p.act) & 15) != 0 || (p.ldact % 4) != 0)) return false;
   const int N4 = (p.N + 3) / 4 * 4;                        // 16-byte pieces: a row's last piece may reach into its padding columns
   if (p.ldc < N4 || (p.ldc % 4) != 0 || (reinterpret_cast<uintptr_t>(p.C) & 15) != 0) return false;
   if (p.epi == TCG_EPI_MASK && p.act && p.ldact < N4) return false;
-  return p.M >= 1024 && p.N >= 256 && p.K >= 128;          // small problems: the planned tiling of the engine above
+  if (p.M < 1024) return false;                            // small problems: the planned tiling of the engine above
+  if (p.N >= 256 && p.K >= 128) return true;
+  // layer 1 of a narrow DAG flow against the gate planes: a short reduction with a wide output (forward: two k-chunks per tile -- the
+  // engine above spends 24 k clocks per tile in its transposing epilogue) and a long reduction with ONE narrow output tile (input cotangent)
+  return (p.K >= 32 && p.K <= 64 && p.N >= 256) || (p.N >= 32 && p.N <= 64 && p.K >= 256);
 }
 
 // =====================================================================================================================
@@ -1377,6 +1381,22 @@ int gnf_linear_fwd_tc_ps(const float* X, int ldx, const float* W_hi, const float
   p.epi = TCG_EPI_BIAS_ACT; p.C = Y; p.ldc = ldy; p.bias = bias; p.bias_ld = N; p.bias_period = bias_period < 1 ? 1 : bias_period; p.relu = relu;
   if (int e = launch_tc_gemm(p, (cudaStream_t)stream)) return e;
   return check_launch("gnf_linear_fwd_tc_ps");
+#endif
+}
+
+int gnf_linear_fwd_tc_ps_tb(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw, const float* table, int ldt, int period, float* Y,
+                            int ldy, int M, int N, int K, int relu, gnf_stream_t stream) {
+#ifdef GNF_EMU
+  return gnf::fail(GNF_ERR_UNSUPPORTED, "tensor-core kernels have no host-simulator flavour");
+#else
+  if (!X || !W_hi || !W_lo || !Y || !table || M < 0 || N <= 0 || K <= 0 || ldx < K || ldw < K || ldy < N || ldt < N || period < 1) return fail(GNF_ERR_INVALID, "gnf_linear_fwd_tc_ps_tb: bad arguments");
+  TcGemmParams p = {};
+  p.A = X; p.lda = ldx; p.a_src = TCG_SRC_K;
+  p.B = W_hi; p.B_lo = W_lo; p.ldb = ldw; p.b_src = TCG_SRC_K;
+  p.M = M; p.N = N; p.K = K; p.passes = 3;
+  p.epi = TCG_EPI_BIAS_ACT; p.C = Y; p.ldc = ldy; p.bias = table; p.bias_ld = ldt; p.bias_period = period; p.relu = relu;
+  if (int e = launch_tc_gemm(p, (cudaStream_t)stream)) return e;
+  return check_launch("gnf_linear_fwd_tc_ps_tb");
 #endif
 }
 

@@ -771,9 +771,10 @@ def _narrow_l1_tc(M, N1, delta):
 
 
 DAG_L1_NARROW_TC = True
-# ... and the forward GEMM too (gnf_dag_gate_planes + gnf_linear_fwd_tc_ps with the periodic bias table)?  Measured slower at cfg4: 5 + 40 us
-# (the planned-tile engine at K = 64) against 46 us for the resident-gate kernel, step 1.049 vs 1.011 ms (profiles/r02ah_*): off.
-DAG_L1_NARROW_TC_FWD = False
+# ... and the forward GEMM too (gnf_dag_gate_planes + gnf_linear_fwd_tc_ps_tb with the periodic bias table).  On the planned-tile engine
+# (K = 64: two k-chunks per tile against its 24 k-clock transposing epilogue) this measured 5 + 40 us against 46 us for the resident-gate
+# kernel (profiles/r02ah_*); engine v2 takes the shape since (g2_eligible: short reduction, wide output)
+DAG_L1_NARROW_TC_FWD = True
 
 
 def _dag_l1_plane(M, N1, d, direction):
@@ -809,8 +810,17 @@ class DagMlpFn(torch.autograd.Function):
         dPdA = torch.empty_like(A)
         _call("gnf_dag_importance", ptr(A), d, gate.imp, gate.h_thresh, ptr(P), ptr(dPdA), st)
         N1 = weights[0].shape[0]
-        T = torch.empty(d if hot else 1, N1, device=x.device, dtype=x.dtype)
-        _call("gnf_dag_bias_table", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st)
+        # narrow flow, stochastic gate, training, tensor-core GEMM mode: gate planes by one kernel (one gate per thread, every SM) + layer 1 as
+        # a GEMM of engine v2 against the plane with the bias table in its epilogue (the table rows padded to 16-byte pieces)
+        tc_fwd = (DAG_L1_NARROW_TC_FWD and DAG_L1_KEEP_GATES and d <= 64 and gate.mode != L.GATE_TABLE and B > 0 and n > 1 and hot
+                  and any(ctx.needs_input_grad) and DAG_L1_NARROW_TC and _GEMM_MODE in ("auto", "tf32x3") and not L._SIMULATOR
+                  and B * d >= 2048 and N1 >= 256 and d >= 32)
+        if tc_fwd:
+            T = torch.empty(d, _pad4(N1), device=x.device, dtype=x.dtype)
+            _call("gnf_dag_bias_table_ld", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), T.stride(0), d, N1, 1, st)
+        else:
+            T = torch.empty(d if hot else 1, N1, device=x.device, dtype=x.dtype)
+            _call("gnf_dag_bias_table", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), d, N1, int(hot), st)
         g = gate.c_struct()
         # the weight splits of the hidden layers depend on nothing of this step: a side branch next to layer 1
         f_split = None
@@ -834,15 +844,13 @@ class DagMlpFn(torch.autograd.Function):
         elif (DAG_L1_KEEP_GATES and d <= 64 and gate.mode != L.GATE_TABLE and B > 0 and any(ctx.needs_input_grad)):
             # narrow flow, stochastic gate, training: the forward leaves e, de/dx, de/dP ([B d, 64] each) for the two backward kernels
             narrow = tuple(torch.empty(B * d, 64, device=x.device, dtype=x.dtype) for _ in range(3))
-            if DAG_L1_NARROW_TC_FWD and _narrow_l1_tc(B * d, N1, y) and n > 1:
-                # gates once (one per thread), then the forward GEMM on the tensor-core engine with the bias table as a periodic bias
+            if tc_fwd:
                 _TIMES_ALIAS["gnf_dag_gate_planes"] = "gnf_dag_l1_fwd"
                 _call("gnf_dag_gate_planes", ptr(x), ptr(P), C.byref(g), ptr(narrow[0]), ptr(narrow[1]), ptr(narrow[2]), B, d, st)
                 hi, lo = _split_weight(weights[0][:, :d])
-                _TIMES_ALIAS["gnf_linear_fwd_tc_ps"] = "gnf_dag_l1_fwd"
-                _call("gnf_linear_fwd_tc_ps", ptr(narrow[0]), 64, ptr(hi), ptr(lo), hi.stride(0), ptr(T), (d if hot else 1), ptr(y), y.stride(0),
+                _TIMES_ALIAS["gnf_linear_fwd_tc_ps_tb"] = "gnf_dag_l1_fwd"
+                _call("gnf_linear_fwd_tc_ps_tb", ptr(narrow[0]), 64, ptr(hi), ptr(lo), hi.stride(0), ptr(T), T.stride(0), d, ptr(y), y.stride(0),
                       B * d, N1, d, 1, st)
-                _TIMES_ALIAS["gnf_linear_fwd_tc_ps"] = "gnf_linear_fwd_tc"
                 _count(4)
             else:
                 _TIMES_ALIAS["gnf_dag_l1_fwd_save"] = "gnf_dag_l1_fwd"

@@ -148,6 +148,10 @@ int gnf_linear_wgrad_bias_tc(const float* dY, int lddy, const float* X, int ldx,
 int gnf_split_tf32(const float* W, int ldw, float* W_hi, float* W_lo, int ld, int N, int K, gnf_stream_t stream);
 int gnf_linear_fwd_tc_ps(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw, const float* bias, int bias_period,
                          float* Y, int ldy, int M, int N, int K, int relu, gnf_stream_t stream);
+/* ... with a periodic bias TABLE of explicit row stride (row m of Y takes row m % period of table [period, ldt]; ldt a multiple of 4
+ * floats lets the engine read it in 16-byte pieces whatever N is: DAG layer 1 with the one-hot half as a per-variable bias). */
+int gnf_linear_fwd_tc_ps_tb(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw, const float* table, int ldt,
+                            int period, float* Y, int ldy, int M, int N, int K, int relu, gnf_stream_t stream);
 int gnf_linear_dgrad_tc_ps(const float* dY, int lddy, const float* W_hi, const float* W_lo, int ldw, const float* act, int ldact,
                            float* dX, int lddx, int M, int N, int K, gnf_stream_t stream);
 /* Both operands pre-split (gnf_split_tf32 on the activations as well: one 10-us elementwise pass per 16 MB operand, reused by the
@@ -204,6 +208,8 @@ int gnf_dag_importance(const float* A, int d, int imp, float h_thresh, float* P,
 int gnf_dag_bias_table(const float* W1, int ldw, const float* b1, float* T, int d, int N, int hot,
                        gnf_stream_t stream);
 /* Gradient of the bias table: dW1[n, d+i] = dT[i,n] (hot), db1[n] = sum_i dT[i,n]. */
+/* The same table with an explicit row stride ldt >= N (padding columns zero). */
+int gnf_dag_bias_table_ld(const float* W1, int ldw, const float* b1, float* T, int ldt, int d, int N, int hot, gnf_stream_t stream);
 int gnf_dag_bias_table_bwd(const float* dT, float* dW1, int ldw, float* db1, int d, int N, int hot,
                            gnf_stream_t stream);
 /* Y[b*d+i, n] = act( sum_j x[b,j] G[b,i,j] W1[n,j] + T[i or 0, n] ). */

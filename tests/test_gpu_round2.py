@@ -525,6 +525,7 @@ def test_narrow_layer1_backward_on_tensor_cores_matches_resident_kernels():
     grads = {}
     from gnf_b200.conditioners import _stack_params
     gate = cond._gate_spec(x)            # one Philox (seed, offset) for the three variants
+    G.ops.DAG_L1_NARROW_TC_FWD = False   # same forward kernel in all three: this test is about the backward (the forward: next test)
     for tag, keep, tc, mode in (("regen", False, False, "auto"), ("saved", True, False, "auto"), ("tc", True, True, "auto")):   # same forward in all three
         G.ops.DAG_L1_KEEP_GATES, G.ops.DAG_L1_NARROW_TC = keep, tc
         G.ops.set_gemm_mode(mode)
@@ -537,6 +538,7 @@ def test_narrow_layer1_backward_on_tensor_cores_matches_resident_kernels():
         finally:
             G.ops.DAG_L1_KEEP_GATES = G.ops.DAG_L1_NARROW_TC = True
             G.ops.set_gemm_mode("ffma")
+    G.ops.DAG_L1_NARROW_TC_FWD = True
     for tag in ("saved", "tc"):
         for a, b in zip(grads["regen"], grads[tag]):
             assert float((a - b).norm() / b.norm()) < (2e-6 if tag == "saved" else 2e-5), tag
@@ -580,3 +582,26 @@ def test_branched_schedule_matches_the_in_line_schedule():
         assert abs(a - b) <= 2e-3 * abs(a), (la, lb)
     for a, b in zip(pa, pb):
         assert float((a - b).norm() / a.norm().clamp_min(1e-12)) < 2e-3
+
+
+def test_narrow_layer1_forward_on_tensor_cores_matches_resident_kernel():
+    """Layer 1 of a cfg4-shaped DAG conditioner, stochastic gate, training: gate-planes kernel + engine-v2 GEMM with the padded bias
+    table (gnf_dag_gate_planes, gnf_dag_bias_table_ld, gnf_linear_fwd_tc_ps_tb) against the resident-gate FFMA kernel, same Philox
+    stream: the conditioner output within 3xTF32 rounding."""
+    from gnf_b200.conditioners import _stack_params
+    torch.manual_seed(4)
+    cond = G.DAGConditioner(63, [630, 630], 30, gumble_T=.5, hot_encoding=True, l1=0.).cuda()
+    x = torch.randn(100, 63, device="cuda", requires_grad=True)
+    gate = cond._gate_spec(x)
+    out = {}
+    G.ops.set_gemm_mode("auto")
+    try:
+        for tag, on in (("ffma", False), ("tc", True)):
+            G.ops.DAG_L1_NARROW_TC_FWD = on
+            l0 = G.ops.launch_count()
+            out[tag] = G.ops.DagMlpFn.apply(x, cond.A, gate, True, *_stack_params(cond.embedding_net.net)).detach().clone()
+    finally:
+        G.ops.DAG_L1_NARROW_TC_FWD = True
+        G.ops.set_gemm_mode("ffma")
+    err = float((out["tc"] - out["ffma"]).abs().max() / out["ffma"].abs().max())
+    assert err < 2e-5, err
