@@ -1209,7 +1209,8 @@ __global__ void __launch_bounds__(kW2Threads, 1) tc_wgrad2_kernel(TcGemmParams p
 
 static bool w2_eligible(const TcGemmParams& p) {
   if (p.passes != 3 || p.epi != TCG_EPI_ATOMIC || p.a_src != TCG_SRC_MN || p.b_src != TCG_SRC_MN || p.A_lo || p.B_lo) return false;
-  return p.M >= 256 && p.N >= 256 && p.K >= 2048;          // small problems: the planned tiling of the first engine
+  if (p.M < 256 || p.K < 2048) return false;               // small problems: the planned tiling of the first engine
+  return p.N >= 256 || (p.N >= 32 && p.N <= 64);           // ... or ONE narrow tile column (layer 1 of a narrow DAG flow against the gate plane)
 }
 
 // splits of the reduction for the weight-gradient engine: work items = tiles x splits over the persistent grid, cost of a round =

@@ -70,9 +70,9 @@ def tc_kernel_name(op, M, N, K, passes=3, presplit=True):
     csrc/tc_gemm.cu for TMA-loadable operands): op 'fwd' / 'dgrad' (M rows, N out-features, K in-features) or 'wgrad'."""
     if passes == 3 and presplit:
         if op == "wgrad":
-            return "tc_wgrad2_kernel" if (N >= 256 and K >= 256 and M >= 2048) else "tc_gemm_kernel"
+            return "tc_wgrad2_kernel" if (N >= 256 and (K >= 256 or 32 <= K <= 64) and M >= 2048) else "tc_gemm_kernel"
         n, k = (N, K) if op == "fwd" else (K, N)
-        return "tc_gemm2_kernel" if (M >= 1024 and n >= 256 and k >= 128) else "tc_gemm_kernel"
+        return "tc_gemm2_kernel" if (M >= 1024 and ((n >= 256 and k >= 128) or (32 <= k <= 64 and n >= 256) or (32 <= n <= 64 and k >= 256))) else "tc_gemm_kernel"
     return "tc_gemm_kernel"
 
 
