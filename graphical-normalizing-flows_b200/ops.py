@@ -813,8 +813,8 @@ class DagMlpFn(torch.autograd.Function):
         # narrow flow, stochastic gate, training, tensor-core GEMM mode: gate planes by one kernel (one gate per thread, every SM) + layer 1 as
         # a GEMM of engine v2 against the plane with the bias table in its epilogue (the table rows padded to 16-byte pieces)
         tc_fwd = (DAG_L1_NARROW_TC_FWD and DAG_L1_KEEP_GATES and d <= 64 and gate.mode != L.GATE_TABLE and B > 0 and n > 1 and hot
-                  and any(ctx.needs_input_grad) and DAG_L1_NARROW_TC and _GEMM_MODE in ("auto", "tf32x3") and not L._SIMULATOR
-                  and B * d >= 2048 and N1 >= 256 and d >= 32)
+                  and DAG_L1_NARROW_TC and _GEMM_MODE in ("auto", "tf32x3", "auto-fast", "tf32") and not L._SIMULATOR
+                  and B * d >= 2048 and N1 >= 256 and d >= 32)        # evaluation (no gradient) takes it as well
         if tc_fwd:
             T = torch.empty(d, _pad4(N1), device=x.device, dtype=x.dtype)
             _call("gnf_dag_bias_table_ld", ptr(weights[0]), weights[0].stride(0), ptr(biases[0]), ptr(T), T.stride(0), d, N1, 1, st)
@@ -841,7 +841,7 @@ class DagMlpFn(torch.autograd.Function):
             W1e = weights[0][:, :d]                 # the masked-input half of layer 1; the one-hot half is the bias table T
             linear_fwd(E, W1e, T, relu=(n > 1), bias_period=(d if hot else 1), out=y, ldy=y.stride(0), K=d, ldx=E.stride(0))
             _count(2)
-        elif (DAG_L1_KEEP_GATES and d <= 64 and gate.mode != L.GATE_TABLE and B > 0 and any(ctx.needs_input_grad)):
+        elif (DAG_L1_KEEP_GATES and d <= 64 and gate.mode != L.GATE_TABLE and B > 0 and (any(ctx.needs_input_grad) or tc_fwd)):
             # narrow flow, stochastic gate, training: the forward leaves e, de/dx, de/dP ([B d, 64] each) for the two backward kernels
             narrow = tuple(torch.empty(B * d, 64, device=x.device, dtype=x.dtype) for _ in range(3))
             if tc_fwd:
@@ -875,7 +875,7 @@ class DagMlpFn(torch.autograd.Function):
         ctx.act_splits = splits if any(ctx.needs_input_grad) else None
         ctx.E, ctx.W1e = (E, W1e) if any(ctx.needs_input_grad) else (None, None)
         ctx.gate_planes = gate_planes
-        ctx.narrow = narrow
+        ctx.narrow = narrow if any(ctx.needs_input_grad) else None
         ctx.save_for_backward(x, A, P, dPdA, *weights, *acts)
         ctx.gate, ctx.hot, ctx.n = gate, hot, n
         if n == 1:
