@@ -112,14 +112,14 @@ class FCNormalizingFlow(NormalizingFlow):
         if x.dim() == 2 and x.shape[0] == 0:
             # empty batch: nothing to launch (the reference returns empty tensors too; keep the graph connected to x)
             return x * 1., x.sum(1)
-        jac_tot = 0.
+        jac_tot = None                       # the reference starts from 0. (NormalizingFlow.py:119): no `0. + tensor` launch for the first step
         n = len(self.steps)
         z = None
         for k, step in enumerate(self.steps):
             # the column reversal feeding the next step is an epilogue of this step's normalizer kernel
             z, jac, zrev = step.forward_fused(x, context, want_rev=(k < n - 1))
             x = zrev
-            jac_tot = jac_tot + jac
+            jac_tot = jac if jac_tot is None else jac_tot + jac
         return z, jac_tot
 
     def compute_ll(self, x, context=None):

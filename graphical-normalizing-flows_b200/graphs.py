@@ -109,6 +109,7 @@ class GraphedTrainStep:
     def _capture(self):
         model, optimizer, bucket, allreduce = self.model, self.opt, self.bucket, self.allreduce
         self.counters = _device_noise_counters(model, self.static_x.device)
+        self._one = torch.ones((), device=self.static_x.device, dtype=self.static_x.dtype)
 
         def body():
             for cnt in self.counters:
@@ -127,7 +128,7 @@ class GraphedTrainStep:
             else:
                 z, jac = model(self.static_x)
                 loss = model.loss(z, jac)
-            loss.backward()
+            loss.backward(gradient=self._one)          # a resident cotangent: no ones_like fill launch per step
             if allreduce:
                 bucket.finish_step()
             optimizer.step()
