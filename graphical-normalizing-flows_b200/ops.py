@@ -224,7 +224,9 @@ class NllLossFn(torch.autograd.Function):
         B, d = z.shape
         if constraint is not None:
             require(constraint, "constraint")
-        key = z.device                 # one persistent buffer per device (made by the eager warm-up steps before any graph capture)
+        # one persistent buffer per (device, stream): calls on one stream are ordered, calls on different streams must not share the
+        # partial sums (made by the eager warm-up steps before any graph capture)
+        key = (z.device, torch.cuda.current_stream().cuda_stream if z.is_cuda else 0)
         n = lib().gnf_nll_loss_work_floats(B)
         work = _NLL_WORK.get(key)
         if work is None or work.numel() < n or L._SIMULATOR:
