@@ -895,17 +895,24 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
       for (int c = 0; c < 64; c += 32) {
         if (n0 + c < p.N) {
           if (!mask && !table) {
+            // the block's 32 bias values: unconditional loads from clamped addresses, all in flight together (the warp's lanes read the
+            // same words: broadcast).  Guarded float4 loads were one exposed L2 round trip per guard -- 8 k clocks per tile in the output
+            // pass (scripts/gemm_trace.py 6300 630 64 fwd 3: fold end 3.7 k -> next fold start 11.8 k), hidden only when a tile is long
+            float bv[32];
+            if (p.bias) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int nb = n0 + c + e;
+                bv[e] = __ldg(p.bias + (nb < p.N ? nb : p.N - 1));       // columns >= N are never stored
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) bv[e] = 0.f;
+            }
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const int nb = n0 + c + 4 * j4;
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias && nb + 4 <= p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb));
-              else if (p.bias && nb < p.N) {               // ragged tail of the bias vector
-                b4.x = __ldg(p.bias + nb);
-                if (nb + 1 < p.N) b4.y = __ldg(p.bias + nb + 1);
-                if (nb + 2 < p.N) b4.z = __ldg(p.bias + nb + 2);
-              }
-              float v0 = run[c + 4 * j4] + b4.x, v1 = run[c + 4 * j4 + 1] + b4.y, v2 = run[c + 4 * j4 + 2] + b4.z, v3 = run[c + 4 * j4 + 3] + b4.w;
+              float v0 = run[c + 4 * j4] + bv[4 * j4], v1 = run[c + 4 * j4 + 1] + bv[4 * j4 + 1], v2 = run[c + 4 * j4 + 2] + bv[4 * j4 + 2],
+                    v3 = run[c + 4 * j4 + 3] + bv[4 * j4 + 3];
               if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
               *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (j4 ^ (lane & 7))) = make_float4(v0, v1, v2, v3);
             }
@@ -917,6 +924,15 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
           }
           __syncwarp();
           const int n = n0 + c + 4 * piece;
+          float4 tb[8];                                  // periodic bias table: the eight pieces of this thread, unconditional loads in flight together
+          if (table) {
+            const int ncl = n < p.N ? n : 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = m0 + 4 * i + sub, mc = m < p.M ? m : p.M - 1;
+              tb[i] = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)(mc % p.bias_period) * p.bias_ld + ncl));
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int R = 4 * i + sub, m = m0 + R;
@@ -926,7 +942,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
                 const uint32_t mb = mbits[c >> 5] >> (4 * i);
                 o.x = (mb & 1u) ? o.x : 0u; o.y = (mb & 2u) ? o.y : 0u; o.z = (mb & 4u) ? o.z : 0u; o.w = (mb & 8u) ? o.w : 0u;
               } else if (table) {                        // N % 4 == 0 here (g2_eligible): the piece is inside the table row
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)(m % p.bias_period) * p.bias_ld + n));
+                const float4 b4 = tb[i];
                 float v0 = __uint_as_float(o.x) + b4.x, v1 = __uint_as_float(o.y) + b4.y, v2 = __uint_as_float(o.z) + b4.z, v3 = __uint_as_float(o.w) + b4.w;
                 if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
                 o = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
