@@ -890,10 +890,12 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
         if (lane == 0) mbar_arrive(&tempty[acc]);
         if (tid == 0) trace_stamp(p.trace, 6, gcount);
       }
-      // ---- output pass
+      // ---- output pass (trace row 7, per tile and 32-column block: start, staged, stored)
+      int otr = (int)((w - blockIdx.x) / gridDim.x) * 6;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         if (n0 + c < p.N) {
+          if (tid == 0) trace_stamp(p.trace, 7, otr++);
           if (!mask && !table) {
             // the block's 32 bias values: unconditional loads from clamped addresses, all in flight together (the warp's lanes read the
             // same words: broadcast).  Guarded float4 loads were one exposed L2 round trip per guard -- 8 k clocks per tile in the output
@@ -923,6 +925,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
                   make_float4(run[c + 4 * j4], run[c + 4 * j4 + 1], run[c + 4 * j4 + 2], run[c + 4 * j4 + 3]);
           }
           __syncwarp();
+          if (tid == 0) trace_stamp(p.trace, 7, otr++);
           const int n = n0 + c + 4 * piece;
           float4 tb[8];                                  // periodic bias table: the eight pieces of this thread, unconditional loads in flight together
           if (table) {
@@ -951,6 +954,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) tc_gemm2_kernel(TcGemmParams p,
             }
           }
           __syncwarp();
+          if (tid == 0) trace_stamp(p.trace, 7, otr++);
         }
       }
     }

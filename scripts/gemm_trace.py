@@ -29,7 +29,7 @@ lib.gnf_tc_gemm_set_trace(None)
 t = buf.cpu().view(8, 256)
 t0 = int(t[t > 0].min())
 names = ["tma issued", "stager landed", "stager published", "mma chunk ready", "mma tile committed", "epi start", "epi end",
-         "epi tile1 chunk phases (start, acc+aux issued, computed, staged, stored, next acc ready) x chunks"]
+         "epi tile1 chunk phases (start, acc+aux issued, computed, staged, stored, next acc ready) x chunks | engine v2: output pass per tile and 32-column block (start, staged, stored)"]
 print(f"M={M} N={N} K={K} {op} passes={passes}: SM clocks relative to the first stamp (engine v2 rows: tma issued, A-writer landed, A-writer published, "
       f"mma chunk ready, mma group committed, fold start, fold end)")
 for r, n in enumerate(names):
