@@ -165,3 +165,37 @@ def test_skinny_split_k_forward_in_simulator(emu):
     """gnf_linear_fwd_splitk (the conditioner's 630 -> 30 output layer): partial tiles + fixed-order sum, against float64."""
     torch.set_num_threads(1)
     _splitk_case("cpu", 1024, 5, 130, False)
+
+
+def test_gate_planes_and_padded_bias_table_in_simulator(emu):
+    """gnf_dag_gate_planes (one gate per thread) against the planes the resident-gate forward leaves (gnf_dag_l1_fwd_save), same
+    replayed noise; gnf_dag_bias_table_ld (padded rows) against gnf_dag_bias_table."""
+    import ctypes as C
+    from gnf_b200.ops import _call, ptr, stream_ptr, GateSpec
+    import gnf_b200._lib as L
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(9)
+    B, d, N1 = 5, 7, 12
+    x, A = torch.randn(B, d, generator=g), torch.randn(d, d, generator=g)
+    W1, b1 = torch.randn(N1, 2 * d, generator=g), torch.randn(N1, generator=g)
+    noise = (torch.rand(B, d, d, generator=g).clamp(1e-3, 1 - 1e-3), torch.rand(B, d, d, generator=g).clamp(1e-3, 1 - 1e-3))
+    gate = GateSpec(L.GATE_GUMBEL, L.IMP_SOFT, 0., .5, noise=noise)
+    P, dPdA = torch.empty_like(A), torch.empty_like(A)
+    _call("gnf_dag_importance", ptr(A), d, gate.imp, gate.h_thresh, ptr(P), ptr(dPdA), stream_ptr())
+    gs = gate.c_struct()
+    planes = [torch.full((B * d, 64), float("nan")) for _ in range(3)]
+    _call("gnf_dag_gate_planes", ptr(x), ptr(P), C.byref(gs), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), B, d, stream_ptr())
+    T = torch.empty(d, N1)
+    _call("gnf_dag_bias_table", ptr(W1), W1.stride(0), ptr(b1), ptr(T), d, N1, 1, stream_ptr())
+    Tp = torch.full((d, 16), float("nan"))
+    _call("gnf_dag_bias_table_ld", ptr(W1), W1.stride(0), ptr(b1), ptr(Tp), 16, d, N1, 1, stream_ptr())
+    assert torch.equal(Tp[:, :N1], T) and bool((Tp[:, N1:] == 0).all())
+    ref = [torch.full((B * d, 64), float("nan")) for _ in range(3)]
+    y = torch.empty(B * d, N1)
+    _call("gnf_dag_l1_fwd_save", ptr(x), ptr(P), C.byref(gs), ptr(W1), W1.stride(0), ptr(T), d, ptr(y), N1, ptr(ref[0]), ptr(ref[1]), ptr(ref[2]),
+          B, d, N1, 1, stream_ptr())
+    for a, b in zip(planes, ref):
+        assert torch.equal(a, b)
+    # and layer 1 itself from the plane: relu(E W1[:, :d]^T + T[i])
+    want = torch.relu(planes[0][:, :d] @ W1[:, :d].t() + T.repeat(B, 1))
+    assert torch.allclose(y, want, rtol=1e-5, atol=1e-5)
